@@ -1,0 +1,236 @@
+/*
+ * plaid_b200.h -- C-ABI of libplaid_b200: the PLAID search hot path of the `next-plaid` crate
+ * (centroid scoring -> IVF candidates -> approximate score -> residual decompression -> MaxSim ->
+ * top-k) as hand-written sm_100a CUDA, behind the entry points a Rust `extern "C"` block in
+ * next-plaid/src/index.rs would bind (INTEGRATION.md shows that shim).
+ *
+ * The reference has no FFI for this path (search is hard-wired to the CPU, search.rs:85-90), so
+ * each export cites the Rust item it replaces.  Paths are relative to next-plaid/src/.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no C++/torch types; every function returns a pb_status (0 = ok);
+ *     pb_last_error() gives the thread-local message the shim maps to Error::Search(String)
+ *     (error.rs:10-66).
+ *   - there is NO CPU fallback: without a usable sm_100 device every entry point fails with
+ *     PB_ERR_CUDA (same contract as NEXT_PLAID_FORCE_GPU, lib.rs:71-84, codec.rs:275-288).
+ *   - index arrays are copied to the device at open; query / result pointers are never retained
+ *     past the call; a handle may be searched from many host threads at once (state.rs:24-47).
+ *   - numerics: every contraction uses one pinned fp32 order (DESIGN.md "Numerics"), the same one
+ *     oracle/plaid_oracle.c uses, so results are bit-identical to that restatement of the
+ *     reference and within 1e-5 of any other sgemm order.
+ */
+#ifndef PLAID_B200_H
+#define PLAID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define PB_API
+#else
+#define PB_API __attribute__((visibility("default")))
+#endif
+
+#define PB_VERSION_MAJOR 0
+#define PB_VERSION_MINOR 1
+
+typedef enum pb_status {
+    PB_OK = 0,
+    PB_ERR_INVALID = 1,     /* bad argument (shape, nbits not dividing 8 -- codec.rs:161-166, ...) */
+    PB_ERR_CUDA = 2,        /* no device / CUDA runtime error (no CPU fallback) */
+    PB_ERR_IO = 3,          /* index directory unreadable or malformed -- Error::IndexLoad */
+    PB_ERR_UNSUPPORTED = 4, /* valid for the reference, outside this build's limits (stated) */
+    PB_ERR_NOMEM = 5,
+    PB_ERR_COMM = 6         /* NCCL */
+} pb_status;
+
+typedef struct pb_index pb_index; /* opaque; replaces next_plaid::MmapIndex (index.rs:995-1016) */
+
+enum { PB_MEM_HOST = 0, PB_MEM_DEVICE = 1 };
+
+/*
+ * The arrays MmapIndex holds after load (index.rs:1026-1139), in the reference's own dtypes.
+ * memory_space = PB_MEM_DEVICE means every pointer is a device pointer on `device` (used by the
+ * synthetic benchmark to build 10^9-token indices without a host copy); arrays are still copied.
+ */
+typedef struct pb_index_desc {
+    int32_t dim;                   /* embedding_dim (index.rs:1310); multiple of 4, <= 1024 */
+    int32_t nbits;                 /* 1, 2, 4 or 8 (codec.rs:161) */
+    int64_t num_centroids;         /* K = centroids.nrows() = ivf_lengths.len() */
+    int64_t num_documents;         /* D */
+    int64_t num_embeddings;        /* N = sum(doc_lengths); padding rows of merged_*.npy excluded */
+    const float *centroids;        /* [K][dim]        centroids.npy  <f4 */
+    const float *bucket_weights;   /* [2^nbits]       bucket_weights.npy <f4 */
+    const int64_t *codes;          /* [N]             merged_codes.npy <i8 */
+    const uint8_t *residuals;      /* [N][dim*nbits/8] merged_residuals.npy u1 */
+    const int64_t *doc_lengths;    /* [D]             doclens.*.json */
+    const int64_t *ivf;            /* [sum ivf_lengths] ivf.npy <i8, per-centroid ascending unique doc ids */
+    const int32_t *ivf_lengths;    /* [K]             ivf_lengths.npy <i4 */
+    int32_t device;                /* CUDA ordinal */
+    int32_t memory_space;          /* PB_MEM_HOST | PB_MEM_DEVICE */
+    int64_t doc_id_base;           /* global id of local doc 0 (doc-sharded deployment), else 0 */
+} pb_index_desc;
+
+/* search.rs:27-69 SearchParameters.  batch_size is accepted and ignored, as in the reference
+ * (it is never read there). */
+typedef struct pb_search_params {
+    int64_t batch_size;
+    int64_t n_full_scores;
+    int64_t top_k;
+    int64_t n_ivf_probe;
+    int64_t centroid_batch_size;      /* 0 or >= K selects the dense variant (search.rs:337) */
+    int32_t has_centroid_score_threshold; /* Option<f32>: 0 = None */
+    float centroid_score_threshold;
+} pb_search_params;
+
+/* SearchParameters::default(), search.rs:58-69 */
+PB_API void pb_search_params_default(pb_search_params *p);
+
+/* ---- index lifetime ------------------------------------------------------------------- */
+
+/* MmapIndex::load(path) (index.rs:1026): reads the reference's index directory as-is
+ * (metadata.json, centroids.npy, bucket_weights.npy, ivf.npy, ivf_lengths.npy, doclens.N.json,
+ * N.codes.npy, N.residuals.npy) and uploads it to `device`. */
+PB_API pb_status pb_index_load(const char *index_dir, int32_t device, pb_index **out);
+
+/* Same, from arrays already in memory (what a Rust MmapIndex owns after its own load). */
+PB_API pb_status pb_index_open(const pb_index_desc *desc, pb_index **out);
+
+/* Drop for the handle. */
+PB_API void pb_index_close(pb_index *ix);
+
+/* accessors, index.rs:1290-1312 */
+PB_API int64_t pb_index_num_documents(const pb_index *ix);
+PB_API int64_t pb_index_num_embeddings(const pb_index *ix);
+PB_API int64_t pb_index_num_partitions(const pb_index *ix);
+PB_API double pb_index_avg_doclen(const pb_index *ix);
+PB_API int32_t pb_index_embedding_dim(const pb_index *ix);
+PB_API int32_t pb_index_nbits(const pb_index *ix);
+PB_API int32_t pb_index_device(const pb_index *ix);
+
+/* ---- search ------------------------------------------------------------------------------ */
+
+/*
+ * MmapIndex::search_batch (index.rs:1279 -> search::search_many_mmap, search.rs:643) and, with
+ * n_queries = 1, MmapIndex::search (index.rs:1258 -> search_one_mmap, search.rs:327).
+ *
+ *   queries        [q_tok_offsets[n_queries]][dim] f32 row-major: the Array2<f32> of each query
+ *                  concatenated (host memory)
+ *   q_tok_offsets  [n_queries+1] row offsets of each query in `queries`
+ *   subset         Option<&[i64]>: NULL = None; otherwise n_subset doc ids (may be empty)
+ *   out_ids        [n_queries][top_k] passage_ids (i64), descending score      (QueryResult,
+ *   out_scores     [n_queries][top_k] scores (f32)                              search.rs:72-80)
+ *   out_counts     [n_queries] number of valid entries of each row (<= top_k)
+ *
+ * query_id of result i is i (search.rs:661).  A query that cannot be searched yields count 0, as
+ * the reference's parallel mode does (search.rs:656-660).
+ */
+PB_API pb_status pb_search_batch(pb_index *ix, const float *queries, const int64_t *q_tok_offsets,
+                                 int64_t n_queries, const pb_search_params *params,
+                                 const int64_t *subset, int64_t n_subset, int64_t *out_ids,
+                                 float *out_scores, int32_t *out_counts);
+
+/* Stage outputs of the last pb_search_batch_traced call, for stage-level parity tests.
+ * All arrays are caller-allocated host memory; any may be NULL. */
+typedef struct pb_trace {
+    int64_t *cells;        /* [n_queries][cells_cap] ascending centroid ids that survive a3 */
+    int32_t *n_cells;      /* [n_queries] */
+    int64_t cells_cap;
+    int64_t *candidates;   /* [n_queries][cand_cap] ascending doc ids (a4) */
+    float *approx;         /* [n_queries][cand_cap] approximate score of each candidate (a5) */
+    int32_t *n_candidates; /* [n_queries] */
+    int64_t cand_cap;
+    int64_t *kept;         /* [n_queries][kept_cap] docs sent to exact scoring, approx-rank order (a6) */
+    float *kept_exact;     /* [n_queries][kept_cap] their exact MaxSim (a7+a8) */
+    int32_t *n_kept;       /* [n_queries] */
+    int64_t kept_cap;
+} pb_trace;
+
+PB_API pb_status pb_search_batch_traced(pb_index *ix, const float *queries,
+                                        const int64_t *q_tok_offsets, int64_t n_queries,
+                                        const pb_search_params *params, const int64_t *subset,
+                                        int64_t n_subset, int64_t *out_ids, float *out_scores,
+                                        int32_t *out_counts, pb_trace *trace);
+
+/* ---- stage entry points (each is one kernel of the path; used by tests, bench and ncu) ---- */
+
+/* Stage 1, S = Q * C^T (search.rs:345).  out: [n_query_tokens][K] row-major f32, host. */
+PB_API pb_status pb_centroid_scores(pb_index *ix, const float *query_tokens, int64_t n_query_tokens,
+                                    float *out_scores);
+
+/* MmapIndex::decompress_documents (index.rs:1197-1245): embeddings of the listed docs,
+ * concatenated.  out_embeddings [sum lengths][dim] f32 host, out_lengths [n_docs]; an id
+ * >= num_documents contributes length 0 as in the reference.  Call with out_embeddings = NULL to
+ * get the lengths first. */
+PB_API pb_status pb_decompress_documents(pb_index *ix, const int64_t *doc_ids, int64_t n_docs,
+                                         float *out_embeddings, int64_t *out_lengths);
+
+/* maxsim::maxsim_score (maxsim.rs:270) for n_docs documents given as decompressed f32 tokens
+ * (doc i = rows [doc_tok_offsets[i], doc_tok_offsets[i+1]) of doc_tokens), one query.
+ * Host pointers; `device` selects the GPU. */
+PB_API pb_status pb_maxsim_scores(int32_t device, const float *query, int32_t n_query_tokens,
+                                  int32_t dim, const float *doc_tokens,
+                                  const int64_t *doc_tok_offsets, int64_t n_docs, float *out_scores);
+
+/* Exact MaxSim of each query against EVERY document of the index through the fused
+ * decompress+MaxSim kernel (recall ground truth).  out_scores [n_queries][num_documents] host. */
+PB_API pb_status pb_exhaustive_scores(pb_index *ix, const float *queries,
+                                      const int64_t *q_tok_offsets, int64_t n_queries,
+                                      float *out_scores);
+
+/* ---- timing hooks for bench.py (device-side, CUDA events on the library's own stream) ----- */
+
+/* Stage ids for pb_last_stage_ms */
+enum {
+    PB_STAGE_H2D = 0,
+    PB_STAGE_CENTROID_SCORES = 1, /* a2 */
+    PB_STAGE_PROBE = 2,           /* a3 */
+    PB_STAGE_CANDIDATES = 3,      /* a4 */
+    PB_STAGE_APPROX = 4,          /* a5 */
+    PB_STAGE_CUT = 5,             /* a6 */
+    PB_STAGE_EXACT = 6,           /* a7+a8 */
+    PB_STAGE_TOPK = 7,            /* a9 */
+    PB_STAGE_D2H = 8,
+    PB_STAGE_COUNT = 9
+};
+
+/* Enable per-stage CUDA-event timing for subsequent searches on this handle (adds event
+ * records only, no synchronisation inside the path). */
+PB_API void pb_set_profiling(pb_index *ix, int32_t enabled);
+/* Milliseconds and kernel launches per stage, summed over the sub-batches of the calling thread's
+ * last pb_search_batch.  out_ms / out_launches: [PB_STAGE_COUNT]. */
+PB_API pb_status pb_last_stage_stats(pb_index *ix, float *out_ms, int32_t *out_launches);
+/* Work counters of the calling thread's last search: candidates scored, doc tokens gathered by the
+ * approximate stage, docs / tokens exact-scored. */
+typedef struct pb_work_counters {
+    int64_t n_queries;
+    int64_t n_query_tokens;
+    int64_t n_cells;
+    int64_t n_candidates;
+    int64_t n_candidate_tokens;
+    int64_t n_exact_docs;
+    int64_t n_exact_tokens;
+} pb_work_counters;
+PB_API pb_status pb_last_work_counters(pb_index *ix, pb_work_counters *out);
+
+/* Search with queries already resident on the device and results left on the device:
+ * the kernel-only timing leg of bench.py ("value"); same semantics as pb_search_batch. */
+PB_API pb_status pb_search_batch_device(pb_index *ix, const float *d_queries,
+                                        const int64_t *q_tok_offsets_host, int64_t n_queries,
+                                        const pb_search_params *params, int64_t *d_out_ids,
+                                        float *d_out_scores, int32_t *d_out_counts);
+
+/* ---- misc ----------------------------------------------------------------------------- */
+
+PB_API const char *pb_last_error(void);       /* thread-local, never NULL */
+PB_API const char *pb_version(void);
+PB_API int32_t pb_device_count(void);         /* 0 when no usable device: callers must fail */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLAID_B200_H */

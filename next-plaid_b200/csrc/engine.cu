@@ -1,0 +1,1001 @@
+// engine.cu -- host side of libplaid_b200: the device-resident index (what MmapIndex holds after
+// load, index.rs:995-1016), the search pipeline that replaces search::search_many_mmap
+// (search.rs:643) and the C-ABI of include/plaid_b200.h.  No CPU fallback anywhere: every entry
+// point needs an sm_100 device.
+#include "engine_internal.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+pb_status pb_fail(pb_status s, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return s;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return pb_fail(PB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                           __FILE__, __LINE__);                                                    \
+    } while (0)
+#define CKS(expr)                                                                                  \
+    do {                                                                                           \
+        pb_status s_ = (expr);                                                                     \
+        if (s_ != PB_OK) return s_;                                                                \
+    } while (0)
+
+extern "C" const char *pb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *pb_version(void) { return "plaid_b200 0.1 (sm_100a)"; }
+
+extern "C" int32_t pb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static pb_status check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return pb_fail(PB_ERR_CUDA, "no CUDA device available (%s); libplaid_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return pb_fail(PB_ERR_INVALID, "device %d out of range (have %d)", device, n);
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10)
+        return pb_fail(PB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major,
+                       p.minor);
+    CK(cudaSetDevice(device));
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// device buffers
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool zero_on_grow = false;
+    pb_status ensure(size_t bytes) {
+        if (bytes <= cap) return PB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return pb_fail(PB_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        if (zero_on_grow) {
+            e = cudaMemset(p, 0, want);
+            if (e != cudaSuccess) return pb_fail(PB_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+        }
+        return PB_OK;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+struct HostBuf {  // pinned
+    void *p = nullptr;
+    size_t cap = 0;
+    pb_status ensure(size_t bytes) {
+        if (bytes <= cap) return PB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes + 256);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return pb_fail(PB_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        }
+        cap = bytes + 256;
+        return PB_OK;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+    ~HostBuf() {
+        if (p) cudaFreeHost(p);
+    }
+};
+
+// per-call scratch; a pool of these makes pb_search_batch re-entrant on one handle
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
+    DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
+        exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list;
+    HostBuf hq, hres, hcounts;
+    pb_status init() {
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (auto &e : ev) CK(cudaEventCreate(&e));
+        bitmap.zero_on_grow = true;
+        maxkey.zero_on_grow = true;
+        subset_bits.zero_on_grow = true;
+        elig.zero_on_grow = true;
+        return PB_OK;
+    }
+    ~Workspace() {
+        for (auto &e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+struct Stats {
+    float ms[PB_STAGE_COUNT] = {};
+    int launches[PB_STAGE_COUNT] = {};
+    pb_work_counters work = {};
+};
+static thread_local Stats g_stats;
+
+struct pb_index {
+    int device = 0;
+    int dim = 0, nbits = 0, packed = 0;
+    long long K = 0, D = 0, N = 0, ivf_len = 0, doc_id_base = 0;
+    int max_doclen = 0;
+    int sm_count = 148;
+    DevBuf centroids, w_rev, codes, residuals, doc_off, ivf, ivf_off;
+    bool profiling = false;
+    size_t st_budget = (size_t)4 << 30;
+    std::mutex mu;
+    std::vector<std::unique_ptr<Workspace>> pool;
+
+    pb_status acquire(std::unique_ptr<Workspace> &ws) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (!pool.empty()) {
+                ws = std::move(pool.back());
+                pool.pop_back();
+                return PB_OK;
+            }
+        }
+        ws.reset(new Workspace());
+        return ws->init();
+    }
+    void release(std::unique_ptr<Workspace> &ws) {
+        std::lock_guard<std::mutex> g(mu);
+        pool.push_back(std::move(ws));
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// DIM dispatch
+// ------------------------------------------------------------------------------------------
+#define PB_DIM_SWITCH(dim, ...)                                                                    \
+    switch (dim) {                                                                                 \
+        case 32: { constexpr int DIM = 32; __VA_ARGS__; } break;                                   \
+        case 64: { constexpr int DIM = 64; __VA_ARGS__; } break;                                   \
+        case 96: { constexpr int DIM = 96; __VA_ARGS__; } break;                                   \
+        case 128: { constexpr int DIM = 128; __VA_ARGS__; } break;                                 \
+        case 256: { constexpr int DIM = 256; __VA_ARGS__; } break;                                 \
+        default: return pb_fail(PB_ERR_UNSUPPORTED, "embedding_dim %d not built (32/64/96/128/256)", dim); \
+    }
+
+static bool dim_supported(int d) { return d == 32 || d == 64 || d == 96 || d == 128 || d == 256; }
+
+static size_t smem_scores(int dim) { return (size_t)(PB_TOK_TILE + PB_Q_TILE) * (dim + 4) * sizeof(float); }
+static size_t smem_exact(int dim) {
+    return (size_t)(PB_TOK_TILE + PB_Q_TILE) * (dim + 4) * sizeof(float) + PB_Q_TILE * 129 * sizeof(float) +
+           PB_TOK_TILE * sizeof(int) + 256 * sizeof(float);
+}
+
+template <class Kern> static pb_status set_smem(Kern k, size_t bytes) {
+    if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// index open / close
+// ------------------------------------------------------------------------------------------
+static unsigned bitrev_n(unsigned v, int nbits) {
+    unsigned r = 0;
+    for (int k = 0; k < nbits; ++k)
+        if (v & (1u << k)) r |= 1u << (nbits - 1 - k);
+    return r;
+}
+
+template <class T>
+static pb_status fetch_host(std::vector<T> &dst, const T *src, size_t n, int space) {
+    dst.resize(n);
+    if (n == 0) return PB_OK;
+    if (space == PB_MEM_DEVICE) CK(cudaMemcpy(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost));
+    else memcpy(dst.data(), src, n * sizeof(T));
+    return PB_OK;
+}
+
+static pb_status upload(DevBuf &dst, const void *src, size_t bytes, int space) {
+    CKS(dst.ensure(std::max<size_t>(bytes, 16)));
+    if (bytes == 0) return PB_OK;
+    CK(cudaMemcpy(dst.p, src, bytes, space == PB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return PB_OK;
+}
+
+// i64 -> u32 with a range check, streamed through a bounded staging buffer, into dst[dst_off..]
+static pb_status upload_narrow(DevBuf &dst, long long dst_off, const int64_t *src, long long n, long long limit,
+                               int space, const char *what) {
+    if (n == 0) return PB_OK;
+    DevBuf bad;
+    CKS(bad.ensure(16));
+    CK(cudaMemset(bad.p, 0, 4));
+    const long long chunk = 1ll << 26;  // 64M elements = 512 MiB of i64
+    DevBuf stage;
+    if (space == PB_MEM_HOST) CKS(stage.ensure((size_t)std::min(n, chunk) * 8));
+    for (long long o = 0; o < n; o += chunk) {
+        long long m = std::min(chunk, n - o);
+        const long long *in = reinterpret_cast<const long long *>(src) + o;
+        if (space == PB_MEM_HOST) {
+            CK(cudaMemcpy(stage.p, in, (size_t)m * 8, cudaMemcpyHostToDevice));
+            in = stage.as<long long>();
+        }
+        k_narrow_i64_u32<<<1184, 256>>>(in, dst.as<uint32_t>() + dst_off + o, m, limit, bad.as<int>());
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+    }
+    int hbad = 0;
+    CK(cudaMemcpy(&hbad, bad.p, 4, cudaMemcpyDeviceToHost));
+    if (hbad) return pb_fail(PB_ERR_INVALID, "%s contains a value outside [0, %lld)", what, limit);
+    return PB_OK;
+}
+
+// codes + packed residuals of tokens [tok_off, tok_off+n) (one chunk file pair, or everything)
+pb_status pb_index_upload_tokens(pb_index *ix, long long tok_off, const int64_t *codes, const uint8_t *residuals,
+                                 long long n, int space) {
+    if (n == 0) return PB_OK;
+    if (tok_off < 0 || tok_off + n > ix->N) return pb_fail(PB_ERR_INVALID, "token range [%lld,+%lld) outside the index", tok_off, n);
+    CK(cudaSetDevice(ix->device));
+    CK(cudaMemcpy(ix->residuals.as<uint8_t>() + (size_t)tok_off * ix->packed, residuals, (size_t)n * ix->packed,
+                  space == PB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return upload_narrow(ix->codes, tok_off, codes, n, ix->K, space, "codes");
+}
+
+// Everything except the per-token arrays (d->codes / d->residuals may be NULL here).
+pb_status pb_index_open_begin(const pb_index_desc *d, pb_index **out) {
+    if (!d || !out) return pb_fail(PB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (d->nbits <= 0 || 8 % d->nbits != 0)  // codec.rs:161-166
+        return pb_fail(PB_ERR_INVALID, "nbits must be a divisor of 8, got %d", d->nbits);
+    if (d->dim <= 0 || d->dim % 4 != 0) return pb_fail(PB_ERR_INVALID, "embedding_dim %d must be a positive multiple of 4", d->dim);
+    if (!dim_supported(d->dim)) return pb_fail(PB_ERR_UNSUPPORTED, "embedding_dim %d not built (32/64/96/128/256)", d->dim);
+    if (d->num_centroids <= 0 || d->num_documents < 0 || d->num_embeddings < 0)
+        return pb_fail(PB_ERR_INVALID, "bad shapes K=%lld D=%lld N=%lld", (long long)d->num_centroids,
+                       (long long)d->num_documents, (long long)d->num_embeddings);
+    if (d->num_centroids >= (1ll << 32) - 1 || d->num_documents >= (1ll << 32) - 1)
+        return pb_fail(PB_ERR_UNSUPPORTED, "K and D must be below 2^32-1 per shard");
+    if (!d->centroids || !d->bucket_weights || (!d->doc_lengths && d->num_documents) || !d->ivf_lengths)
+        return pb_fail(PB_ERR_INVALID, "null index array");
+    CKS(check_device(d->device));
+    std::unique_ptr<pb_index> ix(new pb_index());
+    ix->device = d->device;
+    ix->dim = d->dim;
+    ix->nbits = d->nbits;
+    ix->packed = d->dim * d->nbits / 8;
+    ix->K = d->num_centroids;
+    ix->D = d->num_documents;
+    ix->N = d->num_embeddings;
+    ix->doc_id_base = d->doc_id_base;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, d->device));
+    ix->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("PB_ST_BUDGET_MB")) {
+        long v = atol(e);
+        if (v > 0) ix->st_budget = (size_t)v << 20;
+    }
+    const int sp = d->memory_space;
+    // doc offsets (index.rs:1107-1110)
+    std::vector<int64_t> dl;
+    CKS(fetch_host(dl, d->doc_lengths, (size_t)ix->D, sp));
+    std::vector<long long> doff((size_t)ix->D + 1, 0);
+    int maxlen = 0;
+    for (long long i = 0; i < ix->D; ++i) {
+        if (dl[i] < 0 || dl[i] > (1 << 30)) return pb_fail(PB_ERR_INVALID, "doc_lengths[%lld] = %lld", i, (long long)dl[i]);
+        doff[i + 1] = doff[i] + dl[i];
+        maxlen = std::max<int>(maxlen, (int)dl[i]);
+    }
+    if (doff[ix->D] != ix->N)
+        return pb_fail(PB_ERR_INVALID, "sum(doc_lengths)=%lld != num_embeddings=%lld", doff[ix->D], ix->N);
+    ix->max_doclen = maxlen;
+    CKS(upload(ix->doc_off, doff.data(), doff.size() * 8, PB_MEM_HOST));
+    // ivf offsets (index.rs:1089-1094)
+    std::vector<int32_t> il;
+    CKS(fetch_host(il, d->ivf_lengths, (size_t)ix->K, sp));
+    std::vector<long long> ioff((size_t)ix->K + 1, 0);
+    for (long long i = 0; i < ix->K; ++i) {
+        if (il[i] < 0) return pb_fail(PB_ERR_INVALID, "ivf_lengths[%lld] < 0", i);
+        ioff[i + 1] = ioff[i] + il[i];
+    }
+    ix->ivf_len = ioff[ix->K];
+    if (ix->ivf_len && !d->ivf) return pb_fail(PB_ERR_INVALID, "null ivf");
+    CKS(upload(ix->ivf_off, ioff.data(), ioff.size() * 8, PB_MEM_HOST));
+    // bucket weights with the packer's bit reversal folded in (codec.rs:168-214, :389-395)
+    std::vector<float> w;
+    CKS(fetch_host(w, d->bucket_weights, (size_t)1 << ix->nbits, sp));
+    std::vector<float> wrev(256, 0.f);
+    for (unsigned f = 0; f < (1u << ix->nbits); ++f) wrev[f] = w[bitrev_n(f, ix->nbits)];
+    CKS(upload(ix->w_rev, wrev.data(), 256 * sizeof(float), PB_MEM_HOST));
+    CKS(upload(ix->centroids, d->centroids, (size_t)ix->K * ix->dim * sizeof(float), sp));
+    CKS(ix->residuals.ensure(std::max<size_t>((size_t)ix->N * ix->packed, 16)));
+    CKS(ix->codes.ensure(std::max<size_t>((size_t)ix->N * 4, 16)));
+    CKS(ix->ivf.ensure(std::max<size_t>((size_t)ix->ivf_len * 4, 16)));
+    CKS(upload_narrow(ix->ivf, 0, d->ivf, ix->ivf_len, std::max<long long>(ix->D, 1), sp, "ivf"));
+    *out = ix.release();
+    return PB_OK;
+}
+
+extern "C" pb_status pb_index_open(const pb_index_desc *d, pb_index **out) {
+    if (!d || !out) return pb_fail(PB_ERR_INVALID, "null argument");
+    if (d->num_embeddings > 0 && (!d->codes || !d->residuals)) return pb_fail(PB_ERR_INVALID, "null index array");
+    pb_index *ix = nullptr;
+    CKS(pb_index_open_begin(d, &ix));
+    pb_status s = pb_index_upload_tokens(ix, 0, d->codes, d->residuals, d->num_embeddings, d->memory_space);
+    if (s != PB_OK) {
+        pb_index_close(ix);
+        return s;
+    }
+    *out = ix;
+    return PB_OK;
+}
+
+extern "C" void pb_index_close(pb_index *ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    cudaDeviceSynchronize();
+    delete ix;
+}
+
+extern "C" int64_t pb_index_num_documents(const pb_index *ix) { return ix ? ix->D : 0; }
+extern "C" int64_t pb_index_num_embeddings(const pb_index *ix) { return ix ? ix->N : 0; }
+extern "C" int64_t pb_index_num_partitions(const pb_index *ix) { return ix ? ix->K : 0; }
+extern "C" double pb_index_avg_doclen(const pb_index *ix) { return (ix && ix->D) ? (double)ix->N / (double)ix->D : 0.0; }
+extern "C" int32_t pb_index_embedding_dim(const pb_index *ix) { return ix ? ix->dim : 0; }
+extern "C" int32_t pb_index_nbits(const pb_index *ix) { return ix ? ix->nbits : 0; }
+extern "C" int32_t pb_index_device(const pb_index *ix) { return ix ? ix->device : -1; }
+
+extern "C" void pb_search_params_default(pb_search_params *p) {  // search.rs:58-69
+    if (!p) return;
+    p->batch_size = 2000;
+    p->n_full_scores = 4096;
+    p->top_k = 10;
+    p->n_ivf_probe = 8;
+    p->centroid_batch_size = 100000;
+    p->has_centroid_score_threshold = 1;
+    p->centroid_score_threshold = 0.4f;
+}
+
+extern "C" void pb_set_profiling(pb_index *ix, int32_t enabled) {
+    if (ix) ix->profiling = enabled != 0;
+}
+extern "C" pb_status pb_last_stage_stats(pb_index *, float *out_ms, int32_t *out_launches) {
+    for (int i = 0; i < PB_STAGE_COUNT; ++i) {
+        if (out_ms) out_ms[i] = g_stats.ms[i];
+        if (out_launches) out_launches[i] = g_stats.launches[i];
+    }
+    return PB_OK;
+}
+extern "C" pb_status pb_last_work_counters(pb_index *, pb_work_counters *out) {
+    if (!out) return pb_fail(PB_ERR_INVALID, "null argument");
+    *out = g_stats.work;
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel launch helpers shared by the search pipeline and the stage entry points
+// ------------------------------------------------------------------------------------------
+static pb_status launch_centroid_scores(pb_index *ix, Workspace &ws, int B, int QS, int *launches) {
+    const int tiles = (int)((ix->K + PB_TOK_TILE - 1) / PB_TOK_TILE);
+    // enough CTAs to fill the machine twice over; each CTA keeps its centroid tile in smem and walks queries
+    int groups = std::max(1, std::min(B, (4 * ix->sm_count + tiles - 1) / tiles));
+    PB_DIM_SWITCH(ix->dim, {
+        auto kern = k_centroid_scores<DIM>;
+        CKS(set_smem(kern, smem_scores(DIM)));
+        kern<<<dim3(tiles, groups), 128, smem_scores(DIM), ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), B, QS,
+                                                                        ix->centroids.as<float>(), ix->K,
+                                                                        ws.ST.as<float>());
+    });
+    CK(cudaGetLastError());
+    if (launches) ++*launches;
+    return PB_OK;
+}
+
+static pb_status launch_exact(pb_index *ix, Workspace &ws, int B, int QS, int Mcap, int kept_shared,
+                              long long max_tokens, int *launches) {
+    long long chunks = (max_tokens + PB_TOK_TILE - 1) / PB_TOK_TILE;
+    int gx = (int)std::max<long long>(1, std::min<long long>(chunks, (long long)ix->sm_count * 16));
+    PB_DIM_SWITCH(ix->dim, {
+        auto kern = k_exact<DIM, false>;
+        CKS(set_smem(kern, smem_exact(DIM)));
+        kern<<<dim3(gx, B), 128, smem_exact(DIM), ws.stream>>>(
+            ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits,
+            ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->doc_off.as<long long>(), nullptr,
+            ws.kept.as<uint32_t>(), ws.nkept.as<int>(), ws.tokp.as<long long>(), Mcap, kept_shared,
+            ws.maxkey.as<uint32_t>());
+    });
+    CK(cudaGetLastError());
+    if (launches) ++*launches;
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the search pipeline
+// ------------------------------------------------------------------------------------------
+struct SearchIO {
+    const float *queries;  // host or device
+    bool queries_on_device;
+    const int64_t *q_off;  // host
+    int64_t n_queries;
+    const int64_t *subset;  // host
+    int64_t n_subset;
+    bool has_subset;
+    int64_t *out_ids;  // host or device
+    float *out_scores;
+    int32_t *out_counts;
+    bool out_on_device;
+    pb_trace *trace;
+};
+
+static pb_status search_impl(pb_index *ix, const pb_search_params *p, const SearchIO &io) {
+    if (!ix || !p) return pb_fail(PB_ERR_INVALID, "null argument");
+    if (io.n_queries < 0) return pb_fail(PB_ERR_INVALID, "n_queries < 0");
+    if (io.n_queries > 0 && (!io.queries || !io.q_off)) return pb_fail(PB_ERR_INVALID, "null queries");
+    if (p->top_k < 0 || p->n_full_scores < 0) return pb_fail(PB_ERR_INVALID, "top_k / n_full_scores must be >= 0");
+    if (p->n_ivf_probe < 1) return pb_fail(PB_ERR_INVALID, "n_ivf_probe must be >= 1");
+    if (p->top_k > 0 && (!io.out_ids || !io.out_scores)) return pb_fail(PB_ERR_INVALID, "null outputs");
+    if (!io.out_counts) return pb_fail(PB_ERR_INVALID, "null out_counts");
+    CK(cudaSetDevice(ix->device));
+    g_stats = Stats();
+    const int64_t Bt = io.n_queries;
+    if (Bt == 0) return PB_OK;
+    for (int64_t b = 0; b < Bt; ++b)
+        if (io.q_off[b + 1] < io.q_off[b]) return pb_fail(PB_ERR_INVALID, "q_tok_offsets not monotone");
+    const int top_k = (int)p->top_k;
+    const long long n_dec = std::max<long long>(p->n_full_scores / 4, p->top_k);  // search.rs:468
+    const long long Mll = std::min<long long>(p->n_full_scores, n_dec);             // take(nfs).take(n_dec)
+    if (Mll > 16384)
+        return pb_fail(PB_ERR_UNSUPPORTED, "min(n_full_scores, max(n_full_scores/4, top_k)) = %lld exceeds 16384", Mll);
+    const int M = (int)Mll;
+    const int Mcap = std::max(M, 1);
+    const bool batched = p->centroid_batch_size > 0 && ix->K > p->centroid_batch_size;  // search.rs:337
+    const bool empty_all = (M == 0 || top_k == 0 || ix->D == 0);
+
+    std::unique_ptr<Workspace> wsp;
+    CKS(ix->acquire(wsp));
+    Workspace &ws = *wsp;
+    struct Releaser {
+        pb_index *ix;
+        std::unique_ptr<Workspace> &w;
+        ~Releaser() { ix->release(w); }
+    } rel{ix, wsp};
+
+    auto zero_counts = [&](int64_t b0, int64_t nb) -> pb_status {
+        if (io.out_on_device) CK(cudaMemsetAsync(io.out_counts + b0, 0, (size_t)nb * 4, ws.stream));
+        else memset(io.out_counts + b0, 0, (size_t)nb * 4);
+        return PB_OK;
+    };
+    if (empty_all) {
+        CKS(zero_counts(0, Bt));
+        CK(cudaStreamSynchronize(ws.stream));
+        return PB_OK;
+    }
+
+    // ---- subset preparation (shared by every query of the call) ----
+    const long long Wd = (ix->D + 31) / 32, Wk = (ix->K + 31) / 32;
+    const uint32_t *d_subset_bits = nullptr, *d_elig = nullptr;
+    int n_probe = (int)std::min<long long>(p->n_ivf_probe, ix->K);
+    bool all_eligible = false;
+    long long n_elig = 0;
+    if (io.has_subset) {
+        CKS(ws.subset_bits.ensure((size_t)Wd * 4));
+        CK(cudaMemsetAsync(ws.subset_bits.p, 0, (size_t)Wd * 4, ws.stream));
+        if (io.n_subset > 0) {
+            CKS(ws.subset.ensure((size_t)io.n_subset * 8));
+            CK(cudaMemcpyAsync(ws.subset.p, io.subset, (size_t)io.n_subset * 8, cudaMemcpyHostToDevice, ws.stream));
+            k_subset_bits<<<296, 256, 0, ws.stream>>>(ws.subset.as<long long>(), io.n_subset, ix->doc_id_base, ix->D,
+                                                     ws.subset_bits.as<uint32_t>());
+            CK(cudaGetLastError());
+        }
+        d_subset_bits = ws.subset_bits.as<uint32_t>();
+        if (!batched) {
+            // eligible centroids + n_ivf_probe scaling, dense variant only (search.rs:350-382)
+            CKS(ws.elig.ensure((size_t)Wk * 4));
+            CKS(ws.misc.ensure(64));
+            CK(cudaMemsetAsync(ws.elig.p, 0, (size_t)Wk * 4, ws.stream));
+            CK(cudaMemsetAsync(ws.misc.p, 0, 64, ws.stream));
+            k_eligible_bits<<<ix->sm_count * 8, 256, 0, ws.stream>>>(d_subset_bits, ix->D, ix->doc_off.as<long long>(),
+                                                                     ix->codes.as<uint32_t>(), ws.elig.as<uint32_t>());
+            k_popcount<<<ix->sm_count, 256, 0, ws.stream>>>(ws.elig.as<uint32_t>(), Wk, ws.misc.as<unsigned long long>());
+            CK(cudaGetLastError());
+            unsigned long long ne = 0;
+            CK(cudaMemcpyAsync(&ne, ws.misc.p, 8, cudaMemcpyDeviceToHost, ws.stream));
+            CK(cudaStreamSynchronize(ws.stream));
+            n_elig = (long long)ne;
+            if (n_elig == 0) {  // every per-token pool is empty -> no cells -> empty results
+                CKS(zero_counts(0, Bt));
+                CK(cudaStreamSynchronize(ws.stream));
+                return PB_OK;
+            }
+            unsigned long long scaled = io.n_subset > 0 ? (unsigned long long)p->n_ivf_probe * (unsigned long long)ix->D /
+                                                              (unsigned long long)io.n_subset
+                                                        : (unsigned long long)p->n_ivf_probe;
+            scaled = std::max<unsigned long long>(scaled, (unsigned long long)p->n_ivf_probe);
+            scaled = std::min<unsigned long long>(scaled, (unsigned long long)n_elig);
+            d_elig = ws.elig.as<uint32_t>();
+            if ((long long)scaled >= n_elig) all_eligible = true;
+            else n_probe = (int)scaled;
+        }
+    }
+    if (!all_eligible && n_probe > 64)
+        return pb_fail(PB_ERR_UNSUPPORTED, "effective n_ivf_probe %d exceeds this build's limit of 64", n_probe);
+
+    // ---- sub-batching: bound the transposed score matrix ----
+    int nq_max_all = 0;
+    for (int64_t b = 0; b < Bt; ++b) nq_max_all = std::max<int>(nq_max_all, (int)(io.q_off[b + 1] - io.q_off[b]));
+    const int QS_all = std::max(8, (nq_max_all + 7) & ~7);
+    if (!all_eligible && (long long)QS_all * n_probe > 8192)
+        return pb_fail(PB_ERR_UNSUPPORTED, "query tokens x n_ivf_probe = %lld exceeds 8192", (long long)QS_all * n_probe);
+    size_t per_q = (size_t)ix->K * QS_all * sizeof(float);
+    int QB = (int)std::max<size_t>(1, std::min<size_t>((size_t)Bt, ix->st_budget / std::max<size_t>(per_q, 1)));
+    QB = std::min(QB, 256);
+
+    const bool prof = ix->profiling;
+    std::vector<int> h_counts;
+    for (int64_t b0 = 0; b0 < Bt; b0 += QB) {
+        const int B = (int)std::min<int64_t>(QB, Bt - b0);
+        const int64_t r0 = io.q_off[b0];
+        const int64_t R = io.q_off[b0 + B] - r0;
+        int nq_max = 0;
+        std::vector<int> qoff(B + 1);
+        for (int b = 0; b <= B; ++b) qoff[b] = (int)(io.q_off[b0 + b] - r0);
+        for (int b = 0; b < B; ++b) nq_max = std::max(nq_max, qoff[b + 1] - qoff[b]);
+        const int QS = std::max(8, (nq_max + 7) & ~7);
+        int *L = g_stats.launches;
+        if (prof) CK(cudaEventRecord(ws.ev[0], ws.stream));
+        // ---- H2D ----
+        CKS(ws.Q.ensure(std::max<size_t>((size_t)R * ix->dim * 4, 16)));
+        CKS(ws.qoff.ensure((size_t)(B + 1) * 4));
+        if (R > 0) {
+            if (io.queries_on_device)
+                CK(cudaMemcpyAsync(ws.Q.p, io.queries + (size_t)r0 * ix->dim, (size_t)R * ix->dim * 4,
+                                   cudaMemcpyDeviceToDevice, ws.stream));
+            else {
+                CKS(ws.hq.ensure((size_t)R * ix->dim * 4));
+                memcpy(ws.hq.p, io.queries + (size_t)r0 * ix->dim, (size_t)R * ix->dim * 4);
+                CK(cudaMemcpyAsync(ws.Q.p, ws.hq.p, (size_t)R * ix->dim * 4, cudaMemcpyHostToDevice, ws.stream));
+            }
+        }
+        CKS(ws.hcounts.ensure((size_t)(B + 1) * 4 + (size_t)B * 16 * 4));
+        memcpy(ws.hcounts.p, qoff.data(), (size_t)(B + 1) * 4);
+        CK(cudaMemcpyAsync(ws.qoff.p, ws.hcounts.p, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ws.stream));
+        if (prof) CK(cudaEventRecord(ws.ev[1], ws.stream));
+
+        // ---- a2 centroid scores ----
+        CKS(ws.ST.ensure((size_t)B * ix->K * QS * sizeof(float)));
+        CKS(launch_centroid_scores(ix, ws, B, QS, &L[PB_STAGE_CENTROID_SCORES]));
+        if (prof) CK(cudaEventRecord(ws.ev[2], ws.stream));
+
+        // ---- a3 probe ----
+        int cells_cap;
+        if (all_eligible) {
+            cells_cap = (int)n_elig;
+            CKS(ws.list.ensure((size_t)n_elig * 4 + 16));
+            CKS(ws.cells.ensure((size_t)B * cells_cap * 4));
+            CKS(ws.ncells.ensure((size_t)B * 4 + 16));
+            int *d_listn = reinterpret_cast<int *>(ws.misc.as<char>() + 16);
+            k_cells_from_bits<<<1, 1024, 0, ws.stream>>>(d_elig, ix->K, ws.list.as<uint32_t>(), d_listn);
+            k_cells_filter_list<<<B, 256, 0, ws.stream>>>(ws.list.as<uint32_t>(), d_listn, ws.ST.as<float>(),
+                                                          ws.qoff.as<int>(), ix->K, QS, p->has_centroid_score_threshold,
+                                                          p->centroid_score_threshold, cells_cap, ws.cells.as<uint32_t>(),
+                                                          ws.ncells.as<int>());
+            CK(cudaGetLastError());
+            L[PB_STAGE_PROBE] += 2;
+        } else {
+            const int n = n_probe;
+            const int n_chunks = (int)((ix->K + 1023) / 1024);
+            cells_cap = (int)std::min<long long>((long long)QS * n, ix->K);
+            CKS(ws.partial.ensure((size_t)B * QS * n_chunks * n * 8));
+            CKS(ws.sel.ensure((size_t)B * QS * n * 8));
+            CKS(ws.cells.ensure((size_t)B * cells_cap * 4));
+            CKS(ws.ncells.ensure((size_t)B * 4 + 16));
+            size_t sm1 = (size_t)4 * n * 32 * 8;
+            CKS(set_smem(k_topn_partial, sm1));
+            k_topn_partial<<<dim3((n_chunks + 3) / 4, B, (QS + 31) / 32), 128, sm1, ws.stream>>>(
+                ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, n, d_elig, ws.partial.as<u64>(), n_chunks);
+            k_topn_merge<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.partial.as<u64>(), ws.qoff.as<int>(), QS, n, n_chunks,
+                                                          ws.sel.as<u64>());
+            int P = 1;
+            while (P < std::max(nq_max * n, 1)) P <<= 1;
+            size_t sm2 = (size_t)P * 12;
+            CKS(set_smem(k_cells, sm2));
+            k_cells<<<B, 256, sm2, ws.stream>>>(ws.sel.as<u64>(), ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, n,
+                                                cells_cap, p->has_centroid_score_threshold, p->centroid_score_threshold,
+                                                batched ? 1 : 0, batched ? (long long)p->centroid_batch_size : ix->K,
+                                                ws.cells.as<uint32_t>(), ws.ncells.as<int>());
+            CK(cudaGetLastError());
+            L[PB_STAGE_PROBE] += 3;
+        }
+        if (prof) CK(cudaEventRecord(ws.ev[3], ws.stream));
+
+        // ---- a4 candidates ----
+        CKS(ws.bitmap.ensure((size_t)B * Wd * 4));
+        CKS(ws.cand.ensure((size_t)B * ix->D * 4));
+        CKS(ws.ncand.ensure((size_t)B * 4 + 16));
+        k_mark<<<dim3(cells_cap, B), 128, 0, ws.stream>>>(ws.cells.as<uint32_t>(), ws.ncells.as<int>(), cells_cap,
+                                                         ix->ivf.as<uint32_t>(), ix->ivf_off.as<long long>(), d_subset_bits,
+                                                         ws.bitmap.as<uint32_t>(), Wd);
+        k_compact<<<B, 1024, 0, ws.stream>>>(ws.bitmap.as<uint32_t>(), Wd, ws.cand.as<uint32_t>(), ix->D,
+                                             ws.ncand.as<int>());
+        CK(cudaGetLastError());
+        L[PB_STAGE_CANDIDATES] += 2;
+        if (prof) CK(cudaEventRecord(ws.ev[4], ws.stream));
+
+        // ---- a5 approximate scores ----
+        CKS(ws.approx.ensure((size_t)B * ix->D * 4));
+        CKS(ws.keys.ensure((size_t)B * ix->D * 8));
+        k_approx<<<dim3(ix->sm_count * 8, B), 256, 0, ws.stream>>>(
+            ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, ix->codes.as<uint32_t>(), ix->doc_off.as<long long>(),
+            ws.cand.as<uint32_t>(), ix->D, ws.ncand.as<int>(), ws.approx.as<float>(), ws.keys.as<u64>());
+        CK(cudaGetLastError());
+        L[PB_STAGE_APPROX] += 1;
+        if (prof) CK(cudaEventRecord(ws.ev[5], ws.stream));
+
+        // ---- a6 cut ----
+        CKS(ws.kept.ensure((size_t)B * Mcap * 4));
+        CKS(ws.nkept.ensure((size_t)B * 4 + 16));
+        CKS(ws.tokp.ensure((size_t)B * (Mcap + 1) * 8));
+        int Pm = 1;
+        while (Pm < Mcap) Pm <<= 1;
+        CKS(set_smem(k_cut, (size_t)Pm * 8));
+        k_cut<<<B, 1024, (size_t)Pm * 8, ws.stream>>>(ws.keys.as<u64>(), ws.approx.as<float>(), ix->D, ws.ncand.as<int>(), M,
+                                                      Mcap, ix->doc_off.as<long long>(), ws.kept.as<uint32_t>(),
+                                                      ws.nkept.as<int>(), ws.tokp.as<long long>());
+        CK(cudaGetLastError());
+        L[PB_STAGE_CUT] += 1;
+        if (prof) CK(cudaEventRecord(ws.ev[6], ws.stream));
+
+        // ---- a7+a8 exact ----
+        CKS(ws.maxkey.ensure((size_t)B * Mcap * QS * 4));
+        CKS(ws.exact.ensure((size_t)B * Mcap * 4));
+        CKS(ws.fkeys.ensure((size_t)B * Mcap * 8));
+        CKS(launch_exact(ix, ws, B, QS, Mcap, 0, (long long)Mcap * std::max(ix->max_doclen, 1), &L[PB_STAGE_EXACT]));
+        k_exact_finalize<<<dim3((Mcap + 7) / 8, B), 256, 0, ws.stream>>>(ws.maxkey.as<uint32_t>(), ws.qoff.as<int>(), QS,
+                                                                       ws.nkept.as<int>(), Mcap, 0, ws.exact.as<float>(),
+                                                                       ws.fkeys.as<u64>());
+        CK(cudaGetLastError());
+        L[PB_STAGE_EXACT] += 1;
+        if (prof) CK(cudaEventRecord(ws.ev[7], ws.stream));
+
+        // ---- a9 top-k ----
+        long long *d_ids;
+        float *d_sc;
+        int *d_cn;
+        if (io.out_on_device) {
+            d_ids = reinterpret_cast<long long *>(io.out_ids) + (size_t)b0 * top_k;
+            d_sc = io.out_scores + (size_t)b0 * top_k;
+            d_cn = io.out_counts + b0;
+        } else {
+            CKS(ws.oids.ensure((size_t)B * top_k * 8));
+            CKS(ws.oscores.ensure((size_t)B * top_k * 4));
+            CKS(ws.ocounts.ensure((size_t)B * 4 + 16));
+            d_ids = ws.oids.as<long long>();
+            d_sc = ws.oscores.as<float>();
+            d_cn = ws.ocounts.as<int>();
+        }
+        CKS(set_smem(k_topk, (size_t)Pm * 8));
+        k_topk<<<B, 1024, (size_t)Pm * 8, ws.stream>>>(ws.fkeys.as<u64>(), ws.exact.as<float>(), ws.kept.as<uint32_t>(),
+                                                       ws.nkept.as<int>(), Mcap, top_k, ix->doc_id_base, d_ids, d_sc, d_cn);
+        CK(cudaGetLastError());
+        L[PB_STAGE_TOPK] += 1;
+        if (prof) CK(cudaEventRecord(ws.ev[8], ws.stream));
+
+        // ---- D2H ----
+        int *hc = ws.hcounts.as<int>() + (B + 1);  // [3][B]: n_cells, n_cand, n_kept
+        CK(cudaMemcpyAsync(hc, ws.ncells.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
+        CK(cudaMemcpyAsync(hc + B, ws.ncand.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
+        CK(cudaMemcpyAsync(hc + 2 * B, ws.nkept.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
+        if (!io.out_on_device) {
+            size_t bytes = (size_t)B * top_k * 12 + (size_t)B * 4;
+            CKS(ws.hres.ensure(bytes));
+            char *h = ws.hres.as<char>();
+            CK(cudaMemcpyAsync(h, d_ids, (size_t)B * top_k * 8, cudaMemcpyDeviceToHost, ws.stream));
+            CK(cudaMemcpyAsync(h + (size_t)B * top_k * 8, d_sc, (size_t)B * top_k * 4, cudaMemcpyDeviceToHost, ws.stream));
+            CK(cudaMemcpyAsync(h + (size_t)B * top_k * 12, d_cn, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
+        }
+        if (prof) CK(cudaEventRecord(ws.ev[9], ws.stream));
+        CK(cudaStreamSynchronize(ws.stream));
+        if (!io.out_on_device) {
+            char *h = ws.hres.as<char>();
+            memcpy(io.out_ids + (size_t)b0 * top_k, h, (size_t)B * top_k * 8);
+            memcpy(io.out_scores + (size_t)b0 * top_k, h + (size_t)B * top_k * 8, (size_t)B * top_k * 4);
+            memcpy(io.out_counts + b0, h + (size_t)B * top_k * 12, (size_t)B * 4);
+        }
+        if (prof)
+            for (int s = 0; s < PB_STAGE_COUNT; ++s) {
+                float ms = 0.f;
+                CK(cudaEventElapsedTime(&ms, ws.ev[s], ws.ev[s + 1]));
+                g_stats.ms[s] += ms;
+            }
+        g_stats.work.n_queries += B;
+        g_stats.work.n_query_tokens += R;
+        for (int b = 0; b < B; ++b) {
+            g_stats.work.n_cells += hc[b];
+            g_stats.work.n_candidates += hc[B + b];
+            g_stats.work.n_exact_docs += hc[2 * B + b];
+        }
+        // ---- optional trace (tests only; synchronous copies) ----
+        if (io.trace) {
+            pb_trace *t = io.trace;
+            for (int b = 0; b < B; ++b) {
+                const int64_t gb = b0 + b;
+                if (t->n_cells) t->n_cells[gb] = hc[b];
+                if (t->n_candidates) t->n_candidates[gb] = hc[B + b];
+                if (t->n_kept) t->n_kept[gb] = hc[2 * B + b];
+                if (t->cells) {
+                    int n = (int)std::min<int64_t>(hc[b], t->cells_cap);
+                    std::vector<uint32_t> tmp(n);
+                    CK(cudaMemcpy(tmp.data(), ws.cells.as<uint32_t>() + (size_t)b * cells_cap, (size_t)n * 4, cudaMemcpyDeviceToHost));
+                    for (int i = 0; i < n; ++i) t->cells[gb * t->cells_cap + i] = tmp[i];
+                }
+                if (t->candidates || t->approx) {
+                    int n = (int)std::min<int64_t>(hc[B + b], t->cand_cap);
+                    std::vector<uint32_t> tmp(n);
+                    CK(cudaMemcpy(tmp.data(), ws.cand.as<uint32_t>() + (size_t)b * ix->D, (size_t)n * 4, cudaMemcpyDeviceToHost));
+                    if (t->candidates)
+                        for (int i = 0; i < n; ++i) t->candidates[gb * t->cand_cap + i] = (int64_t)tmp[i] + ix->doc_id_base;
+                    if (t->approx)
+                        CK(cudaMemcpy(t->approx + gb * t->cand_cap, ws.approx.as<float>() + (size_t)b * ix->D, (size_t)n * 4,
+                                      cudaMemcpyDeviceToHost));
+                }
+                if (t->kept || t->kept_exact) {
+                    int n = (int)std::min<int64_t>(hc[2 * B + b], t->kept_cap);
+                    std::vector<uint32_t> tmp(n);
+                    CK(cudaMemcpy(tmp.data(), ws.kept.as<uint32_t>() + (size_t)b * Mcap, (size_t)n * 4, cudaMemcpyDeviceToHost));
+                    if (t->kept)
+                        for (int i = 0; i < n; ++i) t->kept[gb * t->kept_cap + i] = (int64_t)tmp[i] + ix->doc_id_base;
+                    if (t->kept_exact)
+                        CK(cudaMemcpy(t->kept_exact + gb * t->kept_cap, ws.exact.as<float>() + (size_t)b * Mcap, (size_t)n * 4,
+                                      cudaMemcpyDeviceToHost));
+                }
+            }
+        }
+    }
+    return PB_OK;
+}
+
+extern "C" pb_status pb_search_batch_traced(pb_index *ix, const float *queries, const int64_t *q_tok_offsets,
+                                            int64_t n_queries, const pb_search_params *params, const int64_t *subset,
+                                            int64_t n_subset, int64_t *out_ids, float *out_scores, int32_t *out_counts,
+                                            pb_trace *trace) {
+    SearchIO io{queries, false, q_tok_offsets, n_queries, subset, subset ? n_subset : 0, subset != nullptr,
+                out_ids, out_scores, out_counts, false, trace};
+    return search_impl(ix, params, io);
+}
+
+extern "C" pb_status pb_search_batch(pb_index *ix, const float *queries, const int64_t *q_tok_offsets, int64_t n_queries,
+                                     const pb_search_params *params, const int64_t *subset, int64_t n_subset,
+                                     int64_t *out_ids, float *out_scores, int32_t *out_counts) {
+    return pb_search_batch_traced(ix, queries, q_tok_offsets, n_queries, params, subset, n_subset, out_ids, out_scores,
+                                  out_counts, nullptr);
+}
+
+extern "C" pb_status pb_search_batch_device(pb_index *ix, const float *d_queries, const int64_t *q_tok_offsets_host,
+                                            int64_t n_queries, const pb_search_params *params, int64_t *d_out_ids,
+                                            float *d_out_scores, int32_t *d_out_counts) {
+    SearchIO io{d_queries, true, q_tok_offsets_host, n_queries, nullptr, 0, false,
+                d_out_ids, d_out_scores, d_out_counts, true, nullptr};
+    return search_impl(ix, params, io);
+}
+
+// ------------------------------------------------------------------------------------------
+// stage entry points
+// ------------------------------------------------------------------------------------------
+extern "C" pb_status pb_centroid_scores(pb_index *ix, const float *query_tokens, int64_t n, float *out) {
+    if (!ix || (!query_tokens && n) || (!out && n)) return pb_fail(PB_ERR_INVALID, "null argument");
+    if (n == 0) return PB_OK;
+    CK(cudaSetDevice(ix->device));
+    std::unique_ptr<Workspace> wsp;
+    CKS(ix->acquire(wsp));
+    Workspace &ws = *wsp;
+    struct Releaser {
+        pb_index *ix;
+        std::unique_ptr<Workspace> &w;
+        ~Releaser() { ix->release(w); }
+    } rel{ix, wsp};
+    // one pseudo-query per block of <= 64 tokens keeps the per-query transposed layout small
+    const int blk = 64;
+    DevBuf S;
+    CKS(S.ensure((size_t)blk * ix->K * 4));
+    for (int64_t r0 = 0; r0 < n; r0 += blk) {
+        int nq = (int)std::min<int64_t>(blk, n - r0);
+        int QS = std::max(8, (nq + 7) & ~7);
+        CKS(ws.Q.ensure((size_t)nq * ix->dim * 4));
+        CKS(ws.qoff.ensure(8));
+        int qoff[2] = {0, nq};
+        CK(cudaMemcpyAsync(ws.Q.p, query_tokens + (size_t)r0 * ix->dim, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice, ws.stream));
+        CK(cudaMemcpyAsync(ws.qoff.p, qoff, 8, cudaMemcpyHostToDevice, ws.stream));
+        CKS(ws.ST.ensure((size_t)ix->K * QS * 4));
+        CKS(launch_centroid_scores(ix, ws, 1, QS, nullptr));
+        k_transpose_scores<<<(unsigned)((ix->K + 255) / 256), 256, 0, ws.stream>>>(ws.ST.as<float>(), ix->K, QS, nq, S.as<float>());
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out + (size_t)r0 * ix->K, S.p, (size_t)nq * ix->K * 4, cudaMemcpyDeviceToHost, ws.stream));
+        CK(cudaStreamSynchronize(ws.stream));
+    }
+    return PB_OK;
+}
+
+extern "C" pb_status pb_decompress_documents(pb_index *ix, const int64_t *doc_ids, int64_t n_docs, float *out_embeddings,
+                                             int64_t *out_lengths) {
+    if (!ix || (!doc_ids && n_docs) || !out_lengths) return pb_fail(PB_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(ix->device));
+    if (n_docs == 0) return PB_OK;
+    std::vector<long long> doff((size_t)ix->D + 1);
+    CK(cudaMemcpy(doff.data(), ix->doc_off.p, doff.size() * 8, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> docs;
+    std::vector<long long> prefix(1, 0);
+    for (int64_t i = 0; i < n_docs; ++i) {
+        int64_t d = doc_ids[i] - ix->doc_id_base;
+        if (d < 0 || d >= ix->D) {  // index.rs:1202-1204: unknown id -> length 0
+            out_lengths[i] = 0;
+            continue;
+        }
+        out_lengths[i] = doff[d + 1] - doff[d];
+        docs.push_back((uint32_t)d);
+        prefix.push_back(prefix.back() + out_lengths[i]);
+    }
+    if (!out_embeddings || docs.empty() || prefix.back() == 0) return PB_OK;
+    const long long total = prefix.back();
+    DevBuf ddocs, dpre, dout;
+    CKS(upload(ddocs, docs.data(), docs.size() * 4, PB_MEM_HOST));
+    CKS(upload(dpre, prefix.data(), prefix.size() * 8, PB_MEM_HOST));
+    const long long chunk_tok = 1ll << 22;  // bound the staging buffer (2 GiB at dim 128)
+    CKS(dout.ensure((size_t)std::min(total, chunk_tok + ix->max_doclen) * ix->dim * 4));
+    // process doc ranges whose token count fits the staging buffer
+    size_t i0 = 0;
+    while (i0 < docs.size()) {
+        size_t i1 = i0;
+        while (i1 < docs.size() && prefix[i1] - prefix[i0] < chunk_tok) ++i1;  // <= chunk_tok + max_doclen tokens
+        const int nd = (int)(i1 - i0);
+        const long long ntok = prefix[i1] - prefix[i0];
+        std::vector<long long> local(nd + 1);
+        for (int j = 0; j <= nd; ++j) local[j] = prefix[i0 + j] - prefix[i0];
+        CK(cudaMemcpy(dpre.p, local.data(), local.size() * 8, cudaMemcpyHostToDevice));
+        int blocks = (int)std::max<long long>(1, std::min<long long>((ntok + 7) / 8, (long long)ix->sm_count * 8));
+        PB_DIM_SWITCH(ix->dim, {
+            k_decompress<DIM><<<blocks, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits,
+                                               ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(),
+                                               ix->doc_off.as<long long>(), ddocs.as<uint32_t>() + i0, dpre.as<long long>(),
+                                               nd, dout.as<float>());
+        });
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(out_embeddings + (size_t)prefix[i0] * ix->dim, dout.p, (size_t)ntok * ix->dim * 4, cudaMemcpyDeviceToHost));
+        i0 = i1;
+    }
+    return PB_OK;
+}
+
+extern "C" pb_status pb_maxsim_scores(int32_t device, const float *query, int32_t nq, int32_t dim, const float *doc_tokens,
+                                      const int64_t *doc_tok_offsets, int64_t n_docs, float *out_scores) {
+    if ((!query && nq) || (!doc_tok_offsets) || (!out_scores && n_docs)) return pb_fail(PB_ERR_INVALID, "null argument");
+    if (!dim_supported(dim)) return pb_fail(PB_ERR_UNSUPPORTED, "embedding_dim %d not built (32/64/96/128/256)", dim);
+    if (nq < 0 || n_docs < 0) return pb_fail(PB_ERR_INVALID, "negative size");
+    CKS(check_device(device));
+    if (n_docs == 0) return PB_OK;
+    if (n_docs > (1 << 30)) return pb_fail(PB_ERR_UNSUPPORTED, "too many documents in one call");
+    const long long total = doc_tok_offsets[n_docs] - doc_tok_offsets[0];
+    const int QS = std::max(8, (nq + 7) & ~7);
+    const int Mcap = (int)n_docs;
+    DevBuf dQ, dqoff, dtok, dkept, dnk, dtp, dmax, dex;
+    dmax.zero_on_grow = true;
+    int qoff[2] = {0, nq};
+    std::vector<long long> tp(n_docs + 1);
+    for (int64_t i = 0; i <= n_docs; ++i) tp[i] = doc_tok_offsets[i] - doc_tok_offsets[0];
+    CKS(upload(dQ, query, (size_t)nq * dim * 4, PB_MEM_HOST));
+    CKS(upload(dqoff, qoff, 8, PB_MEM_HOST));
+    CKS(upload(dtok, doc_tokens + (size_t)doc_tok_offsets[0] * dim, (size_t)total * dim * 4, PB_MEM_HOST));
+    CKS(upload(dtp, tp.data(), tp.size() * 8, PB_MEM_HOST));
+    CKS(upload(dnk, &Mcap, 4, PB_MEM_HOST));
+    CKS(dkept.ensure((size_t)Mcap * 4));
+    CKS(dmax.ensure((size_t)Mcap * QS * 4));
+    CKS(dex.ensure((size_t)Mcap * 4));
+    long long chunks = (total + PB_TOK_TILE - 1) / PB_TOK_TILE;
+    int gx = (int)std::max<long long>(1, std::min<long long>(chunks, 148ll * 16));
+    switch (dim) {
+#define PB_CASE(DV)                                                                                              \
+    case DV: {                                                                                                   \
+        auto kern = k_exact<DV, true>;                                                                           \
+        CKS(set_smem(kern, smem_exact(DV)));                                                                     \
+        kern<<<dim3(gx, 1), 128, smem_exact(DV)>>>(dQ.as<float>(), dqoff.as<int>(), QS, nullptr, nullptr, 8, nullptr, \
+                                                   nullptr, nullptr, dtok.as<float>(), dkept.as<uint32_t>(),    \
+                                                   dnk.as<int>(), dtp.as<long long>(), Mcap, 0, dmax.as<uint32_t>()); \
+    } break;
+        PB_CASE(32) PB_CASE(64) PB_CASE(96) PB_CASE(128) PB_CASE(256)
+#undef PB_CASE
+        default: break;
+    }
+    CK(cudaGetLastError());
+    k_exact_finalize<<<dim3((Mcap + 7) / 8, 1), 256>>>(dmax.as<uint32_t>(), dqoff.as<int>(), QS, dnk.as<int>(), Mcap, 0,
+                                                      dex.as<float>(), nullptr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out_scores, dex.p, (size_t)Mcap * 4, cudaMemcpyDeviceToHost));
+    return PB_OK;
+}
+
+extern "C" pb_status pb_exhaustive_scores(pb_index *ix, const float *queries, const int64_t *q_off, int64_t n_queries,
+                                          float *out_scores) {
+    if (!ix || (!queries && n_queries) || !q_off || (!out_scores && n_queries)) return pb_fail(PB_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(ix->device));
+    if (n_queries == 0 || ix->D == 0) return PB_OK;
+    std::unique_ptr<Workspace> wsp;
+    CKS(ix->acquire(wsp));
+    Workspace &ws = *wsp;
+    struct Releaser {
+        pb_index *ix;
+        std::unique_ptr<Workspace> &w;
+        ~Releaser() { ix->release(w); }
+    } rel{ix, wsp};
+    std::vector<long long> doff((size_t)ix->D + 1);
+    CK(cudaMemcpy(doff.data(), ix->doc_off.p, doff.size() * 8, cudaMemcpyDeviceToHost));
+    const int QBmax = 32;
+    const int Mblk = 1 << 16;
+    for (int64_t b0 = 0; b0 < n_queries; b0 += QBmax) {
+        const int B = (int)std::min<int64_t>(QBmax, n_queries - b0);
+        const int64_t r0 = q_off[b0], R = q_off[b0 + B] - r0;
+        std::vector<int> qoff(B + 1);
+        int nq_max = 0;
+        for (int b = 0; b <= B; ++b) qoff[b] = (int)(q_off[b0 + b] - r0);
+        for (int b = 0; b < B; ++b) nq_max = std::max(nq_max, qoff[b + 1] - qoff[b]);
+        const int QS = std::max(8, (nq_max + 7) & ~7);
+        CKS(ws.Q.ensure(std::max<size_t>((size_t)R * ix->dim * 4, 16)));
+        CKS(ws.qoff.ensure((size_t)(B + 1) * 4));
+        if (R) CK(cudaMemcpyAsync(ws.Q.p, queries + (size_t)r0 * ix->dim, (size_t)R * ix->dim * 4, cudaMemcpyHostToDevice, ws.stream));
+        CK(cudaMemcpyAsync(ws.qoff.p, qoff.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ws.stream));
+        CK(cudaStreamSynchronize(ws.stream));
+        CKS(ws.kept.ensure((size_t)Mblk * 4));
+        CKS(ws.nkept.ensure(16));
+        CKS(ws.tokp.ensure((size_t)(Mblk + 1) * 8));
+        CKS(ws.maxkey.ensure((size_t)B * Mblk * QS * 4));
+        CKS(ws.exact.ensure((size_t)B * Mblk * 4));
+        // maxkey layout changes with QS/Mcap: rows are reset by finalize, but only those < n_kept
+        for (long long d0 = 0; d0 < ix->D; d0 += Mblk) {
+            const int nd = (int)std::min<long long>(Mblk, ix->D - d0);
+            k_fill_identity<<<64, 256, 0, ws.stream>>>(ws.kept.as<uint32_t>(), nd, (uint32_t)d0);
+            k_range_prefix<<<64, 256, 0, ws.stream>>>(ix->doc_off.as<long long>(), d0, nd, ws.tokp.as<long long>());
+            CK(cudaMemcpyAsync(ws.nkept.p, &nd, 4, cudaMemcpyHostToDevice, ws.stream));
+            CKS(launch_exact(ix, ws, B, QS, Mblk, 1, doff[d0 + nd] - doff[d0], nullptr));
+            k_exact_finalize<<<dim3((Mblk + 7) / 8, B), 256, 0, ws.stream>>>(ws.maxkey.as<uint32_t>(), ws.qoff.as<int>(), QS,
+                                                                           ws.nkept.as<int>(), Mblk, 1, ws.exact.as<float>(),
+                                                                           nullptr);
+            CK(cudaGetLastError());
+            for (int b = 0; b < B; ++b)
+                CK(cudaMemcpyAsync(out_scores + (size_t)(b0 + b) * ix->D + d0, ws.exact.as<float>() + (size_t)b * Mblk,
+                                   (size_t)nd * 4, cudaMemcpyDeviceToHost, ws.stream));
+            CK(cudaStreamSynchronize(ws.stream));
+        }
+    }
+    return PB_OK;
+}

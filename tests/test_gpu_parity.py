@@ -1,0 +1,230 @@
+"""GPU parity tests proper: every stage of the CUDA path, called through the C-ABI, against the CPU
+oracle on the same seeded inputs.  Bar: bit-exact for ids/indices AND for fp32 values, because both
+sides use the same pinned accumulation order (DESIGN.md "Numerics"); the 1e-4 tolerance of the
+north star is the bound against *other* sgemm orders and is checked separately against float64."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def npb():
+    import next_plaid_b200 as m
+    m.build_library()
+    if m.device_count() < 1:
+        pytest.fail("GPU tests need a B200; the library has no CPU fallback")
+    return m
+
+
+def _gpu_index(npb, ix, **kw):
+    return npb.MmapIndex.from_arrays(ix.centroids, ix.bucket_weights, ix.codes, ix.residuals,
+                                     ix.doc_lengths, ix.ivf, ix.ivf_lengths, ix.nbits, **kw)
+
+
+@pytest.fixture(scope="module")
+def corpus(oracle, npb):
+    docs = oracle.synthetic_corpus(3000, 48, dim=128, seed=21, ragged=True)
+    ix = oracle.create_index(docs, nbits=4, seed=4, num_partitions=512)
+    qs, src = oracle.synthetic_queries(docs, 12, nq=32, seed=9)
+    return docs, ix, qs, src, _gpu_index(npb, ix)
+
+
+def _params(npb, oracle, **kw):
+    return npb.SearchParameters(**kw), oracle.SearchParameters(**kw)
+
+
+def test_accessors(corpus):
+    docs, ix, qs, src, gpu = corpus
+    assert gpu.num_documents() == ix.num_documents
+    assert gpu.num_embeddings() == ix.num_embeddings
+    assert gpu.num_partitions() == ix.num_centroids
+    assert gpu.embedding_dim() == ix.dim and gpu.nbits() == 4
+    assert abs(gpu.avg_doclen() - ix.num_embeddings / ix.num_documents) < 1e-9
+
+
+def test_stage1_centroid_scores_bit_exact(oracle, corpus):
+    docs, ix, qs, src, gpu = corpus
+    q = np.concatenate(qs[:3], 0)
+    S = gpu.centroid_scores(q)
+    want = oracle.centroid_scores(q, ix.centroids)
+    assert np.array_equal(S, want)
+    assert np.abs(S - q.astype(np.float64) @ ix.centroids.astype(np.float64).T).max() < 1e-5
+
+
+def test_stage2_decompress_bit_exact(oracle, corpus):
+    docs, ix, qs, src, gpu = corpus
+    ids = [0, 7, 2999, 1234, 7]
+    emb, lens = gpu.decompress_documents(ids)
+    want = np.concatenate([oracle.get_document_embeddings(ix, d) for d in ids], 0)
+    assert lens.tolist() == [int(ix.doc_lengths[d]) for d in ids]
+    assert np.array_equal(emb, want)
+    assert np.allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-6)
+    # unknown ids contribute length 0 (index.rs:1202-1204)
+    emb2, lens2 = gpu.decompress_documents([5, 10 ** 9])
+    assert lens2.tolist() == [int(ix.doc_lengths[5]), 0]
+    assert np.array_equal(emb2, oracle.get_document_embeddings(ix, 5))
+
+
+def test_stage3_maxsim_bit_exact(oracle, npb, corpus):
+    docs, ix, qs, src, gpu = corpus
+    dd = [oracle.get_document_embeddings(ix, d) for d in (1, 50, 51, 700, 2998)]
+    got = npb.maxsim_scores(qs[0], dd)
+    want = np.array([oracle.maxsim_score(qs[0], d) for d in dd], np.float32)
+    assert np.array_equal(got, want)
+    # north-star tolerance against a different accumulation order (float64 sgemm)
+    ref64 = np.array([(qs[0].astype(np.float64) @ d.astype(np.float64).T).max(1).sum() for d in dd])
+    assert np.abs(got - ref64).max() < 1e-4
+
+
+def test_maxsim_kats_on_gpu(npb):
+    # maxsim.rs:393-413 (1.7) and :498-507 (NaN row entries -> 8.0): same KATs that pin the oracle
+    q = np.zeros((2, 32), np.float32); q[0, 0] = 1; q[1, 1] = 1
+    d = np.zeros((3, 32), np.float32); d[0, :2] = [0.5, 0.5]; d[1, :2] = [0.8, 0.2]; d[2, 1:3] = [0.9, 0.1]
+    assert abs(npb.maxsim_scores(q, [d])[0] - 1.7) < 1e-5
+    q2 = np.zeros((16, 32), np.float32); q2[:, 0] = 1
+    d2 = np.zeros((16, 32), np.float32); d2[:, 0] = 0.5; d2[15, 0] = np.nan
+    assert abs(npb.maxsim_scores(q2, [d2])[0] - 8.0) < 1e-5
+
+
+@pytest.mark.parametrize("cbs,thr", [(100_000, 0.4), (100_000, None), (128, 0.4), (128, None), (0, 0.45)])
+def test_search_stages_and_results_bit_exact(oracle, npb, corpus, cbs, thr):
+    docs, ix, qs, src, gpu = corpus
+    pg, po = _params(npb, oracle, top_k=10, n_ivf_probe=8, n_full_scores=256,
+                     centroid_batch_size=cbs, centroid_score_threshold=thr)
+    res, tr = gpu.search_batch(qs, pg, trace=True)
+    for i, q in enumerate(qs):
+        want, wt = oracle.search_one(ix, q, po, trace=True)
+        assert tr.cells[i].tolist() == wt.cells.tolist(), f"cells q{i}"
+        assert tr.candidates[i].tolist() == wt.candidates.tolist(), f"candidates q{i}"
+        assert np.array_equal(tr.approx[i], wt.approx), f"approx q{i}"
+        assert tr.kept[i].tolist() == wt.kept.tolist(), f"kept q{i}"
+        assert np.array_equal(tr.kept_exact[i], wt.kept_exact), f"exact q{i}"
+        assert res[i].query_id == i
+        assert res[i].passage_ids.tolist() == want.passage_ids.tolist()
+        assert np.array_equal(res[i].scores, want.scores)
+
+
+def test_search_single_equals_batch(oracle, npb, corpus):
+    docs, ix, qs, src, gpu = corpus
+    pg, po = _params(npb, oracle, top_k=5, n_full_scores=128)
+    r = gpu.search(qs[3], pg)
+    w = oracle.search_one(ix, qs[3], po)
+    assert r.query_id == 0 and r.passage_ids.tolist() == w.passage_ids.tolist()
+    assert np.array_equal(r.scores, w.scores)
+
+
+def test_ragged_query_lengths_and_small_dims(oracle, npb):
+    for dim, nbits in ((64, 2), (96, 4), (32, 8), (256, 4), (128, 1)):
+        docs = oracle.synthetic_corpus(400, 20, dim=dim, seed=dim, ragged=True)
+        ix = oracle.create_index(docs, nbits=nbits, seed=1, num_partitions=64)
+        gpu = _gpu_index(npb, ix)
+        qs = []
+        for nq, seed in ((1, 1), (5, 2), (32, 3), (33, 4), (48, 5), (70, 6)):
+            qs.append(oracle.synthetic_queries(docs, 1, nq=nq, seed=seed)[0][0])
+        qs.append(np.zeros((0, dim), np.float32))       # empty query -> empty result
+        pg, po = _params(npb, oracle, top_k=7, n_ivf_probe=4, n_full_scores=64, centroid_score_threshold=0.3)
+        res = gpu.search_batch(qs, pg)
+        for q, r in zip(qs, res):
+            w = oracle.search_one(ix, q, po)
+            assert r.passage_ids.tolist() == w.passage_ids.tolist(), (dim, nbits, q.shape)
+            assert np.array_equal(r.scores, w.scores), (dim, nbits, q.shape)
+        emb, _ = gpu.decompress_documents([0, 1, 399])
+        want = np.concatenate([oracle.get_document_embeddings(ix, d) for d in (0, 1, 399)], 0)
+        assert np.array_equal(emb, want), (dim, nbits)
+        gpu.close()
+
+
+def test_subset_prefilter(oracle, npb, corpus):
+    # search.rs:350-382 (dense: eligible centroids + n_ivf_probe scaling), :434-437, :542-545
+    docs, ix, qs, src, gpu = corpus
+    rng = np.random.default_rng(0)
+    subsets = [list(range(0, 3000, 2)),                      # 50% -> scaled probe 16
+               sorted(rng.choice(3000, 40, replace=False)),  # tiny -> every eligible centroid
+               [5, 5, 17, 10 ** 7, -3],                      # duplicates and out-of-range ids
+               []]
+    for cbs in (100_000, 128):
+        for ss in subsets:
+            pg, po = _params(npb, oracle, top_k=10, n_ivf_probe=8, n_full_scores=256, centroid_batch_size=cbs)
+            res = gpu.search_batch(qs[:4], pg, subset=ss)
+            for q, r in zip(qs[:4], res):
+                w = oracle.search_one(ix, q, po, subset=ss)
+                assert r.passage_ids.tolist() == w.passage_ids.tolist(), (cbs, len(ss))
+                assert np.array_equal(r.scores, w.scores)
+                assert set(r.passage_ids.tolist()) <= set(ss)
+
+
+def test_edge_cases(oracle, npb, corpus):
+    docs, ix, qs, src, gpu = corpus
+    # everything pruned by the threshold -> empty (search.rs:439-445)
+    pg, po = _params(npb, oracle, top_k=10, centroid_score_threshold=2.0)
+    assert all(len(r.passage_ids) == 0 for r in gpu.search_batch(qs[:2], pg))
+    # top_k larger than what survives the cut: take(n_full_scores) caps first (search.rs:461-469)
+    pg, po = _params(npb, oracle, top_k=500, n_full_scores=64, centroid_score_threshold=None)
+    for q, r in zip(qs[:2], gpu.search_batch(qs[:2], pg)):
+        w = oracle.search_one(ix, q, po)
+        assert len(r.passage_ids) == len(w.passage_ids) <= 64
+        assert r.passage_ids.tolist() == w.passage_ids.tolist()
+    # n_ivf_probe = 1 and 64
+    for n in (1, 64):
+        pg, po = _params(npb, oracle, top_k=10, n_ivf_probe=n, n_full_scores=128)
+        for q, r in zip(qs[:3], gpu.search_batch(qs[:3], pg)):
+            w = oracle.search_one(ix, q, po)
+            assert r.passage_ids.tolist() == w.passage_ids.tolist()
+    # zero queries
+    assert gpu.search_batch([], npb.SearchParameters()) == []
+    # bad arguments
+    with pytest.raises(npb.PlaidError):
+        gpu.search_batch(qs[:1], npb.SearchParameters(n_ivf_probe=0))
+    with pytest.raises(npb.PlaidError):
+        gpu.search_batch([np.zeros((4, 64), np.float32)], npb.SearchParameters())
+
+
+def test_index_directory_load(oracle, npb, corpus, tmp_path):
+    # the GPU loader reads the reference's on-disk format (index.rs:1026-1139) chunk by chunk
+    docs, ix, qs, src, gpu = corpus
+    path = str(tmp_path / "idx")
+    oracle.write_index(ix, path, chunk_docs=700, merged=True)
+    g2 = npb.MmapIndex.load(path)
+    assert g2.num_documents() == ix.num_documents and g2.num_embeddings() == ix.num_embeddings
+    pg, po = _params(npb, oracle, top_k=10, n_full_scores=256)
+    for q, r in zip(qs[:4], g2.search_batch(qs[:4], pg)):
+        w = oracle.search_one(ix, q, po)
+        assert r.passage_ids.tolist() == w.passage_ids.tolist() and np.array_equal(r.scores, w.scores)
+    g2.close()
+
+
+def test_exhaustive_scores_and_recall_property(oracle, npb, corpus):
+    docs, ix, qs, src, gpu = corpus
+    ex = gpu.exhaustive_scores(qs[:3])
+    for i in range(3):
+        want = oracle.exhaustive_scores(ix, qs[i])
+        assert np.array_equal(ex[i], want)
+    # size-independent property: PLAID results are a subset of the corpus with exact scores equal to
+    # the exhaustive score of the same doc, and the planted source doc ranks first
+    pg = npb.SearchParameters(top_k=10, n_full_scores=512)
+    for i, r in enumerate(gpu.search_batch(qs[:3], pg)):
+        assert np.array_equal(r.scores, ex[i][r.passage_ids])
+        assert r.passage_ids[0] == src[i]
+
+
+def test_concurrent_searches_share_one_handle(oracle, npb, corpus):
+    # state.rs:24-47: one index, many worker threads
+    import threading
+    docs, ix, qs, src, gpu = corpus
+    pg, po = _params(npb, oracle, top_k=10, n_full_scores=256)
+    want = [oracle.search_one(ix, q, po).passage_ids.tolist() for q in qs]
+    errs = []
+
+    def work(k):
+        try:
+            for _ in range(5):
+                res = gpu.search_batch(qs[k::4], pg)
+                for r, w in zip(res, want[k::4]):
+                    assert r.passage_ids.tolist() == w
+        except Exception as e:  # noqa
+            errs.append(e)
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
