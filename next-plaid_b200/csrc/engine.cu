@@ -131,7 +131,7 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
-        exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list;
+        exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -589,7 +589,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
                 CK(cudaMemcpyAsync(ws.Q.p, ws.hq.p, (size_t)R * ix->dim * 4, cudaMemcpyHostToDevice, ws.stream));
             }
         }
-        CKS(ws.hcounts.ensure((size_t)(B + 1) * 4 + (size_t)B * 16 * 4));
+        CKS(ws.hcounts.ensure((size_t)(B + 1) * 4 + (size_t)B * 16 * 4 + (size_t)(B + 2) * 8 + 64));
         memcpy(ws.hcounts.p, qoff.data(), (size_t)(B + 1) * 4);
         CK(cudaMemcpyAsync(ws.qoff.p, ws.hcounts.p, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ws.stream));
         if (prof) CK(cudaEventRecord(ws.ev[1], ws.stream));
@@ -655,11 +655,14 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         if (prof) CK(cudaEventRecord(ws.ev[4], ws.stream));
 
         // ---- a5 approximate scores ----
+        CKS(ws.counters.ensure((size_t)(B + 1) * 8));  // [0] candidate tokens, [1+b] kept-doc tokens
+        CK(cudaMemsetAsync(ws.counters.p, 0, (size_t)(B + 1) * 8, ws.stream));
         CKS(ws.approx.ensure((size_t)B * ix->D * 4));
         CKS(ws.keys.ensure((size_t)B * ix->D * 8));
         k_approx<<<dim3(ix->sm_count * 8, B), 256, 0, ws.stream>>>(
             ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, ix->codes.as<uint32_t>(), ix->doc_off.as<long long>(),
-            ws.cand.as<uint32_t>(), ix->D, ws.ncand.as<int>(), ws.approx.as<float>(), ws.keys.as<u64>());
+            ws.cand.as<uint32_t>(), ix->D, ws.ncand.as<int>(), ws.approx.as<float>(), ws.keys.as<u64>(),
+            ws.counters.as<unsigned long long>());
         CK(cudaGetLastError());
         L[PB_STAGE_APPROX] += 1;
         if (prof) CK(cudaEventRecord(ws.ev[5], ws.stream));
@@ -673,7 +676,8 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         CKS(set_smem(k_cut, (size_t)Pm * 8));
         k_cut<<<B, 1024, (size_t)Pm * 8, ws.stream>>>(ws.keys.as<u64>(), ws.approx.as<float>(), ix->D, ws.ncand.as<int>(), M,
                                                       Mcap, ix->doc_off.as<long long>(), ws.kept.as<uint32_t>(),
-                                                      ws.nkept.as<int>(), ws.tokp.as<long long>());
+                                                      ws.nkept.as<int>(), ws.tokp.as<long long>(),
+                                                      ws.counters.as<long long>() + 1);
         CK(cudaGetLastError());
         L[PB_STAGE_CUT] += 1;
         if (prof) CK(cudaEventRecord(ws.ev[6], ws.stream));
@@ -718,6 +722,9 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         CK(cudaMemcpyAsync(hc, ws.ncells.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
         CK(cudaMemcpyAsync(hc + B, ws.ncand.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
         CK(cudaMemcpyAsync(hc + 2 * B, ws.nkept.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
+        unsigned long long *hcnt = reinterpret_cast<unsigned long long *>(hc + 4 * B);  // 8-byte aligned: (B+1+4B) ints
+        if ((reinterpret_cast<uintptr_t>(hcnt) & 7) != 0) hcnt = reinterpret_cast<unsigned long long *>(hc + 4 * B + 1);
+        CK(cudaMemcpyAsync(hcnt, ws.counters.p, (size_t)(B + 1) * 8, cudaMemcpyDeviceToHost, ws.stream));
         if (!io.out_on_device) {
             size_t bytes = (size_t)B * top_k * 12 + (size_t)B * 4;
             CKS(ws.hres.ensure(bytes));
@@ -742,10 +749,12 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             }
         g_stats.work.n_queries += B;
         g_stats.work.n_query_tokens += R;
+        g_stats.work.n_candidate_tokens += (long long)hcnt[0];
         for (int b = 0; b < B; ++b) {
             g_stats.work.n_cells += hc[b];
             g_stats.work.n_candidates += hc[B + b];
             g_stats.work.n_exact_docs += hc[2 * B + b];
+            g_stats.work.n_exact_tokens += (long long)hcnt[1 + b];
         }
         // ---- optional trace (tests only; synchronous copies) ----
         if (io.trace) {
