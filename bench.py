@@ -47,7 +47,7 @@ sys.path.insert(0, ROOT)
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--docs", type=int, default=1_000_000, help="documents per GPU")
@@ -228,29 +228,42 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    if world > 1:
-        raise SystemExit("multi-GPU doc-sharded search lands in a later commit of this round")
     t0 = time.time()
     tens = make_index_tensors(args, dev, rank)
     gpu = open_index(npb, tens, args, local, rank * args.docs)
     t_build = time.time() - t0
+    if world > 1:   # doc-sharded: the library runs its own NCCL all-gathers; torch only ships the unique id
+        uid = [npb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        gpu.comm_init(uid[0], rank, world)
     params = npb.SearchParameters(top_k=args.top_k, n_ivf_probe=args.n_ivf_probe, n_full_scores=args.n_full_scores,
                                   centroid_score_threshold=args.threshold)
     n_batches = max(args.steps + args.warmup, 4)
     n_batches = min(n_batches, 16)
     queries, src = make_queries(gpu, args, n_batches * args.batch, seed=args.seed + 7)
+    if world > 1:
+        box = [queries if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        queries = box[0]
     batches = [queries[i * args.batch:(i + 1) * args.batch] for i in range(n_batches)]
 
     # ---- recall@top_k against exhaustive exact MaxSim over the decompressed corpus (untimed) ----
     rq = queries[:args.recall_queries]
     recall = None
     if rq:
-        ex = gpu.exhaustive_scores(rq)
-        res = gpu.search_batch(rq, params)
-        hits = []
-        for i, r in enumerate(res):
-            order = np.lexsort((np.arange(ex.shape[1]), -ex[i]))[:args.top_k]
-            hits.append(len(set(order.tolist()) & set(r.passage_ids.tolist())) / float(args.top_k))
+        ex = gpu.exhaustive_scores(rq)                       # this shard's docs
+        res = gpu.search_batch(rq, params)                   # collective when sharded
+        top = []
+        for i in range(len(rq)):
+            o = np.lexsort((np.arange(ex.shape[1]), -ex[i]))[:args.top_k]
+            top.append([(float(ex[i][j]), int(j) + rank * args.docs) for j in o])
+        if world > 1:
+            alls = [None] * world
+            dist.all_gather_object(alls, top)
+            top = [sorted((t for part in alls for t in part[i]), key=lambda t: (-t[0], t[1]))[:args.top_k]
+                   for i in range(len(rq))]
+        hits = [len({t[1] for t in top[i]} & set(r.passage_ids.tolist())) / float(args.top_k)
+                for i, r in enumerate(res)]
         recall = float(np.mean(hits))
         del ex
 
@@ -266,6 +279,8 @@ def run_b200(args):
         gpu.search_batch_device(d_q[i % n_batches].data_ptr(), offs, params, d_ids.data_ptr(), d_sc.data_ptr(),
                                 d_cn.data_ptr())
     torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
     sampler = ClockSampler(local)
     stage_ms = {}
     launches = 0
@@ -282,6 +297,8 @@ def run_b200(args):
         for k, v in gpu.last_work_counters().items():
             work[k] = work.get(k, 0) + v
     torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
     clocks = sampler.stop()
     gpu.set_profiling(False)
 
@@ -304,6 +321,8 @@ def run_b200(args):
     for i in range(args.warmup):
         e2e_step(i)
     torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
     t1 = time.perf_counter()
     for i in range(args.steps):
         e2e_step(args.warmup + i)
@@ -313,7 +332,7 @@ def run_b200(args):
     # ---- CPU baseline + parity on a bounded sample ----
     cpu = None
     parity = None
-    if not args.no_cpu and args.cpu_queries > 0:
+    if not args.no_cpu and args.cpu_queries > 0 and world == 1:
         from oracle import oracle
         hix = host_index_from_tensors(oracle, tens, args)
         po = oracle.SearchParameters(top_k=args.top_k, n_ivf_probe=args.n_ivf_probe,
@@ -355,6 +374,10 @@ def run_b200(args):
             "peak_source": peak_src, "ms_per_launch": dom_ms,
             "algorithmic_bytes_per_launch": alg.get(dom, 0) / max(args.steps, 1)}
 
+    if world > 1:
+        tt = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(tt[0]), float(tt[1])
     qps = args.batch * args.steps / (dev_ms * 1e-3)
     out = {
         "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
@@ -372,6 +395,10 @@ def run_b200(args):
     }
     if rank == 0:
         print(json.dumps(out))
+    gpu.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def run_reference(args):

@@ -224,6 +224,18 @@ PB_API pb_status pb_search_batch_device(pb_index *ix, const float *d_queries,
                                         const pb_search_params *params, int64_t *d_out_ids,
                                         float *d_out_scores, int32_t *d_out_counts);
 
+/* ---- doc-sharded deployment (no reference analogue: the reference is single-process) ----
+ *
+ * One process per GPU; shard g holds a contiguous doc-id range (pb_index_desc.doc_id_base) with the
+ * centroids replicated.  After pb_index_comm_init every pb_search_batch on the handle is a collective:
+ * all ranks call it with the same queries and parameters and all receive the same global result,
+ * bit-identical to searching the unsharded index.  Two NCCL all-gathers per sub-batch (per-shard
+ * top-M approximate keys, then exact triples) reproduce the reference's GLOBAL n_full_scores/4 cut
+ * (search.rs:460-469) and its stable final sort (search.rs:496).
+ */
+PB_API pb_status pb_comm_unique_id(uint8_t *out128);   /* rank 0: 128-byte NCCL unique id */
+PB_API pb_status pb_index_comm_init(pb_index *ix, const uint8_t *id128, int32_t rank, int32_t world);
+
 /* ---- misc ----------------------------------------------------------------------------- */
 
 PB_API const char *pb_last_error(void);       /* thread-local, never NULL */

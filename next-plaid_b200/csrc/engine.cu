@@ -15,6 +15,40 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
+// ------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen) so single-GPU hosts need no libnccl.  Only the doc-sharded path
+// (pb_index_comm_init) touches it.  Types restated from nccl.h 2.27 (stable ABI since 2.x).
+// ------------------------------------------------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { PB_NCCL_UINT64 = 5 };
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (h) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) return false;
+        GetUniqueId = (int (*)(ncclUniqueId *))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+        CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+        AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+        GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllGather && GetErrorString;
+    }
+};
+static NcclApi g_nccl;
+
 // ------------------------------------------------------------------------------------------
 // errors
 // ------------------------------------------------------------------------------------------
@@ -36,6 +70,11 @@ pb_status pb_fail(pb_status s, const char *fmt, ...) {
         if (e_ != cudaSuccess)                                                                     \
             return pb_fail(PB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
                            __FILE__, __LINE__);                                                    \
+    } while (0)
+#define CKN(call)                                                                                  \
+    do {                                                                                           \
+        int r_ = (call);                                                                           \
+        if (r_ != 0) return pb_fail(PB_ERR_COMM, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
     } while (0)
 #define CKS(expr)                                                                                  \
     do {                                                                                           \
@@ -131,7 +170,8 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
-        exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters;
+        exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys,
+        gkeys, krank, payload, gfkeys, gpayload;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -165,6 +205,8 @@ struct pb_index {
     DevBuf centroids, w_rev, codes, residuals, doc_off, ivf, ivf_off;
     bool profiling = false;
     size_t st_budget = (size_t)4 << 30;
+    ncclComm_t comm = nullptr;  // doc-sharded deployment: one rank per GPU
+    int rank = 0, world = 1;
     std::mutex mu;
     std::vector<std::unique_ptr<Workspace>> pool;
 
@@ -289,6 +331,8 @@ pb_status pb_index_open_begin(const pb_index_desc *d, pb_index **out) {
                        (long long)d->num_documents, (long long)d->num_embeddings);
     if (d->num_centroids >= (1ll << 32) - 1 || d->num_documents >= (1ll << 32) - 1)
         return pb_fail(PB_ERR_UNSUPPORTED, "K and D must be below 2^32-1 per shard");
+    if (d->doc_id_base < 0 || d->doc_id_base + d->num_documents >= (1ll << 32) - 1)
+        return pb_fail(PB_ERR_UNSUPPORTED, "global doc ids must stay below 2^32-1");
     if (!d->centroids || !d->bucket_weights || (!d->doc_lengths && d->num_documents) || !d->ivf_lengths)
         return pb_fail(PB_ERR_INVALID, "null index array");
     CKS(check_device(d->device));
@@ -367,6 +411,7 @@ extern "C" void pb_index_close(pb_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     cudaDeviceSynchronize();
+    if (ix->comm) g_nccl.CommDestroy(ix->comm);
     delete ix;
 }
 
@@ -482,7 +527,14 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
     const int M = (int)Mll;
     const int Mcap = std::max(M, 1);
     const bool batched = p->centroid_batch_size > 0 && ix->K > p->centroid_batch_size;  // search.rs:337
-    const bool empty_all = (M == 0 || top_k == 0 || ix->D == 0);
+    const bool sharded = ix->world > 1;
+    if (sharded && (long long)ix->world * M > 16384)
+        return pb_fail(PB_ERR_UNSUPPORTED, "shards x kept docs = %lld exceeds 16384", (long long)ix->world * M);
+    if (sharded && io.has_subset && !batched)
+        return pb_fail(PB_ERR_UNSUPPORTED, "subset with the dense variant needs the global eligible-centroid set; "
+                                            "not built for doc-sharded indices");
+    // a shard with no documents still takes part in the exchanges
+    const bool empty_all = (M == 0 || top_k == 0 || (ix->D == 0 && !sharded));
 
     std::unique_ptr<Workspace> wsp;
     CKS(ix->acquire(wsp));
@@ -662,7 +714,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         k_approx<<<dim3(ix->sm_count * 8, B), 256, 0, ws.stream>>>(
             ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, ix->codes.as<uint32_t>(), ix->doc_off.as<long long>(),
             ws.cand.as<uint32_t>(), ix->D, ws.ncand.as<int>(), ws.approx.as<float>(), ws.keys.as<u64>(),
-            ws.counters.as<unsigned long long>());
+            ws.counters.as<unsigned long long>(), (uint32_t)ix->doc_id_base);
         CK(cudaGetLastError());
         L[PB_STAGE_APPROX] += 1;
         if (prof) CK(cudaEventRecord(ws.ev[5], ws.stream));
@@ -671,15 +723,33 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         CKS(ws.kept.ensure((size_t)B * Mcap * 4));
         CKS(ws.nkept.ensure((size_t)B * 4 + 16));
         CKS(ws.tokp.ensure((size_t)B * (Mcap + 1) * 8));
+        if (sharded) CKS(ws.lkeys.ensure((size_t)B * Mcap * 8));
         int Pm = 1;
         while (Pm < Mcap) Pm <<= 1;
         CKS(set_smem(k_cut, (size_t)Pm * 8));
         k_cut<<<B, 1024, (size_t)Pm * 8, ws.stream>>>(ws.keys.as<u64>(), ws.approx.as<float>(), ix->D, ws.ncand.as<int>(), M,
                                                       Mcap, ix->doc_off.as<long long>(), ws.kept.as<uint32_t>(),
                                                       ws.nkept.as<int>(), ws.tokp.as<long long>(),
-                                                      ws.counters.as<long long>() + 1);
+                                                      ws.counters.as<long long>() + 1, (uint32_t)ix->doc_id_base,
+                                                      sharded ? ws.lkeys.as<u64>() : nullptr);
         CK(cudaGetLastError());
         L[PB_STAGE_CUT] += 1;
+        if (sharded) {
+            // exchange 1: every shard's sorted top-M cut keys -> global cut -> my members
+            const int G = ix->world;
+            CKS(ws.gkeys.ensure((size_t)G * B * M * 8));
+            CKS(ws.krank.ensure((size_t)B * Mcap * 4));
+            CKN(g_nccl.AllGather(ws.lkeys.p, ws.gkeys.p, (size_t)B * M, PB_NCCL_UINT64, ix->comm, ws.stream));
+            int Pg = 1;
+            while (Pg < G * M) Pg <<= 1;
+            CKS(set_smem(k_merge_cut, (size_t)Pg * 8));
+            k_merge_cut<<<B, 1024, (size_t)Pg * 8, ws.stream>>>(ws.gkeys.as<u64>(), G, B, M, (uint32_t)ix->doc_id_base, ix->D,
+                                                                ix->doc_off.as<long long>(), ws.kept.as<uint32_t>(),
+                                                                ws.krank.as<uint32_t>(), ws.nkept.as<int>(),
+                                                                ws.tokp.as<long long>(), ws.counters.as<long long>() + 1);
+            CK(cudaGetLastError());
+            L[PB_STAGE_CUT] += 2;
+        }
         if (prof) CK(cudaEventRecord(ws.ev[6], ws.stream));
 
         // ---- a7+a8 exact ----
@@ -687,9 +757,14 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         CKS(ws.exact.ensure((size_t)B * Mcap * 4));
         CKS(ws.fkeys.ensure((size_t)B * Mcap * 8));
         CKS(launch_exact(ix, ws, B, QS, Mcap, 0, (long long)Mcap * std::max(ix->max_doclen, 1), &L[PB_STAGE_EXACT]));
-        k_exact_finalize<<<dim3((Mcap + 7) / 8, B), 256, 0, ws.stream>>>(ws.maxkey.as<uint32_t>(), ws.qoff.as<int>(), QS,
-                                                                       ws.nkept.as<int>(), Mcap, 0, ws.exact.as<float>(),
-                                                                       ws.fkeys.as<u64>());
+        if (sharded) {
+            CKS(ws.payload.ensure((size_t)B * Mcap * 8));
+            CK(cudaMemsetAsync(ws.fkeys.p, 0xff, (size_t)B * Mcap * 8, ws.stream));  // ~0 = no entry
+        }
+        k_exact_finalize<<<dim3((Mcap + 7) / 8, B), 256, 0, ws.stream>>>(
+            ws.maxkey.as<uint32_t>(), ws.qoff.as<int>(), QS, ws.nkept.as<int>(), Mcap, 0, ws.exact.as<float>(),
+            ws.fkeys.as<u64>(), sharded ? ws.krank.as<uint32_t>() : nullptr, ws.kept.as<uint32_t>(),
+            (uint32_t)ix->doc_id_base, sharded ? ws.payload.as<u64>() : nullptr);
         CK(cudaGetLastError());
         L[PB_STAGE_EXACT] += 1;
         if (prof) CK(cudaEventRecord(ws.ev[7], ws.stream));
@@ -710,11 +785,27 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             d_sc = ws.oscores.as<float>();
             d_cn = ws.ocounts.as<int>();
         }
-        CKS(set_smem(k_topk, (size_t)Pm * 8));
-        k_topk<<<B, 1024, (size_t)Pm * 8, ws.stream>>>(ws.fkeys.as<u64>(), ws.exact.as<float>(), ws.kept.as<uint32_t>(),
-                                                       ws.nkept.as<int>(), Mcap, top_k, ix->doc_id_base, d_ids, d_sc, d_cn);
-        CK(cudaGetLastError());
-        L[PB_STAGE_TOPK] += 1;
+        if (sharded) {
+            // exchange 2: (exact key | global approx rank) + (doc id | score) of every shard, merged on every rank
+            const int G = ix->world;
+            CKS(ws.gfkeys.ensure((size_t)G * B * M * 8));
+            CKS(ws.gpayload.ensure((size_t)G * B * M * 8));
+            CKN(g_nccl.AllGather(ws.fkeys.p, ws.gfkeys.p, (size_t)B * M, PB_NCCL_UINT64, ix->comm, ws.stream));
+            CKN(g_nccl.AllGather(ws.payload.p, ws.gpayload.p, (size_t)B * M, PB_NCCL_UINT64, ix->comm, ws.stream));
+            int Pg = 1;
+            while (Pg < G * M) Pg <<= 1;
+            size_t sm = (size_t)Pg * 8 + (size_t)M * 8;
+            CKS(set_smem(k_merge_topk, sm));
+            k_merge_topk<<<B, 1024, sm, ws.stream>>>(ws.gfkeys.as<u64>(), ws.gpayload.as<u64>(), G, B, M, top_k, d_ids, d_sc, d_cn);
+            CK(cudaGetLastError());
+            L[PB_STAGE_TOPK] += 3;
+        } else {
+            CKS(set_smem(k_topk, (size_t)Pm * 8));
+            k_topk<<<B, 1024, (size_t)Pm * 8, ws.stream>>>(ws.fkeys.as<u64>(), ws.exact.as<float>(), ws.kept.as<uint32_t>(),
+                                                           ws.nkept.as<int>(), Mcap, top_k, ix->doc_id_base, d_ids, d_sc, d_cn);
+            CK(cudaGetLastError());
+            L[PB_STAGE_TOPK] += 1;
+        }
         if (prof) CK(cudaEventRecord(ws.ev[8], ws.stream));
 
         // ---- D2H ----
@@ -948,7 +1039,7 @@ extern "C" pb_status pb_maxsim_scores(int32_t device, const float *query, int32_
     }
     CK(cudaGetLastError());
     k_exact_finalize<<<dim3((Mcap + 7) / 8, 1), 256>>>(dmax.as<uint32_t>(), dqoff.as<int>(), QS, dnk.as<int>(), Mcap, 0,
-                                                      dex.as<float>(), nullptr);
+                                                      dex.as<float>(), nullptr, nullptr, nullptr, 0u, nullptr);
     CK(cudaGetLastError());
     CK(cudaMemcpy(out_scores, dex.p, (size_t)Mcap * 4, cudaMemcpyDeviceToHost));
     return PB_OK;
@@ -998,7 +1089,7 @@ extern "C" pb_status pb_exhaustive_scores(pb_index *ix, const float *queries, co
             CKS(launch_exact(ix, ws, B, QS, Mblk, 1, doff[d0 + nd] - doff[d0], nullptr));
             k_exact_finalize<<<dim3((Mblk + 7) / 8, B), 256, 0, ws.stream>>>(ws.maxkey.as<uint32_t>(), ws.qoff.as<int>(), QS,
                                                                            ws.nkept.as<int>(), Mblk, 1, ws.exact.as<float>(),
-                                                                           nullptr);
+                                                                           nullptr, nullptr, nullptr, 0u, nullptr);
             CK(cudaGetLastError());
             for (int b = 0; b < B; ++b)
                 CK(cudaMemcpyAsync(out_scores + (size_t)(b0 + b) * ix->D + d0, ws.exact.as<float>() + (size_t)b * Mblk,
@@ -1006,5 +1097,35 @@ extern "C" pb_status pb_exhaustive_scores(pb_index *ix, const float *queries, co
             CK(cudaStreamSynchronize(ws.stream));
         }
     }
+    return PB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// doc-sharded deployment: one process per GPU, NCCL all-gathers of the per-shard top lists.
+// The host passes the 128-byte NCCL unique id between ranks however it likes (torch.distributed,
+// MPI, a file); nothing else crosses the C-ABI.
+// ------------------------------------------------------------------------------------------
+extern "C" pb_status pb_comm_unique_id(uint8_t *out128) {
+    if (!out128) return pb_fail(PB_ERR_INVALID, "null argument");
+    if (!g_nccl.load()) return pb_fail(PB_ERR_COMM, "libnccl.so.2 not found (%s)", dlerror());
+    ncclUniqueId id;
+    CKN(g_nccl.GetUniqueId(&id));
+    memcpy(out128, id.internal, 128);
+    return PB_OK;
+}
+
+extern "C" pb_status pb_index_comm_init(pb_index *ix, const uint8_t *id128, int32_t rank, int32_t world) {
+    if (!ix || !id128) return pb_fail(PB_ERR_INVALID, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return pb_fail(PB_ERR_INVALID, "bad rank %d / world %d", rank, world);
+    if (ix->comm) return pb_fail(PB_ERR_INVALID, "communicator already initialised");
+    if (world == 1) return PB_OK;
+    if (!g_nccl.load()) return pb_fail(PB_ERR_COMM, "libnccl.so.2 not found (%s)", dlerror());
+    CK(cudaSetDevice(ix->device));
+    ncclUniqueId id;
+    memcpy(id.internal, id128, 128);
+    CKN(g_nccl.CommInitRank(&ix->comm, world, id, rank));
+    ix->rank = rank;
+    ix->world = world;
     return PB_OK;
 }

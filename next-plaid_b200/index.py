@@ -74,7 +74,7 @@ EXPORTS = [
     "pb_search_batch", "pb_search_batch_traced", "pb_centroid_scores", "pb_decompress_documents",
     "pb_maxsim_scores", "pb_exhaustive_scores", "pb_set_profiling", "pb_last_stage_stats",
     "pb_last_work_counters", "pb_search_batch_device", "pb_last_error", "pb_version",
-    "pb_device_count",
+    "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init",
 ]
 
 _lib = None
@@ -117,6 +117,8 @@ def load_library():
         L.pb_exhaustive_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.pb_last_stage_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pb_last_work_counters.argtypes = [C.c_void_p, C.POINTER(_Work)]
+        L.pb_comm_unique_id.argtypes = [C.c_void_p]
+        L.pb_index_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         _lib = L
     return _lib
 
@@ -128,6 +130,13 @@ def _check(status: int):
 
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def comm_unique_id() -> bytes:
+    """pb_comm_unique_id (rank 0); ship the 128 bytes to the other ranks."""
+    buf = np.zeros(128, np.uint8)
+    _check(load_library().pb_comm_unique_id(_ptr(buf)))
+    return buf.tobytes()
 
 
 def device_count() -> int:
@@ -333,6 +342,13 @@ class MmapIndex:
         out = np.zeros((len(queries), self.num_documents()), np.float32)
         _check(load_library().pb_exhaustive_scores(self._h, _ptr(flat), _ptr(offs), len(queries), _ptr(out)))
         return out
+
+    # -- doc-sharded deployment ------------------------------------------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """pb_index_comm_init: after this, search_batch is a collective over `world` ranks."""
+        buf = np.frombuffer(bytes(unique_id), np.uint8).copy()
+        assert buf.size == 128
+        _check(load_library().pb_index_comm_init(self._h, _ptr(buf), rank, world))
 
     # -- measurement hooks -------------------------------------------------------------------------
     def set_profiling(self, on: bool):
