@@ -240,8 +240,8 @@ def run_b200(args):
                                   centroid_score_threshold=args.threshold)
     n_batches = max(args.steps + args.warmup, 4)
     n_batches = min(n_batches, 16)
-    queries, src = make_queries(gpu, args, n_batches * args.batch, seed=args.seed + 7)
-    if world > 1:
+    queries = make_queries(gpu, args, n_batches * args.batch, seed=args.seed + 7)[0] if rank == 0 else None
+    if world > 1:   # the same queries on every rank, drawn from shard 0
         box = [queries if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         queries = box[0]
