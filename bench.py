@@ -275,13 +275,13 @@ def run_b200(args):
     d_sc = torch.empty((args.batch, args.top_k), dtype=torch.float32, device=dev)
     d_cn = torch.empty((args.batch,), dtype=torch.int32, device=dev)
     gpu.set_profiling(True)
+    sampler = ClockSampler(local)       # spans warm-up + both timed regions (nvidia-smi needs ~0.2 s to start)
     for i in range(args.warmup):
         gpu.search_batch_device(d_q[i % n_batches].data_ptr(), offs, params, d_ids.data_ptr(), d_sc.data_ptr(),
                                 d_cn.data_ptr())
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
     stage_ms = {}
     launches = 0
     work = {}
@@ -299,7 +299,6 @@ def run_b200(args):
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop()
     gpu.set_profiling(False)
 
     # ---- end-to-end through the public API: pinned host queries in, host results out ----
@@ -328,6 +327,7 @@ def run_b200(args):
         e2e_step(args.warmup + i)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t1
+    clocks = sampler.stop()
 
     # ---- CPU baseline + parity on a bounded sample ----
     cpu = None

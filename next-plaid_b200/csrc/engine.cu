@@ -244,9 +244,9 @@ struct pb_index {
 static bool dim_supported(int d) { return d == 32 || d == 64 || d == 96 || d == 128 || d == 256; }
 
 static size_t smem_scores(int dim) { return (size_t)(PB_TOK_TILE + PB_Q_TILE) * (dim + 4) * sizeof(float); }
-static size_t smem_exact(int dim) {
+static size_t smem_exact(int dim, int packed) {
     return (size_t)(PB_TOK_TILE + PB_Q_TILE) * (dim + 4) * sizeof(float) + PB_Q_TILE * 129 * sizeof(float) +
-           PB_TOK_TILE * sizeof(int) + 256 * sizeof(float);
+           PB_TOK_TILE * sizeof(int) + 256 * sizeof(float) + (size_t)PB_TOK_TILE * packed;
 }
 
 template <class Kern> static pb_status set_smem(Kern k, size_t bytes) {
@@ -471,12 +471,14 @@ static pb_status launch_centroid_scores(pb_index *ix, Workspace &ws, int B, int 
 
 static pb_status launch_exact(pb_index *ix, Workspace &ws, int B, int QS, int Mcap, int kept_shared,
                               long long max_tokens, int *launches) {
+    // each CTA owns a contiguous range of chunks; aim for 8 waves of 2 CTAs/SM over the whole grid
     long long chunks = (max_tokens + PB_TOK_TILE - 1) / PB_TOK_TILE;
-    int gx = (int)std::max<long long>(1, std::min<long long>(chunks, (long long)ix->sm_count * 16));
+    long long want = std::max<long long>(1, ((long long)ix->sm_count * 16 + B - 1) / B);
+    int gx = (int)std::max<long long>(1, std::min<long long>(chunks, want));
     PB_DIM_SWITCH(ix->dim, {
         auto kern = k_exact<DIM, false>;
-        CKS(set_smem(kern, smem_exact(DIM)));
-        kern<<<dim3(gx, B), 128, smem_exact(DIM), ws.stream>>>(
+        CKS(set_smem(kern, smem_exact(DIM, ix->packed)));
+        kern<<<dim3(gx, B), 128, smem_exact(DIM, ix->packed), ws.stream>>>(
             ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits,
             ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->doc_off.as<long long>(), nullptr,
             ws.kept.as<uint32_t>(), ws.nkept.as<int>(), ws.tokp.as<long long>(), Mcap, kept_shared,
@@ -1028,8 +1030,8 @@ extern "C" pb_status pb_maxsim_scores(int32_t device, const float *query, int32_
 #define PB_CASE(DV)                                                                                              \
     case DV: {                                                                                                   \
         auto kern = k_exact<DV, true>;                                                                           \
-        CKS(set_smem(kern, smem_exact(DV)));                                                                     \
-        kern<<<dim3(gx, 1), 128, smem_exact(DV)>>>(dQ.as<float>(), dqoff.as<int>(), QS, nullptr, nullptr, 8, nullptr, \
+        CKS(set_smem(kern, smem_exact(DV, 0)));                                                                  \
+        kern<<<dim3(gx, 1), 128, smem_exact(DV, 0)>>>(dQ.as<float>(), dqoff.as<int>(), QS, nullptr, nullptr, 8, nullptr, \
                                                    nullptr, nullptr, dtok.as<float>(), dkept.as<uint32_t>(),    \
                                                    dnk.as<int>(), dtp.as<long long>(), Mcap, 0, dmax.as<uint32_t>()); \
     } break;
