@@ -202,7 +202,8 @@ struct pb_index {
     long long K = 0, D = 0, N = 0, ivf_len = 0, doc_id_base = 0;
     int max_doclen = 0;
     int sm_count = 148;
-    DevBuf centroids, w_rev, codes, residuals, doc_off, ivf, ivf_off;
+    DevBuf centroids, w_rev, codes, residuals, doc_off, ivf, ivf_off, ucodes, udoc_off;
+    long long n_ucodes = 0;
     bool profiling = false;
     size_t st_budget = (size_t)4 << 30;
     ncclComm_t comm = nullptr;  // doc-sharded deployment: one rank per GPU
@@ -243,7 +244,7 @@ struct pb_index {
 
 static bool dim_supported(int d) { return d == 32 || d == 64 || d == 96 || d == 128 || d == 256; }
 
-static size_t smem_scores(int dim) { return (size_t)(PB_TOK_TILE + PB_Q_TILE) * (dim + 4) * sizeof(float); }
+static size_t smem_scores(int dim) { return (size_t)(PB_TOK_TILE + 2 * PB_Q_TILE) * (dim + 4) * sizeof(float); }
 static size_t smem_exact(int dim, int packed) {
     return (size_t)(PB_TOK_TILE + PB_Q_TILE) * (dim + 4) * sizeof(float) + PB_Q_TILE * 129 * sizeof(float) +
            PB_TOK_TILE * sizeof(int) + 256 * sizeof(float) + (size_t)PB_TOK_TILE * packed;
@@ -393,12 +394,42 @@ pb_status pb_index_open_begin(const pb_index_desc *d, pb_index **out) {
     return PB_OK;
 }
 
+// Derived arrays that need every token: the per-doc distinct-code lists k_approx walks.
+pb_status pb_index_finalize(pb_index *ix) {
+    CK(cudaSetDevice(ix->device));
+    if ((unsigned long long)ix->K * 1024ull * 4ull >= (1ull << 40)) return pb_fail(PB_ERR_UNSUPPORTED, "K too large");
+    std::vector<long long> uoff((size_t)ix->D + 1, 0);
+    if (ix->D > 0) {
+        DevBuf counts;
+        CKS(counts.ensure((size_t)ix->D * 4));
+        const int blocks = (int)std::min<long long>(ix->D, (long long)ix->sm_count * 16);
+        k_unique_codes<<<blocks, 128>>>(ix->codes.as<uint32_t>(), ix->doc_off.as<long long>(), ix->D, nullptr, nullptr,
+                                        counts.as<int>());
+        CK(cudaGetLastError());
+        std::vector<int> hc((size_t)ix->D);
+        CK(cudaMemcpy(hc.data(), counts.p, hc.size() * 4, cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < ix->D; ++i) uoff[i + 1] = uoff[i] + hc[i];
+    }
+    ix->n_ucodes = uoff[ix->D];
+    CKS(upload(ix->udoc_off, uoff.data(), uoff.size() * 8, PB_MEM_HOST));
+    CKS(ix->ucodes.ensure(std::max<size_t>((size_t)ix->n_ucodes * 4, 16)));
+    if (ix->D > 0) {
+        const int blocks = (int)std::min<long long>(ix->D, (long long)ix->sm_count * 16);
+        k_unique_codes<<<blocks, 128>>>(ix->codes.as<uint32_t>(), ix->doc_off.as<long long>(), ix->D,
+                                        ix->udoc_off.as<long long>(), ix->ucodes.as<uint32_t>(), nullptr);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+    }
+    return PB_OK;
+}
+
 extern "C" pb_status pb_index_open(const pb_index_desc *d, pb_index **out) {
     if (!d || !out) return pb_fail(PB_ERR_INVALID, "null argument");
     if (d->num_embeddings > 0 && (!d->codes || !d->residuals)) return pb_fail(PB_ERR_INVALID, "null index array");
     pb_index *ix = nullptr;
     CKS(pb_index_open_begin(d, &ix));
     pb_status s = pb_index_upload_tokens(ix, 0, d->codes, d->residuals, d->num_embeddings, d->memory_space);
+    if (s == PB_OK) s = pb_index_finalize(ix);
     if (s != PB_OK) {
         pb_index_close(ix);
         return s;
@@ -614,6 +645,8 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
     if (!all_eligible && (long long)QS_all * n_probe > 8192)
         return pb_fail(PB_ERR_UNSUPPORTED, "query tokens x n_ivf_probe = %lld exceeds 8192", (long long)QS_all * n_probe);
     size_t per_q = (size_t)ix->K * QS_all * sizeof(float);
+    if (per_q >= ((size_t)1 << 32))
+        return pb_fail(PB_ERR_UNSUPPORTED, "num_centroids x query tokens x 4 = %zu bytes per query exceeds 2^32", per_q);
     int QB = (int)std::max<size_t>(1, std::min<size_t>((size_t)Bt, ix->st_budget / std::max<size_t>(per_q, 1)));
     QB = std::min(QB, 256);
 
@@ -714,7 +747,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         CKS(ws.approx.ensure((size_t)B * ix->D * 4));
         CKS(ws.keys.ensure((size_t)B * ix->D * 8));
         k_approx<<<dim3(ix->sm_count * 8, B), 256, 0, ws.stream>>>(
-            ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, ix->codes.as<uint32_t>(), ix->doc_off.as<long long>(),
+            ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(),
             ws.cand.as<uint32_t>(), ix->D, ws.ncand.as<int>(), ws.approx.as<float>(), ws.keys.as<u64>(),
             ws.counters.as<unsigned long long>(), (uint32_t)ix->doc_id_base);
         CK(cudaGetLastError());

@@ -7,3 +7,5 @@ pb_status pb_fail(pb_status s, const char *fmt, ...);
 pb_status pb_index_open_begin(const pb_index_desc *d, pb_index **out);
 pb_status pb_index_upload_tokens(pb_index *ix, long long tok_off, const int64_t *codes, const uint8_t *residuals,
                                  long long n, int space);
+// call once after the last pb_index_upload_tokens
+pb_status pb_index_finalize(pb_index *ix);

@@ -228,6 +228,10 @@ extern "C" pb_status pb_index_load(const char *index_dir, int32_t device, pb_ind
         }
         off += chunk_tokens[c];
     }
+    if (pb_status s = pb_index_finalize(ix)) {
+        pb_index_close(ix);
+        return s;
+    }
     *out = ix;
     return PB_OK;
 }
