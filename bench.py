@@ -65,6 +65,10 @@ def parse_args():
     ap.add_argument("--cpu-queries", type=int, default=2, help="queries in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--docs-per-topic", type=int, default=1024)
+    ap.add_argument("--pool", type=int, default=256, help="centroids per topic pool")
+    ap.add_argument("--res-sigma", type=float, default=0.05, help="per-dimension residual scale")
+    ap.add_argument("--query-noise", type=float, default=0.15)
     return ap.parse_args()
 
 
@@ -78,12 +82,13 @@ def make_index_tensors(args, device, shard: int):
     g.manual_seed(args.seed)                       # shared across shards: centroids, pools, weights
     cent = torch.randn(K, dim, generator=g, device=device, dtype=torch.float32)
     cent /= cent.norm(dim=1, keepdim=True)
-    n_topics = max((D * max(args.gpus, 1)) // 256, 4)
-    P = min(512, K)
+    n_topics = max((D * max(args.gpus, 1)) // args.docs_per_topic, 4)
+    P = min(args.pool, K)
     pools = torch.randint(0, K, (n_topics, P), generator=g, device=device, dtype=torch.int32)
+    hubs = torch.randint(0, K, (4096,), generator=g, device=device, dtype=torch.int64)   # stop-word-like centroids
     nb = 1 << nbits
     probs = (torch.arange(nb, dtype=torch.float64) + 0.5) / nb
-    w = (0.025 * torch.special.ndtri(probs)).to(torch.float32).to(device)   # quantile mid-points of N(0, .025^2)
+    w = (args.res_sigma * torch.special.ndtri(probs)).to(torch.float32).to(device)   # quantile mid-points of N(0, s^2)
     g.manual_seed(args.seed + 1000 * (shard + 1))   # per-shard documents
     doc_topic = torch.randint(0, n_topics, (D,), generator=g, device=device, dtype=torch.int64)
     N = D * T
@@ -98,11 +103,13 @@ def make_index_tensors(args, device, shard: int):
         pidx = (u * u * P).to(torch.int64).clamp_(max=P - 1)
         from_pool = pools[topic, pidx].to(torch.int64)
         rnd = torch.randint(0, K, (n,), generator=g, device=device, dtype=torch.int64)
-        use_pool = torch.rand(n, generator=g, device=device) < 0.8
-        codes[d0 * T:d1 * T] = torch.where(use_pool, from_pool, rnd)
+        sel = torch.rand(n, generator=g, device=device)
+        hub = hubs[torch.randint(0, 4096, (n,), generator=g, device=device)]
+        codes[d0 * T:d1 * T] = torch.where(sel < 0.7, from_pool, torch.where(sel < 0.9, rnd, hub))
+        del sel, hub
         residuals[d0 * T:d1 * T] = torch.randint(0, 256, (n, dim * nbits // 8), generator=g, device=device,
                                                  dtype=torch.uint8)
-        del topic, u, pidx, from_pool, rnd, use_pool
+        del topic, u, pidx, from_pool, rnd
     doc_lengths = torch.full((D,), T, dtype=torch.int64, device=device)
     # IVF: per centroid the ascending unique doc ids (index.rs:479-499)
     keys = torch.empty(N, dtype=torch.int64, device=device)
@@ -137,7 +144,7 @@ def make_queries(gpu, args, n_queries: int, seed: int):
         tok = emb[rng.integers(0, emb.shape[0], size=args.nq)]
         noise = rng.standard_normal(tok.shape).astype(np.float32)
         noise /= np.linalg.norm(noise, axis=1, keepdims=True)
-        q = tok + 0.15 * noise
+        q = tok + args.query_noise * noise
         q /= np.linalg.norm(q, axis=1, keepdims=True)
         out.append(q.astype(np.float32))
     return out, src

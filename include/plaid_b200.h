@@ -198,6 +198,11 @@ enum {
     PB_STAGE_COUNT = 9
 };
 
+/* Diagnostic switch for the approximate stage (default on): 1 = two-pass (16-bit first pass +
+ * exact re-check of the docs that can still make the cut), 0 = single exact pass over every
+ * candidate.  Both produce the reference's cut bit for bit; tests compare them. */
+PB_API void pb_set_fast_approx(pb_index *ix, int32_t enabled);
+
 /* Enable per-stage CUDA-event timing for subsequent searches on this handle (adds event
  * records only, no synchronisation inside the path). */
 PB_API void pb_set_profiling(pb_index *ix, int32_t enabled);

@@ -6,6 +6,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -170,7 +171,7 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
-        exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys,
+        exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2,
         gkeys, krank, payload, gfkeys, gpayload;
     HostBuf hq, hres, hcounts;
     pb_status init() {
@@ -204,6 +205,8 @@ struct pb_index {
     int sm_count = 148;
     DevBuf centroids, w_rev, codes, residuals, doc_off, ivf, ivf_off, ucodes, udoc_off;
     long long n_ucodes = 0;
+    float cmax = 1.0f;         // largest centroid L2 norm (range of the 16-bit score table)
+    bool fast_approx = true;   // two-pass approximate stage (exact cut either way)
     bool profiling = false;
     size_t st_budget = (size_t)4 << 30;
     ncclComm_t comm = nullptr;  // doc-sharded deployment: one rank per GPU
@@ -410,6 +413,17 @@ pb_status pb_index_finalize(pb_index *ix) {
         CK(cudaMemcpy(hc.data(), counts.p, hc.size() * 4, cudaMemcpyDeviceToHost));
         for (long long i = 0; i < ix->D; ++i) uoff[i + 1] = uoff[i] + hc[i];
     }
+    {
+        DevBuf mx;
+        CKS(mx.ensure(16));
+        CK(cudaMemset(mx.p, 0, 4));
+        k_max_row_norm<<<ix->sm_count * 4, 256>>>(ix->centroids.as<float>(), ix->K, ix->dim, mx.as<float>());
+        CK(cudaGetLastError());
+        float m2 = 0.f;
+        CK(cudaMemcpy(&m2, mx.p, 4, cudaMemcpyDeviceToHost));
+        ix->cmax = sqrtf(m2);
+        if (const char *e = getenv("PB_FAST_APPROX")) ix->fast_approx = atoi(e) != 0;
+    }
     ix->n_ucodes = uoff[ix->D];
     CKS(upload(ix->udoc_off, uoff.data(), uoff.size() * 8, PB_MEM_HOST));
     CKS(ix->ucodes.ensure(std::max<size_t>((size_t)ix->n_ucodes * 4, 16)));
@@ -465,6 +479,9 @@ extern "C" void pb_search_params_default(pb_search_params *p) {  // search.rs:58
     p->centroid_score_threshold = 0.4f;
 }
 
+extern "C" void pb_set_fast_approx(pb_index *ix, int32_t enabled) {
+    if (ix) ix->fast_approx = enabled != 0;
+}
 extern "C" void pb_set_profiling(pb_index *ix, int32_t enabled) {
     if (ix) ix->profiling = enabled != 0;
 }
@@ -484,7 +501,7 @@ extern "C" pb_status pb_last_work_counters(pb_index *, pb_work_counters *out) {
 // ------------------------------------------------------------------------------------------
 // kernel launch helpers shared by the search pipeline and the stage entry points
 // ------------------------------------------------------------------------------------------
-static pb_status launch_centroid_scores(pb_index *ix, Workspace &ws, int B, int QS, int *launches) {
+static pb_status launch_centroid_scores(pb_index *ix, Workspace &ws, int B, int QS, int *launches, bool with16 = false) {
     const int tiles = (int)((ix->K + PB_TOK_TILE - 1) / PB_TOK_TILE);
     // enough CTAs to fill the machine twice over; each CTA keeps its centroid tile in smem and walks queries
     int groups = std::max(1, std::min(B, (4 * ix->sm_count + tiles - 1) / tiles));
@@ -493,7 +510,9 @@ static pb_status launch_centroid_scores(pb_index *ix, Workspace &ws, int B, int 
         CKS(set_smem(kern, smem_scores(DIM)));
         kern<<<dim3(tiles, groups), 128, smem_scores(DIM), ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), B, QS,
                                                                         ix->centroids.as<float>(), ix->K,
-                                                                        ws.ST.as<float>());
+                                                                        ws.ST.as<float>(),
+                                                                        with16 ? ws.ST16.as<unsigned short>() : nullptr,
+                                                                        ws.qrange.as<float2>(), ws.qflag.as<int>());
     });
     CK(cudaGetLastError());
     if (launches) ++*launches;
@@ -683,7 +702,17 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
 
         // ---- a2 centroid scores ----
         CKS(ws.ST.ensure((size_t)B * ix->K * QS * sizeof(float)));
-        CKS(launch_centroid_scores(ix, ws, B, QS, &L[PB_STAGE_CENTROID_SCORES]));
+        const bool fast = ix->fast_approx && !io.trace;  // trace wants every candidate's exact approx score
+        if (fast) {
+            CKS(ws.ST16.ensure((size_t)B * ix->K * QS * 2));
+            CKS(ws.qrange.ensure((size_t)B * 8 + 16));
+            CKS(ws.qflag.ensure((size_t)B * 4 + 16));
+            k_query_range<<<B, 32, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), ix->dim, ix->cmax,
+                                                   ws.qrange.as<float2>(), ws.qflag.as<int>());
+            CK(cudaGetLastError());
+            L[PB_STAGE_CENTROID_SCORES] += 1;
+        }
+        CKS(launch_centroid_scores(ix, ws, B, QS, &L[PB_STAGE_CENTROID_SCORES], fast));
         if (prof) CK(cudaEventRecord(ws.ev[2], ws.stream));
 
         // ---- a3 probe ----
@@ -742,14 +771,33 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         if (prof) CK(cudaEventRecord(ws.ev[4], ws.stream));
 
         // ---- a5 approximate scores ----
-        CKS(ws.counters.ensure((size_t)(B + 1) * 8));  // [0] candidate tokens, [1+b] kept-doc tokens
-        CK(cudaMemsetAsync(ws.counters.p, 0, (size_t)(B + 1) * 8, ws.stream));
+        CKS(ws.counters.ensure((size_t)(B + 2) * 8));  // [0] candidate codes gathered, [1+b] kept-doc tokens, [B+1] re-check gathers
+        CK(cudaMemsetAsync(ws.counters.p, 0, (size_t)(B + 2) * 8, ws.stream));
         CKS(ws.approx.ensure((size_t)B * ix->D * 4));
         CKS(ws.keys.ensure((size_t)B * ix->D * 8));
+        const uint32_t *cand_list = ws.cand.as<uint32_t>();
+        const int *cand_n = ws.ncand.as<int>();
+        if (fast) {
+            CKS(ws.lsum.ensure((size_t)B * ix->D * 4));
+            CKS(ws.cand2.ensure((size_t)B * ix->D * 4));
+            CKS(ws.ncand2.ensure((size_t)B * 4 + 16));
+            k_approx16<<<dim3(ix->sm_count * 8, B), 256, 0, ws.stream>>>(
+                ws.ST16.as<unsigned short>(), ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
+                ix->udoc_off.as<long long>(), ws.cand.as<uint32_t>(), ix->D, ws.ncand.as<int>(), ws.lsum.as<uint32_t>(),
+                ws.counters.as<unsigned long long>());
+            k_select16<<<B, 1024, 0, ws.stream>>>(ws.lsum.as<uint32_t>(), ws.cand.as<uint32_t>(), ix->D, ws.ncand.as<int>(),
+                                                  ws.qoff.as<int>(), ws.qflag.as<int>(), M, ws.cand2.as<uint32_t>(),
+                                                  ws.ncand2.as<int>());
+            CK(cudaGetLastError());
+            L[PB_STAGE_APPROX] += 2;
+            cand_list = ws.cand2.as<uint32_t>();
+            cand_n = ws.ncand2.as<int>();
+        }
         k_approx<<<dim3(ix->sm_count * 8, B), 256, 0, ws.stream>>>(
             ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(),
-            ws.cand.as<uint32_t>(), ix->D, ws.ncand.as<int>(), ws.approx.as<float>(), ws.keys.as<u64>(),
-            ws.counters.as<unsigned long long>(), (uint32_t)ix->doc_id_base);
+            cand_list, ix->D, cand_n, ws.approx.as<float>(), ws.keys.as<u64>(),
+            fast ? ws.counters.as<unsigned long long>() + B + 1 : ws.counters.as<unsigned long long>(),
+            (uint32_t)ix->doc_id_base);
         CK(cudaGetLastError());
         L[PB_STAGE_APPROX] += 1;
         if (prof) CK(cudaEventRecord(ws.ev[5], ws.stream));
@@ -762,7 +810,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         int Pm = 1;
         while (Pm < Mcap) Pm <<= 1;
         CKS(set_smem(k_cut, (size_t)Pm * 8));
-        k_cut<<<B, 1024, (size_t)Pm * 8, ws.stream>>>(ws.keys.as<u64>(), ws.approx.as<float>(), ix->D, ws.ncand.as<int>(), M,
+        k_cut<<<B, 1024, (size_t)Pm * 8, ws.stream>>>(ws.keys.as<u64>(), ws.approx.as<float>(), ix->D, cand_n, M,
                                                       Mcap, ix->doc_off.as<long long>(), ws.kept.as<uint32_t>(),
                                                       ws.nkept.as<int>(), ws.tokp.as<long long>(),
                                                       ws.counters.as<long long>() + 1, (uint32_t)ix->doc_id_base,
@@ -850,7 +898,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         CK(cudaMemcpyAsync(hc + 2 * B, ws.nkept.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
         unsigned long long *hcnt = reinterpret_cast<unsigned long long *>(hc + 4 * B);  // 8-byte aligned: (B+1+4B) ints
         if ((reinterpret_cast<uintptr_t>(hcnt) & 7) != 0) hcnt = reinterpret_cast<unsigned long long *>(hc + 4 * B + 1);
-        CK(cudaMemcpyAsync(hcnt, ws.counters.p, (size_t)(B + 1) * 8, cudaMemcpyDeviceToHost, ws.stream));
+        CK(cudaMemcpyAsync(hcnt, ws.counters.p, (size_t)(B + 2) * 8, cudaMemcpyDeviceToHost, ws.stream));
         if (!io.out_on_device) {
             size_t bytes = (size_t)B * top_k * 12 + (size_t)B * 4;
             CKS(ws.hres.ensure(bytes));

@@ -74,7 +74,7 @@ EXPORTS = [
     "pb_search_batch", "pb_search_batch_traced", "pb_centroid_scores", "pb_decompress_documents",
     "pb_maxsim_scores", "pb_exhaustive_scores", "pb_set_profiling", "pb_last_stage_stats",
     "pb_last_work_counters", "pb_search_batch_device", "pb_last_error", "pb_version",
-    "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init",
+    "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init", "pb_set_fast_approx",
 ]
 
 _lib = None
@@ -102,6 +102,8 @@ def load_library():
         L.pb_index_close.restype = None
         L.pb_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         L.pb_set_profiling.restype = None
+        L.pb_set_fast_approx.argtypes = [C.c_void_p, C.c_int32]
+        L.pb_set_fast_approx.restype = None
         L.pb_index_load.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
         L.pb_index_open.argtypes = [C.POINTER(_Desc), C.POINTER(C.c_void_p)]
         L.pb_search_batch_traced.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
@@ -351,6 +353,9 @@ class MmapIndex:
         _check(load_library().pb_index_comm_init(self._h, _ptr(buf), rank, world))
 
     # -- measurement hooks -------------------------------------------------------------------------
+    def set_fast_approx(self, on: bool):
+        load_library().pb_set_fast_approx(self._h, 1 if on else 0)
+
     def set_profiling(self, on: bool):
         load_library().pb_set_profiling(self._h, 1 if on else 0)
 

@@ -228,3 +228,44 @@ def test_concurrent_searches_share_one_handle(oracle, npb, corpus):
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errs, errs
+
+
+def test_two_pass_approx_equals_single_pass_and_oracle(oracle, npb, corpus):
+    # DESIGN.md "a5 two-pass": the 16-bit first pass only prunes docs that provably cannot make the cut
+    docs, ix, qs, src, gpu = corpus
+    for kw in (dict(top_k=10, n_full_scores=64), dict(top_k=100, n_full_scores=400),
+               dict(top_k=10, n_full_scores=256, centroid_score_threshold=None, n_ivf_probe=32),
+               dict(top_k=3, n_full_scores=8, centroid_batch_size=128)):
+        pg, po = _params(npb, oracle, **kw)
+        gpu.set_fast_approx(True)
+        fast = gpu.search_batch(qs, pg)
+        gpu.set_fast_approx(False)
+        slow = gpu.search_batch(qs, pg)
+        gpu.set_fast_approx(True)
+        for q, f, s in zip(qs, fast, slow):
+            w = oracle.search_one(ix, q, po)
+            assert f.passage_ids.tolist() == s.passage_ids.tolist() == w.passage_ids.tolist(), kw
+            assert np.array_equal(f.scores, w.scores) and np.array_equal(s.scores, w.scores)
+
+
+def test_two_pass_approx_with_massive_ties_and_odd_ranges(oracle, npb):
+    # many byte-identical docs -> identical approximate scores straddling the cut: the certified band
+    # must keep all of them so the doc-id tie-break of the stable sort (search.rs:460) decides
+    base = oracle.synthetic_corpus(40, 24, dim=64, seed=5)
+    docs = [base[i % 4] if i % 3 else base[i % 40] for i in range(900)]
+    ix = oracle.create_index(docs, nbits=4, seed=2, num_partitions=64)
+    qs, _ = oracle.synthetic_queries(docs, 6, nq=16, seed=4)
+    qs.append(qs[0] * 7.5)                      # non-unit query norms scale the 16-bit range
+    qs.append(qs[1] * 1e-3)
+    bad = qs[2].copy(); bad[3, 5] = np.inf      # non-finite query -> flagged, single exact pass
+    qs.append(bad)
+    gpu = _gpu_index(npb, ix)
+    for kw in (dict(top_k=10, n_full_scores=64, centroid_score_threshold=None),
+               dict(top_k=50, n_full_scores=100, centroid_score_threshold=None, n_ivf_probe=16),
+               dict(top_k=5, n_full_scores=20, centroid_score_threshold=0.2)):
+        pg, po = _params(npb, oracle, **kw)
+        for q, r in zip(qs, gpu.search_batch(qs, pg)):
+            w = oracle.search_one(ix, q, po)
+            assert r.passage_ids.tolist() == w.passage_ids.tolist(), kw
+            assert np.array_equal(r.scores, w.scores, equal_nan=True), kw
+    gpu.close()
