@@ -171,7 +171,7 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
-        exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2,
+        exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2, cand3, ncand3, ub, theta, rel,
         gkeys, krank, payload, gfkeys, gpayload;
     HostBuf hq, hres, hcounts;
     pb_status init() {
@@ -207,6 +207,8 @@ struct pb_index {
     long long n_ucodes = 0;
     float cmax = 1.0f;         // largest centroid L2 norm (range of the 16-bit score table)
     bool fast_approx = true;   // two-pass approximate stage (exact cut either way)
+    bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
+                               // the cut sits well above the background score level
     bool profiling = false;
     size_t st_budget = (size_t)4 << 30;
     ncclComm_t comm = nullptr;  // doc-sharded deployment: one rank per GPU
@@ -423,6 +425,7 @@ pb_status pb_index_finalize(pb_index *ix) {
         CK(cudaMemcpy(&m2, mx.p, 4, cudaMemcpyDeviceToHost));
         ix->cmax = sqrtf(m2);
         if (const char *e = getenv("PB_FAST_APPROX")) ix->fast_approx = atoi(e) != 0;
+        if (const char *e = getenv("PB_CASCADE")) ix->cascade = atoi(e) != 0;
     }
     ix->n_ucodes = uoff[ix->D];
     CKS(upload(ix->udoc_off, uoff.data(), uoff.size() * 8, PB_MEM_HOST));
@@ -480,7 +483,9 @@ extern "C" void pb_search_params_default(pb_search_params *p) {  // search.rs:58
 }
 
 extern "C" void pb_set_fast_approx(pb_index *ix, int32_t enabled) {
-    if (ix) ix->fast_approx = enabled != 0;
+    if (!ix) return;
+    ix->fast_approx = enabled != 0;  // 0 = single exact pass, 1 = two-pass, 2 = two-pass behind the pruning cascade
+    ix->cascade = enabled == 2;
 }
 extern "C" void pb_set_profiling(pb_index *ix, int32_t enabled) {
     if (ix) ix->profiling = enabled != 0;
@@ -781,13 +786,50 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             CKS(ws.lsum.ensure((size_t)B * ix->D * 4));
             CKS(ws.cand2.ensure((size_t)B * ix->D * 4));
             CKS(ws.ncand2.ensure((size_t)B * 4 + 16));
-            k_approx16<<<dim3(ix->sm_count * 8, B), 256, 0, ws.stream>>>(
-                ws.ST16.as<unsigned short>(), ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
-                ix->udoc_off.as<long long>(), ws.cand.as<uint32_t>(), ix->D, ws.ncand.as<int>(), ws.lsum.as<uint32_t>(),
-                ws.counters.as<unsigned long long>());
-            k_select16<<<B, 1024, 0, ws.stream>>>(ws.lsum.as<uint32_t>(), ws.cand.as<uint32_t>(), ix->D, ws.ncand.as<int>(),
-                                                  ws.qoff.as<int>(), ws.qflag.as<int>(), M, ws.cand2.as<uint32_t>(),
-                                                  ws.ncand2.as<int>());
+            const dim3 ga(ix->sm_count * 8, B);
+            const unsigned short *st16 = ws.ST16.as<unsigned short>();
+            const uint32_t *list = ws.cand.as<uint32_t>();
+            const int *list_n = ws.ncand.as<int>();
+            unsigned long long *cnt = ws.counters.as<unsigned long long>();
+            const size_t rel_bytes = (size_t)Wk * 4;
+            const bool cascade = ix->cascade && rel_bytes <= 200 * 1024;
+            if (cascade) {
+                // pruning cascade: certified upper bound first, 16-bit sums only where it matters
+                CKS(ws.cand3.ensure((size_t)B * ix->D * 4));
+                CKS(ws.ncand3.ensure((size_t)B * 4 + 16));
+                CKS(ws.ub.ensure((size_t)B * ix->D * 4));
+                CKS(ws.theta.ensure((size_t)B * 4 + 16));
+                CKS(ws.rel.ensure((size_t)B * rel_bytes));
+                k_theta16<<<B, 1024, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ws.theta.as<uint32_t>());
+                k_relevant_bits<<<dim3((unsigned)((Wk + 7) / 8), B), 256, 0, ws.stream>>>(
+                    st16, ws.qoff.as<int>(), ix->K, QS, ws.theta.as<uint32_t>(), ws.rel.as<uint32_t>(), Wk);
+                CKS(set_smem(k_approx_ub, rel_bytes));
+                k_approx_ub<<<ga, 256, rel_bytes, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
+                                                               ix->udoc_off.as<long long>(), list, ix->D, list_n,
+                                                               ws.theta.as<uint32_t>(), ws.rel.as<uint32_t>(), Wk,
+                                                               ws.ub.as<uint32_t>(), cnt);
+                // S' = top 2M by upper bound
+                k_select_u32<<<B, 1024, 0, ws.stream>>>(ws.ub.as<uint32_t>(), list_n, 2 * M, 0, ws.ub.as<uint32_t>(), list,
+                                                        list_n, ix->D, ws.qoff.as<int>(), ws.qflag.as<int>(),
+                                                        ws.cand2.as<uint32_t>(), ws.ncand2.as<int>());
+                k_approx16<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
+                                                      ix->udoc_off.as<long long>(), ws.cand2.as<uint32_t>(), ix->D,
+                                                      ws.ncand2.as<int>(), ws.lsum.as<uint32_t>(), cnt + B + 1);
+                // list2 = every candidate whose upper bound reaches tau' - W
+                k_select_u32<<<B, 1024, 0, ws.stream>>>(ws.lsum.as<uint32_t>(), ws.ncand2.as<int>(), M, 4, ws.ub.as<uint32_t>(),
+                                                        list, list_n, ix->D, ws.qoff.as<int>(), ws.qflag.as<int>(),
+                                                        ws.cand3.as<uint32_t>(), ws.ncand3.as<int>());
+                CK(cudaGetLastError());
+                L[PB_STAGE_APPROX] += 6;
+                list = ws.cand3.as<uint32_t>();
+                list_n = ws.ncand3.as<int>();
+            }
+            k_approx16<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
+                                                  ix->udoc_off.as<long long>(), list, ix->D, list_n, ws.lsum.as<uint32_t>(),
+                                                  cascade ? cnt + B + 1 : cnt);
+            k_select_u32<<<B, 1024, 0, ws.stream>>>(ws.lsum.as<uint32_t>(), list_n, M, 4, ws.lsum.as<uint32_t>(), list, list_n,
+                                                    ix->D, ws.qoff.as<int>(), ws.qflag.as<int>(), ws.cand2.as<uint32_t>(),
+                                                    ws.ncand2.as<int>());
             CK(cudaGetLastError());
             L[PB_STAGE_APPROX] += 2;
             cand_list = ws.cand2.as<uint32_t>();

@@ -353,8 +353,9 @@ class MmapIndex:
         _check(load_library().pb_index_comm_init(self._h, _ptr(buf), rank, world))
 
     # -- measurement hooks -------------------------------------------------------------------------
-    def set_fast_approx(self, on: bool):
-        load_library().pb_set_fast_approx(self._h, 1 if on else 0)
+    def set_fast_approx(self, mode):
+        """0/False = single exact pass, 1/True = two-pass (default), 2 = two-pass + pruning cascade."""
+        load_library().pb_set_fast_approx(self._h, int(mode))
 
     def set_profiling(self, on: bool):
         load_library().pb_set_profiling(self._h, 1 if on else 0)

@@ -237,15 +237,17 @@ def test_two_pass_approx_equals_single_pass_and_oracle(oracle, npb, corpus):
                dict(top_k=10, n_full_scores=256, centroid_score_threshold=None, n_ivf_probe=32),
                dict(top_k=3, n_full_scores=8, centroid_batch_size=128)):
         pg, po = _params(npb, oracle, **kw)
-        gpu.set_fast_approx(True)
+        gpu.set_fast_approx(1)
         fast = gpu.search_batch(qs, pg)
-        gpu.set_fast_approx(False)
+        gpu.set_fast_approx(0)
         slow = gpu.search_batch(qs, pg)
-        gpu.set_fast_approx(True)
-        for q, f, s in zip(qs, fast, slow):
+        gpu.set_fast_approx(2)
+        casc = gpu.search_batch(qs, pg)
+        gpu.set_fast_approx(1)
+        for q, f, s, c in zip(qs, fast, slow, casc):
             w = oracle.search_one(ix, q, po)
-            assert f.passage_ids.tolist() == s.passage_ids.tolist() == w.passage_ids.tolist(), kw
-            assert np.array_equal(f.scores, w.scores) and np.array_equal(s.scores, w.scores)
+            assert f.passage_ids.tolist() == s.passage_ids.tolist() == c.passage_ids.tolist() == w.passage_ids.tolist(), kw
+            assert np.array_equal(f.scores, w.scores) and np.array_equal(s.scores, w.scores) and np.array_equal(c.scores, w.scores)
 
 
 def test_two_pass_approx_with_massive_ties_and_odd_ranges(oracle, npb):
@@ -264,8 +266,10 @@ def test_two_pass_approx_with_massive_ties_and_odd_ranges(oracle, npb):
                dict(top_k=50, n_full_scores=100, centroid_score_threshold=None, n_ivf_probe=16),
                dict(top_k=5, n_full_scores=20, centroid_score_threshold=0.2)):
         pg, po = _params(npb, oracle, **kw)
-        for q, r in zip(qs, gpu.search_batch(qs, pg)):
-            w = oracle.search_one(ix, q, po)
-            assert r.passage_ids.tolist() == w.passage_ids.tolist(), kw
-            assert np.array_equal(r.scores, w.scores, equal_nan=True), kw
+        for mode in (1, 2):
+            gpu.set_fast_approx(mode)
+            for q, r in zip(qs, gpu.search_batch(qs, pg)):
+                w = oracle.search_one(ix, q, po)
+                assert r.passage_ids.tolist() == w.passage_ids.tolist(), (kw, mode)
+                assert np.array_equal(r.scores, w.scores, equal_nan=True), (kw, mode)
     gpu.close()
