@@ -525,7 +525,8 @@ static pb_status launch_centroid_scores(pb_index *ix, Workspace &ws, int B, int 
 }
 
 static pb_status launch_exact(pb_index *ix, Workspace &ws, int B, int QS, int Mcap, int kept_shared,
-                              long long max_tokens, int *launches) {
+                              long long max_tokens, int *launches, int nq_max = 1 << 30) {
+    (void)nq_max;
     // each CTA owns a contiguous range of chunks; aim for 8 waves of 2 CTAs/SM over the whole grid
     long long chunks = (max_tokens + PB_TOK_TILE - 1) / PB_TOK_TILE;
     long long want = std::max<long long>(1, ((long long)ix->sm_count * 16 + B - 1) / B);
@@ -881,7 +882,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         CKS(ws.maxkey.ensure((size_t)B * Mcap * QS * 4));
         CKS(ws.exact.ensure((size_t)B * Mcap * 4));
         CKS(ws.fkeys.ensure((size_t)B * Mcap * 8));
-        CKS(launch_exact(ix, ws, B, QS, Mcap, 0, (long long)Mcap * std::max(ix->max_doclen, 1), &L[PB_STAGE_EXACT]));
+        CKS(launch_exact(ix, ws, B, QS, Mcap, 0, (long long)Mcap * std::max(ix->max_doclen, 1), &L[PB_STAGE_EXACT], nq_max));
         if (sharded) {
             CKS(ws.payload.ensure((size_t)B * Mcap * 8));
             CK(cudaMemsetAsync(ws.fkeys.p, 0xff, (size_t)B * Mcap * 8, ws.stream));  // ~0 = no entry
@@ -1211,7 +1212,7 @@ extern "C" pb_status pb_exhaustive_scores(pb_index *ix, const float *queries, co
             k_fill_identity<<<64, 256, 0, ws.stream>>>(ws.kept.as<uint32_t>(), nd, (uint32_t)d0);
             k_range_prefix<<<64, 256, 0, ws.stream>>>(ix->doc_off.as<long long>(), d0, nd, ws.tokp.as<long long>());
             CK(cudaMemcpyAsync(ws.nkept.p, &nd, 4, cudaMemcpyHostToDevice, ws.stream));
-            CKS(launch_exact(ix, ws, B, QS, Mblk, 1, doff[d0 + nd] - doff[d0], nullptr));
+            CKS(launch_exact(ix, ws, B, QS, Mblk, 1, doff[d0 + nd] - doff[d0], nullptr, nq_max));
             k_exact_finalize<<<dim3((Mblk + 7) / 8, B), 256, 0, ws.stream>>>(ws.maxkey.as<uint32_t>(), ws.qoff.as<int>(), QS,
                                                                            ws.nkept.as<int>(), Mblk, 1, ws.exact.as<float>(),
                                                                            nullptr, nullptr, nullptr, 0u, nullptr);
