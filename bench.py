@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--n-full-scores", type=int, default=4096)
     ap.add_argument("--threshold", type=float, default=0.4)
     ap.add_argument("--recall-queries", type=int, default=8)
-    ap.add_argument("--cpu-queries", type=int, default=2, help="queries in the CPU-baseline sample")
+    ap.add_argument("--cpu-queries", type=int, default=8, help="queries in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--docs-per-topic", type=int, default=1024)
@@ -359,27 +359,44 @@ def run_b200(args):
                                          f"{c_s:.1f} s of wall time (C restatement of the reference, OpenMP)"}
         del hix
 
-    # ---- roofline of the dominant kernel ----
+    # ---- roofline: every stage's algorithmic traffic / CUDA-event time; the headline block is the
+    #      stage with the largest share of the step (DESIGN.md section 4 states the per-unit bytes) ----
     peak, peak_src = measured_peaks()
     kern_stages = {k: v for k, v in stage_ms.items() if k not in ("h2d", "d2h")}
-    dom = max(kern_stages, key=kern_stages.get)
     nq_tot = work.get("n_query_tokens", 0)
     K = 1 << args.log2k
+    packed = args.dim * args.nbits // 8
     alg = {
-        # per candidate token one u32 code + per (query, centroid) one S entry read once
-        "approx": work.get("n_candidate_tokens", 0) * 4 + nq_tot * K * 4,
-        # fused decompress+MaxSim: packed residual + code per token
-        "exact": work.get("n_exact_tokens", 0) * (args.dim * args.nbits // 8 + 4),
-        "centroid_scores": args.steps * K * args.dim * 4 + nq_tot * K * 4,
-        "probe": nq_tot * K * 4, "candidates": 0, "cut": work.get("n_candidates", 0) * 8, "topk": 0,
+        # C read once per launch, fp32 S written once, 16-bit copy written once
+        "centroid_scores": args.steps * K * args.dim * 4 + nq_tot * K * 6,
+        "probe": nq_tot * K * 4,                                   # S streamed once
+        # one u32 code per (candidate, distinct code) + each 16-bit S entry once
+        "approx": work.get("n_candidate_tokens", 0) * 4 + nq_tot * K * 2,
+        "exact": work.get("n_exact_tokens", 0) * (packed + 4),     # packed residual + code per token
+        "cut": work.get("n_candidates", 0) * 8, "candidates": 0, "topk": 0,
     }
-    dom_ms = kern_stages[dom] / max(args.steps, 1)
-    achieved = alg.get(dom, 0) / max(args.steps, 1) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    roof = {"bound": "hbm", "kernel": {"approx": "k_approx", "exact": "k_exact", "centroid_scores": "k_centroid_scores",
-                                       "probe": "k_topn_partial", "cut": "k_cut"}.get(dom, dom),
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "peak_source": peak_src, "ms_per_launch": dom_ms,
-            "algorithmic_bytes_per_launch": alg.get(dom, 0) / max(args.steps, 1)}
+    flops = {"centroid_scores": 2.0 * nq_tot * K * args.dim,
+             "exact": 2.0 * work.get("n_exact_tokens", 0) * args.nq * args.dim}
+    names = {"approx": "k_approx16 (+k_select_u32, k_approx re-check)", "exact": "k_exact", "centroid_scores": "k_centroid_scores",
+             "probe": "k_topn_partial (+merge, k_cells)", "cut": "k_cut", "candidates": "k_mark/k_compact", "topk": "k_topk"}
+    per_stage = {}
+    for st, ms_tot in kern_stages.items():
+        ms1 = ms_tot / max(args.steps, 1)
+        gbs = alg.get(st, 0) / max(args.steps, 1) / (ms1 * 1e-3) / 1e9 if ms1 > 0 else 0.0
+        ent = {"kernel": names.get(st, st), "ms_per_step": ms1, "algorithmic_bytes_per_step": alg.get(st, 0) / max(args.steps, 1),
+               "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+        if st in flops and ms1 > 0:
+            ent["fp32_tflops"] = flops[st] / max(args.steps, 1) / (ms1 * 1e-3) / 1e12
+            ent["frac_of_fp32_fma_peak"] = ent["fp32_tflops"] / 74.4   # 148 SMs x 128 FMA x 2 x 1.965 GHz
+        per_stage[st] = ent
+    dom = max(kern_stages, key=kern_stages.get)
+    d = per_stage[dom]
+    roof = {"bound": "hbm", "kernel": d["kernel"], "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": d["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src, "ms_per_launch": d["ms_per_step"],
+            "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_step"],
+            "note": "k_exact and k_centroid_scores are fp32-FMA bound by design (pinned accumulation order, "
+                    "DESIGN.md Numerics): see fp32_tflops in roofline_all",
+            "fp32_tflops": d.get("fp32_tflops"), "frac_of_fp32_fma_peak": d.get("frac_of_fp32_fma_peak")}
 
     if world > 1:
         tt = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
@@ -395,7 +412,8 @@ def run_b200(args):
         "e2e": {"value": args.batch * args.steps / e2e_s, "unit": "queries/s",
                 "h2d_bytes_per_step": int(flat[0].nbytes + offs.nbytes),
                 "d2h_bytes_per_step": int(h_ids.nbytes + h_sc.nbytes + h_cn.nbytes), "ms_per_step": 1e3 * e2e_s / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_all": per_stage,
+        "cpu_baseline": cpu, "parity": parity,
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
         "work_per_step": {k: v / args.steps for k, v in work.items()},
         "index_build_s": t_build,
