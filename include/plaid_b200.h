@@ -230,6 +230,32 @@ PB_API pb_status pb_search_batch_device(pb_index *ix, const float *d_queries,
                                         const pb_search_params *params, int64_t *d_out_ids,
                                         float *d_out_scores, int32_t *d_out_counts);
 
+/* ---- index-build path (secondary) ----------------------------------------------
+ *
+ * The reference's build-time GPU seams are cuda::compress_into_codes_cuda_batched (cuda.rs:353, called
+ * from codec.rs:265-272) and cuda::compress_and_residuals_cuda_batched (cuda.rs:496, called from
+ * index.rs:318-323) plus third-party k-means (kmeans.rs:125-130).  Here a pb_codec holds the
+ * centroids / cutoffs on the device (ResidualCodec, codec.rs:107-123) and every call is bit-identical
+ * to the CPU implementation (compress_into_codes_cpu, quantize_residuals), including its last-maximum
+ * tie rule -- the reference's own CUDA kernel picks the FIRST maximum (cuda.rs:202).
+ * k-means: fastkmeans-rs is not in the reference tree, so pb_kmeans_fit is parity-unpinned. */
+typedef struct pb_codec pb_codec;
+PB_API pb_status pb_codec_open(int32_t device, const float *centroids, int64_t num_centroids, int32_t dim,
+                               int32_t nbits, const float *bucket_cutoffs /* may be NULL */, pb_codec **out);
+PB_API void pb_codec_close(pb_codec *c);
+/* ResidualCodec::compress_into_codes (codec.rs:260): out_codes[n] i64 */
+PB_API pb_status pb_codec_compress_into_codes(pb_codec *c, const float *embeddings, int64_t n, int64_t *out_codes);
+/* compress_and_residuals (index.rs:17-40 / cuda.rs:496): codes + f32 residuals [n][dim] */
+PB_API pb_status pb_codec_compress_and_residuals(pb_codec *c, const float *embeddings, int64_t n,
+                                                 int64_t *out_codes, float *out_residuals);
+/* encode_index_chunk (index.rs:289-371): codes + packed residuals [n][dim*nbits/8] (quantize_residuals,
+ * codec.rs:356-411) */
+PB_API pb_status pb_codec_encode_chunk(pb_codec *c, const float *embeddings, int64_t n, int64_t *out_codes,
+                                       uint8_t *out_residuals_packed);
+/* compute_kmeans' inner fit + L2 normalisation (kmeans.rs:319-419): out_centroids [K][dim] */
+PB_API pb_status pb_kmeans_fit(int32_t device, const float *samples, int64_t n, int32_t dim, int64_t num_centroids,
+                               int32_t niters, uint64_t seed, float *out_centroids);
+
 /* ---- doc-sharded deployment (no reference analogue: the reference is single-process) ----
  *
  * One process per GPU; shard g holds a contiguous doc-id range (pb_index_desc.doc_id_base) with the

@@ -1255,3 +1255,161 @@ extern "C" pb_status pb_index_comm_init(pb_index *ix, const uint8_t *id128, int3
     ix->world = world;
     return PB_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// index-build path (secondary): ResidualCodec on the device
+// ------------------------------------------------------------------------------------------
+struct pb_codec {
+    int device = 0, dim = 0, nbits = 0, sm_count = 148;
+    long long K = 0;
+    DevBuf centroids, cutoffs;
+    bool has_cutoffs = false;
+};
+
+static size_t smem_assign(int dim) { return (size_t)((dim <= 128 ? 2 : 1) * PB_TOK_TILE + 64) * (dim + 4) * sizeof(float); }
+
+static pb_status launch_assign(int dim, int sm_count, const float *dX, long long n, const float *dC, long long K,
+                               const float *bias, long long *codes64, uint32_t *codes32, cudaStream_t st) {
+    if (n == 0) return PB_OK;
+    (void)sm_count;
+    const unsigned blocks = (unsigned)((n + 63) / 64);
+    PB_DIM_SWITCH(dim, {
+        auto kern = k_assign<DIM>;
+        CKS(set_smem(kern, smem_assign(DIM)));
+        kern<<<blocks, 256, smem_assign(DIM), st>>>(dX, n, dC, K, bias, codes64, codes32);
+    });
+    CK(cudaGetLastError());
+    return PB_OK;
+}
+
+extern "C" pb_status pb_codec_open(int32_t device, const float *centroids, int64_t K, int32_t dim, int32_t nbits,
+                                   const float *bucket_cutoffs, pb_codec **out) {
+    if (!centroids || !out) return pb_fail(PB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (nbits <= 0 || 8 % nbits != 0) return pb_fail(PB_ERR_INVALID, "nbits must be a divisor of 8, got %d", nbits);
+    if (K <= 0 || K >= (1ll << 32) - 1) return pb_fail(PB_ERR_INVALID, "bad num_centroids %lld", (long long)K);
+    if (!dim_supported(dim)) return pb_fail(PB_ERR_UNSUPPORTED, "embedding_dim %d not built (32/64/96/128/256)", dim);
+    CKS(check_device(device));
+    std::unique_ptr<pb_codec> c(new pb_codec());
+    c->device = device;
+    c->dim = dim;
+    c->nbits = nbits;
+    c->K = K;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CKS(upload(c->centroids, centroids, (size_t)K * dim * 4, PB_MEM_HOST));
+    if (bucket_cutoffs) {
+        CKS(upload(c->cutoffs, bucket_cutoffs, (size_t)((1 << nbits) - 1) * 4, PB_MEM_HOST));
+        c->has_cutoffs = true;
+    }
+    *out = c.release();
+    return PB_OK;
+}
+
+extern "C" void pb_codec_close(pb_codec *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    delete c;
+}
+
+// embeddings are processed in slabs so the staging buffers stay bounded
+static pb_status codec_run(pb_codec *c, const float *emb, int64_t n, int64_t *out_codes, uint8_t *out_packed,
+                           float *out_residuals) {
+    if (!c || (!emb && n) || n < 0) return pb_fail(PB_ERR_INVALID, "null argument");
+    if ((out_packed) && !c->has_cutoffs) return pb_fail(PB_ERR_INVALID, "bucket_cutoffs required for quantization");  // codec.rs:359-362
+    CK(cudaSetDevice(c->device));
+    if (n == 0) return PB_OK;
+    const long long slab = 1ll << 20;
+    const int packed = c->dim * c->nbits / 8;
+    DevBuf dX, dcodes, dpk, dres;
+    CKS(dX.ensure((size_t)std::min<long long>(n, slab) * c->dim * 4));
+    CKS(dcodes.ensure((size_t)std::min<long long>(n, slab) * 8));
+    if (out_packed) CKS(dpk.ensure((size_t)std::min<long long>(n, slab) * packed));
+    if (out_residuals) CKS(dres.ensure((size_t)std::min<long long>(n, slab) * c->dim * 4));
+    for (long long o = 0; o < n; o += slab) {
+        const long long m = std::min(slab, n - o);
+        CK(cudaMemcpy(dX.p, emb + (size_t)o * c->dim, (size_t)m * c->dim * 4, cudaMemcpyHostToDevice));
+        CKS(launch_assign(c->dim, c->sm_count, dX.as<float>(), m, c->centroids.as<float>(), c->K, nullptr,
+                          dcodes.as<long long>(), nullptr, 0));
+        if (out_packed || out_residuals) {
+            PB_DIM_SWITCH(c->dim, {
+                k_quantize_pack<DIM><<<c->sm_count * 8, 256>>>(dX.as<float>(), m, c->centroids.as<float>(),
+                                                                dcodes.as<long long>(), c->cutoffs.as<float>(), c->nbits,
+                                                                out_packed ? dpk.as<uint8_t>() : nullptr,
+                                                                out_residuals ? dres.as<float>() : nullptr);
+            });
+            CK(cudaGetLastError());
+        }
+        if (out_codes) CK(cudaMemcpy(out_codes + o, dcodes.p, (size_t)m * 8, cudaMemcpyDeviceToHost));
+        if (out_packed) CK(cudaMemcpy(out_packed + (size_t)o * packed, dpk.p, (size_t)m * packed, cudaMemcpyDeviceToHost));
+        if (out_residuals) CK(cudaMemcpy(out_residuals + (size_t)o * c->dim, dres.p, (size_t)m * c->dim * 4, cudaMemcpyDeviceToHost));
+    }
+    return PB_OK;
+}
+
+extern "C" pb_status pb_codec_compress_into_codes(pb_codec *c, const float *embeddings, int64_t n, int64_t *out_codes) {
+    if (!out_codes && n) return pb_fail(PB_ERR_INVALID, "null argument");
+    return codec_run(c, embeddings, n, out_codes, nullptr, nullptr);
+}
+
+extern "C" pb_status pb_codec_encode_chunk(pb_codec *c, const float *embeddings, int64_t n, int64_t *out_codes,
+                                           uint8_t *out_residuals_packed) {
+    if ((!out_codes || !out_residuals_packed) && n) return pb_fail(PB_ERR_INVALID, "null argument");
+    return codec_run(c, embeddings, n, out_codes, out_residuals_packed, nullptr);
+}
+
+extern "C" pb_status pb_codec_compress_and_residuals(pb_codec *c, const float *embeddings, int64_t n, int64_t *out_codes,
+                                                     float *out_residuals) {
+    if ((!out_codes || !out_residuals) && n) return pb_fail(PB_ERR_INVALID, "null argument");
+    // residuals only need the subtraction: run the pack kernel without a packed output
+    bool had = c && c->has_cutoffs;
+    if (c && !had) {  // the kernel reads ncut cutoffs only when packing; give it a valid (unused) pointer
+        float zero[255] = {0};
+        CKS(upload(c->cutoffs, zero, sizeof zero, PB_MEM_HOST));
+    }
+    return codec_run(c, embeddings, n, out_codes, nullptr, out_residuals);
+}
+
+extern "C" pb_status pb_kmeans_fit(int32_t device, const float *samples, int64_t n, int32_t dim, int64_t K, int32_t niters,
+                                   uint64_t seed, float *out_centroids) {
+    if (!samples || !out_centroids) return pb_fail(PB_ERR_INVALID, "null argument");
+    if (n <= 0 || K <= 0 || K > n) return pb_fail(PB_ERR_INVALID, "need 0 < K <= n (K=%lld, n=%lld)", (long long)K, (long long)n);
+    if (!dim_supported(dim)) return pb_fail(PB_ERR_UNSUPPORTED, "embedding_dim %d not built (32/64/96/128/256)", dim);
+    CKS(check_device(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int sms = prop.multiProcessorCount;
+    DevBuf dX, dC, dbias, dcodes, dsums, dcnt, didx;
+    CKS(upload(dX, samples, (size_t)n * dim * 4, PB_MEM_HOST));
+    CKS(dC.ensure((size_t)K * dim * 4));
+    CKS(dbias.ensure((size_t)K * 4));
+    CKS(dcodes.ensure((size_t)n * 4));
+    CKS(dsums.ensure((size_t)K * dim * 4));
+    CKS(dcnt.ensure((size_t)K * 4));
+    // initial centroids: K distinct sample points (partial Fisher-Yates with a 64-bit LCG)
+    std::vector<long long> perm((size_t)n);
+    for (long long i = 0; i < n; ++i) perm[i] = i;
+    uint64_t s = seed * 6364136223846793005ull + 1442695040888963407ull;
+    for (long long i = 0; i < K; ++i) {
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        long long j = i + (long long)((s >> 11) % (uint64_t)(n - i));
+        std::swap(perm[i], perm[j]);
+    }
+    CKS(upload(didx, perm.data(), (size_t)K * 8, PB_MEM_HOST));
+    k_gather_rows<<<sms * 4, 256>>>(dX.as<float>(), didx.as<long long>(), K, dim, dC.as<float>());
+    CK(cudaGetLastError());
+    for (int it = 0; it < niters; ++it) {
+        k_half_sqnorm<<<sms * 4, 256>>>(dC.as<float>(), K, dim, dbias.as<float>());
+        CKS(launch_assign(dim, sms, dX.as<float>(), n, dC.as<float>(), K, dbias.as<float>(), nullptr, dcodes.as<uint32_t>(), 0));
+        CK(cudaMemset(dsums.p, 0, (size_t)K * dim * 4));
+        CK(cudaMemset(dcnt.p, 0, (size_t)K * 4));
+        k_accumulate<<<sms * 8, 256>>>(dX.as<float>(), n, dim, dcodes.as<uint32_t>(), dsums.as<float>(), dcnt.as<float>());
+        k_update_centroids<<<sms * 4, 256>>>(dC.as<float>(), K, dim, dsums.as<float>(), dcnt.as<float>());
+        CK(cudaGetLastError());
+    }
+    k_normalize_rows<<<sms * 4, 256>>>(dC.as<float>(), K, dim);  // kmeans.rs:415-419
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out_centroids, dC.p, (size_t)K * dim * 4, cudaMemcpyDeviceToHost));
+    return PB_OK;
+}

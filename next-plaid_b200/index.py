@@ -75,6 +75,8 @@ EXPORTS = [
     "pb_maxsim_scores", "pb_exhaustive_scores", "pb_set_profiling", "pb_last_stage_stats",
     "pb_last_work_counters", "pb_search_batch_device", "pb_last_error", "pb_version",
     "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init", "pb_set_fast_approx",
+    "pb_codec_open", "pb_codec_close", "pb_codec_compress_into_codes", "pb_codec_compress_and_residuals",
+    "pb_codec_encode_chunk", "pb_kmeans_fit",
 ]
 
 _lib = None
@@ -119,6 +121,15 @@ def load_library():
         L.pb_exhaustive_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.pb_last_stage_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pb_last_work_counters.argtypes = [C.c_void_p, C.POINTER(_Work)]
+        L.pb_codec_open.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                    C.POINTER(C.c_void_p)]
+        L.pb_codec_close.argtypes = [C.c_void_p]
+        L.pb_codec_close.restype = None
+        L.pb_codec_compress_into_codes.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.pb_codec_compress_and_residuals.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.pb_codec_encode_chunk.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.pb_kmeans_fit.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_uint64,
+                                    C.c_void_p]
         L.pb_comm_unique_id.argtypes = [C.c_void_p]
         L.pb_index_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         _lib = L
@@ -392,4 +403,59 @@ def maxsim_scores(query: np.ndarray, docs: Sequence[np.ndarray], device: int = 0
     out = np.zeros(len(docs), np.float32)
     _check(load_library().pb_maxsim_scores(device, _ptr(q), q.shape[0], q.shape[1], _ptr(flat), _ptr(offs),
                                            len(docs), _ptr(out)))
+    return out
+
+
+class ResidualCodec:
+    """Device-resident next_plaid::ResidualCodec (codec.rs:107-123) for the index-build path."""
+
+    def __init__(self, nbits: int, centroids: np.ndarray, bucket_cutoffs: Optional[np.ndarray] = None,
+                 device: int = 0):
+        cen = np.ascontiguousarray(centroids, np.float32)
+        cut = None if bucket_cutoffs is None else np.ascontiguousarray(bucket_cutoffs, np.float32)
+        h = C.c_void_p()
+        _check(load_library().pb_codec_open(device, _ptr(cen), cen.shape[0], cen.shape[1], nbits, _ptr(cut),
+                                            C.byref(h)))
+        self._h, self.nbits, self.dim = h, nbits, cen.shape[1]
+
+    def close(self):
+        if self._h:
+            load_library().pb_codec_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compress_into_codes(self, embeddings: np.ndarray) -> np.ndarray:
+        """codec.rs:260."""
+        e = np.ascontiguousarray(embeddings, np.float32)
+        out = np.zeros(e.shape[0], np.int64)
+        _check(load_library().pb_codec_compress_into_codes(self._h, _ptr(e), e.shape[0], _ptr(out)))
+        return out
+
+    def compress_and_residuals(self, embeddings: np.ndarray):
+        """index.rs:17-40."""
+        e = np.ascontiguousarray(embeddings, np.float32)
+        codes = np.zeros(e.shape[0], np.int64)
+        res = np.zeros_like(e)
+        _check(load_library().pb_codec_compress_and_residuals(self._h, _ptr(e), e.shape[0], _ptr(codes), _ptr(res)))
+        return codes, res
+
+    def encode_chunk(self, embeddings: np.ndarray):
+        """encode_index_chunk (index.rs:289): (codes i64 [n], packed residuals u8 [n, dim*nbits/8])."""
+        e = np.ascontiguousarray(embeddings, np.float32)
+        codes = np.zeros(e.shape[0], np.int64)
+        packed = np.zeros((e.shape[0], self.dim * self.nbits // 8), np.uint8)
+        _check(load_library().pb_codec_encode_chunk(self._h, _ptr(e), e.shape[0], _ptr(codes), _ptr(packed)))
+        return codes, packed
+
+
+def kmeans_fit(samples: np.ndarray, num_centroids: int, niters: int = 4, seed: int = 42, device: int = 0) -> np.ndarray:
+    """The fit inside compute_kmeans (kmeans.rs:319-419): Lloyd iterations + L2 normalisation."""
+    x = np.ascontiguousarray(samples, np.float32)
+    out = np.zeros((num_centroids, x.shape[1]), np.float32)
+    _check(load_library().pb_kmeans_fit(device, _ptr(x), x.shape[0], x.shape[1], num_centroids, niters, seed, _ptr(out)))
     return out

@@ -1,0 +1,107 @@
+"""Index-build path on the GPU: nearest-centroid codes and packed residuals are
+bit-identical to the CPU oracle (compress_into_codes_cpu codec.rs:297, quantize_residuals codec.rs:356);
+k-means is parity-unpinned (fastkmeans-rs is not in the reference tree) and checked statistically."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def npb():
+    import next_plaid_b200 as m
+    m.build_library()
+    if m.device_count() < 1:
+        pytest.fail("GPU tests need a B200; the library has no CPU fallback")
+    return m
+
+
+def test_codec_kats_on_gpu(npb):
+    # maxsim.rs:444-477 -> [0,1,2,0,2]; codec.rs:637-663 -> [0,2]; codec.rs:733-752 NaN centroid -> 1;
+    # last maximum wins exact ties (codec.rs:329-337)
+    def pad(a, d=32):
+        out = np.zeros((a.shape[0], d), np.float32); out[:, :a.shape[1]] = a; return out
+    c = pad(np.eye(3, 4, dtype=np.float32))
+    e = pad(np.array([[0.9, 0.1, 0, 0], [0.1, 0.9, 0, 0], [0, 0.1, 0.9, 0], [0.8, 0.2, 0, 0], [0, 0, 0.8, 0.2]], np.float32))
+    assert npb.ResidualCodec(2, c).compress_into_codes(e).tolist() == [0, 1, 2, 0, 2]
+    e2 = pad(np.array([[0.9, 0.1, 0, 0], [0, 0, 0.95, 0.05]], np.float32))
+    assert npb.ResidualCodec(2, c).compress_into_codes(e2).tolist() == [0, 2]
+    cn = pad(np.array([[np.nan, 0], [1, 0], [0, 1]], np.float32))
+    assert npb.ResidualCodec(2, cn).compress_into_codes(pad(np.array([[1, 0]], np.float32))).tolist() == [1]
+    ct = pad(np.array([[1, 0], [1, 0], [0, 1]], np.float32))
+    assert npb.ResidualCodec(2, ct).compress_into_codes(pad(np.array([[1, 0]], np.float32))).tolist() == [1]
+
+
+@pytest.mark.parametrize("dim,nbits,K", [(128, 4, 300), (128, 2, 1024), (64, 8, 77), (96, 1, 130), (32, 4, 64), (256, 4, 200)])
+def test_encode_chunk_bit_exact(oracle, npb, dim, nbits, K):
+    rng = np.random.default_rng(dim + nbits)
+    cent = rng.standard_normal((K, dim)).astype(np.float32)
+    cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+    cent[K // 2] = cent[3]                        # exact duplicate centroid: the LAST one must win
+    emb = cent[rng.integers(0, K, 1500)] + 0.3 * rng.standard_normal((1500, dim)).astype(np.float32) / np.sqrt(dim)
+    emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+    emb[7] = cent[3]
+    want_codes = oracle.compress_into_codes(emb, cent)
+    res = oracle.residuals_of(emb, cent, want_codes)
+    n_opt = 1 << nbits
+    cut = oracle.quantiles(res.ravel(), [i / n_opt for i in range(1, n_opt)])
+    want_packed = oracle.quantize_residuals(res, cut, nbits)
+    codec = npb.ResidualCodec(nbits, cent, cut)
+    codes, packed = codec.encode_chunk(emb)
+    assert codes.tolist() == want_codes.tolist()
+    assert codes[7] == max(3, K // 2)
+    assert np.array_equal(packed, want_packed)
+    c2, r2 = codec.compress_and_residuals(emb)
+    assert c2.tolist() == want_codes.tolist() and np.array_equal(r2, res)
+    assert codec.compress_into_codes(np.zeros((0, dim), np.float32)).shape == (0,)
+    codec.close()
+
+
+def test_codec_argument_errors(npb):
+    with pytest.raises(npb.PlaidError) as e:
+        npb.ResidualCodec(3, np.zeros((4, 32), np.float32))
+    assert "divisor of 8" in str(e.value)                       # codec.rs:161-166
+    codec = npb.ResidualCodec(4, np.eye(4, 32, dtype=np.float32))
+    with pytest.raises(npb.PlaidError) as e:
+        codec.encode_chunk(np.zeros((2, 32), np.float32))
+    assert "bucket_cutoffs required" in str(e.value)            # codec.rs:359-362
+
+
+def test_kmeans_fit_shape_norm_and_quality(oracle, npb):
+    # kmeans.rs:461-534 pins shape and unit norm only; add: better than random centroids
+    docs = oracle.synthetic_corpus(800, 32, dim=64, seed=3)
+    x = np.concatenate(docs, 0)
+    K = 256
+    cent = npb.kmeans_fit(x, K, niters=4, seed=42)
+    assert cent.shape == (K, 64)
+    assert np.allclose(np.linalg.norm(cent, axis=1), 1.0, atol=1e-5)
+    rng = np.random.default_rng(0)
+    rnd = rng.standard_normal((K, 64)).astype(np.float32)
+    rnd /= np.linalg.norm(rnd, axis=1, keepdims=True)
+    fit = (x @ cent.T).max(1).mean()
+    base = (x @ rnd.T).max(1).mean()
+    ref = (x @ oracle.kmeans(x, K, 4, 42).T).max(1).mean()
+    assert fit > base + 0.2 and fit > ref - 0.03
+
+
+def test_gpu_built_index_serves_searches(oracle, npb):
+    # create_with_kmeans (index.rs:1392) with the numeric steps on the GPU, then search it
+    docs = oracle.synthetic_corpus(1200, 32, dim=128, seed=13, ragged=True)
+    x = np.concatenate(docs, 0)
+    cent = npb.kmeans_fit(x, 256, niters=4, seed=42)
+    art = oracle.prepare_codec_artifacts(docs, cent, 4, seed=42)     # quantiles of the held-out residuals (host)
+    codec = npb.ResidualCodec(4, cent, art.bucket_cutoffs)
+    codes, packed = codec.encode_chunk(x)
+    doclens = np.array([d.shape[0] for d in docs], np.int64)
+    ivf, ivf_lengths = oracle.build_ivf(codes, doclens, 256)
+    ix = oracle.Index(cent, art.bucket_weights, art.bucket_cutoffs, codes, packed, doclens, ivf, ivf_lengths, 4)
+    gpu = npb.MmapIndex.from_arrays(cent, art.bucket_weights, codes, packed, doclens, ivf, ivf_lengths, 4)
+    qs, src = oracle.synthetic_queries(docs, 8, nq=32, seed=1)
+    pg = npb.SearchParameters(top_k=5, n_full_scores=256)
+    po = oracle.SearchParameters(top_k=5, n_full_scores=256)
+    hits = 0
+    for q, s, r in zip(qs, src, gpu.search_batch(qs, pg)):
+        w = oracle.search_one(ix, q, po)
+        assert r.passage_ids.tolist() == w.passage_ids.tolist() and np.array_equal(r.scores, w.scores)
+        hits += int(len(r.passage_ids) and r.passage_ids[0] == s)
+    assert hits >= 7
