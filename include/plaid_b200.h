@@ -243,6 +243,11 @@ typedef struct pb_codec pb_codec;
 PB_API pb_status pb_codec_open(int32_t device, const float *centroids, int64_t num_centroids, int32_t dim,
                                int32_t nbits, const float *bucket_cutoffs /* may be NULL */, pb_codec **out);
 PB_API void pb_codec_close(pb_codec *c);
+/* How the last compress/encode call found its codes: tokens whose argmax the tcgen05 shortlist certified
+ * vs tokens sent through the exact fp32 kernel (all of them when the filter is not in use: dim not in
+ * {64, 96, 128}, K < 256, or PB_ASSIGN_EXACT set). */
+PB_API pb_status pb_codec_last_assign_stats(pb_codec *c, int64_t *n_tokens, int64_t *n_exact_fallback,
+                                            int32_t *used_tensor_cores);
 /* ResidualCodec::compress_into_codes (codec.rs:260): out_codes[n] i64 */
 PB_API pb_status pb_codec_compress_into_codes(pb_codec *c, const float *embeddings, int64_t n, int64_t *out_codes);
 /* compress_and_residuals (index.rs:17-40 / cuda.rs:496): codes + f32 residuals [n][dim] */

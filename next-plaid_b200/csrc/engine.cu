@@ -1262,9 +1262,17 @@ extern "C" pb_status pb_index_comm_init(pb_index *ix, const uint8_t *id128, int3
 struct pb_codec {
     int device = 0, dim = 0, nbits = 0, sm_count = 148;
     long long K = 0;
-    DevBuf centroids, cutoffs;
+    DevBuf centroids, cutoffs, cent_bf16, cent_norm;
     bool has_cutoffs = false;
+    bool use_tc = false;   // tcgen05 certified filter in front of the exact assignment
+    float cmax = 0.f;
+    int c_finite = 1;
+    long long last_tokens = 0, last_fallback = 0;
 };
+
+static size_t smem_assign_tc(int dim) {
+    return (size_t)PB_TC_M * dim * 2 + (size_t)PB_TC_STAGES * PB_TC_N * dim * 2 + (2 * PB_TC_STAGES + 4) * 8 + 16;
+}
 
 static size_t smem_assign(int dim) { return (size_t)((dim <= 128 ? 2 : 1) * PB_TOK_TILE + 64) * (dim + 4) * sizeof(float); }
 
@@ -1303,7 +1311,83 @@ extern "C" pb_status pb_codec_open(int32_t device, const float *centroids, int64
         CKS(upload(c->cutoffs, bucket_cutoffs, (size_t)((1 << nbits) - 1) * 4, PB_MEM_HOST));
         c->has_cutoffs = true;
     }
+    // tensor-core filter: bf16 copy of the centroids, their largest norm, finiteness
+    c->use_tc = (dim == 64 || dim == 96 || dim == 128) && K >= PB_TC_N && !getenv("PB_ASSIGN_EXACT") &&
+                smem_assign_tc(dim) <= 227 * 1024;
+    if (c->use_tc) {
+        CKS(c->cent_bf16.ensure((size_t)K * dim * 2));
+        CKS(c->cent_norm.ensure((size_t)K * 4));
+        k_rows_to_bf16<<<c->sm_count * 8, 256>>>(c->centroids.as<float>(), K, dim, c->cent_bf16.as<__nv_bfloat16>(),
+                                                 c->cent_norm.as<float>());
+        CK(cudaGetLastError());
+        std::vector<float> nr((size_t)K);
+        CK(cudaMemcpy(nr.data(), c->cent_norm.p, (size_t)K * 4, cudaMemcpyDeviceToHost));
+        float mx = 0.f;
+        for (float v : nr) {
+            if (!(v < 1e18f)) c->c_finite = 0;
+            else mx = std::max(mx, v);
+        }
+        c->cmax = mx;
+    }
     *out = c.release();
+    return PB_OK;
+}
+
+extern "C" pb_status pb_codec_last_assign_stats(pb_codec *c, int64_t *n_tokens, int64_t *n_exact_fallback, int32_t *used_tensor_cores) {
+    if (!c) return pb_fail(PB_ERR_INVALID, "null argument");
+    if (n_tokens) *n_tokens = c->last_tokens;
+    if (n_exact_fallback) *n_exact_fallback = c->last_fallback;
+    if (used_tensor_cores) *used_tensor_cores = c->use_tc ? 1 : 0;
+    return PB_OK;
+}
+
+// nearest-centroid codes of m device-resident rows: tensor-core shortlist + certified exact re-score,
+// exact kernel for whatever cannot be certified
+static pb_status assign_codes(pb_codec *c, const float *dX, long long m, long long *dcodes) {
+    if (!c->use_tc) {
+        c->last_fallback += m;
+        return launch_assign(c->dim, c->sm_count, dX, m, c->centroids.as<float>(), c->K, nullptr, dcodes, nullptr, 0);
+    }
+    DevBuf xb, xn, ts, ti, nfb, fl;
+    CKS(xb.ensure((size_t)m * c->dim * 2));
+    CKS(xn.ensure((size_t)m * 4));
+    CKS(ts.ensure((size_t)m * 16));
+    CKS(ti.ensure((size_t)m * 16));
+    CKS(nfb.ensure(16));
+    CKS(fl.ensure((size_t)m * 8));
+    CK(cudaMemset(nfb.p, 0, 4));
+    k_rows_to_bf16<<<c->sm_count * 8, 256>>>(dX, m, c->dim, xb.as<__nv_bfloat16>(), xn.as<float>());
+    const unsigned blocks = (unsigned)((m + PB_TC_M - 1) / PB_TC_M);
+    const size_t sm = smem_assign_tc(c->dim);
+    switch (c->dim) {
+#define PB_TC_CASE(DV)                                                                                     \
+    case DV: {                                                                                             \
+        auto kern = k_assign_tc<DV>;                                                                       \
+        CKS(set_smem(kern, sm));                                                                           \
+        kern<<<blocks, 192, sm>>>(xb.as<__nv_bfloat16>(), m, c->cent_bf16.as<__nv_bfloat16>(), c->K, ts.as<float>(), \
+                                  ti.as<uint32_t>());                                                      \
+    } break;
+        PB_TC_CASE(64) PB_TC_CASE(96) PB_TC_CASE(128)
+#undef PB_TC_CASE
+        default: return pb_fail(PB_ERR_UNSUPPORTED, "tensor-core assignment not built for dim %d", c->dim);
+    }
+    CK(cudaGetLastError());
+    k_assign_certify<<<c->sm_count * 8, 256>>>(dX, m, c->dim, c->centroids.as<float>(), xn.as<float>(), c->cmax, c->c_finite,
+                                               ts.as<float>(), ti.as<uint32_t>(), dcodes, nfb.as<int>(), fl.as<long long>());
+    CK(cudaGetLastError());
+    int nf = 0;
+    CK(cudaMemcpy(&nf, nfb.p, 4, cudaMemcpyDeviceToHost));
+    c->last_fallback += nf;
+    if (nf > 0) {
+        DevBuf gx, gc;
+        CKS(gx.ensure((size_t)nf * c->dim * 4));
+        CKS(gc.ensure((size_t)nf * 8));
+        k_gather_rows_i64<<<c->sm_count * 8, 256>>>(dX, fl.as<long long>(), nf, c->dim, gx.as<float>());
+        CKS(launch_assign(c->dim, c->sm_count, gx.as<float>(), nf, c->centroids.as<float>(), c->K, nullptr, gc.as<long long>(),
+                          nullptr, 0));
+        k_scatter_codes<<<(nf + 255) / 256, 256>>>(gc.as<long long>(), fl.as<long long>(), nf, dcodes);
+        CK(cudaGetLastError());
+    }
     return PB_OK;
 }
 
@@ -1322,6 +1406,8 @@ static pb_status codec_run(pb_codec *c, const float *emb, int64_t n, int64_t *ou
     if (n == 0) return PB_OK;
     const long long slab = 1ll << 20;
     const int packed = c->dim * c->nbits / 8;
+    c->last_tokens = n;
+    c->last_fallback = 0;
     DevBuf dX, dcodes, dpk, dres;
     CKS(dX.ensure((size_t)std::min<long long>(n, slab) * c->dim * 4));
     CKS(dcodes.ensure((size_t)std::min<long long>(n, slab) * 8));
@@ -1330,8 +1416,7 @@ static pb_status codec_run(pb_codec *c, const float *emb, int64_t n, int64_t *ou
     for (long long o = 0; o < n; o += slab) {
         const long long m = std::min(slab, n - o);
         CK(cudaMemcpy(dX.p, emb + (size_t)o * c->dim, (size_t)m * c->dim * 4, cudaMemcpyHostToDevice));
-        CKS(launch_assign(c->dim, c->sm_count, dX.as<float>(), m, c->centroids.as<float>(), c->K, nullptr,
-                          dcodes.as<long long>(), nullptr, 0));
+        CKS(assign_codes(c, dX.as<float>(), m, dcodes.as<long long>()));
         if (out_packed || out_residuals) {
             PB_DIM_SWITCH(c->dim, {
                 k_quantize_pack<DIM><<<c->sm_count * 8, 256>>>(dX.as<float>(), m, c->centroids.as<float>(),

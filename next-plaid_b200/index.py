@@ -76,7 +76,7 @@ EXPORTS = [
     "pb_last_work_counters", "pb_search_batch_device", "pb_last_error", "pb_version",
     "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init", "pb_set_fast_approx",
     "pb_codec_open", "pb_codec_close", "pb_codec_compress_into_codes", "pb_codec_compress_and_residuals",
-    "pb_codec_encode_chunk", "pb_kmeans_fit",
+    "pb_codec_encode_chunk", "pb_kmeans_fit", "pb_codec_last_assign_stats",
 ]
 
 _lib = None
@@ -125,6 +125,7 @@ def load_library():
                                     C.POINTER(C.c_void_p)]
         L.pb_codec_close.argtypes = [C.c_void_p]
         L.pb_codec_close.restype = None
+        L.pb_codec_last_assign_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pb_codec_compress_into_codes.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.pb_codec_compress_and_residuals.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.pb_codec_encode_chunk.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
@@ -428,6 +429,11 @@ class ResidualCodec:
             self.close()
         except Exception:
             pass
+
+    def last_assign_stats(self) -> dict:
+        n, f, tc = C.c_int64(), C.c_int64(), C.c_int32()
+        _check(load_library().pb_codec_last_assign_stats(self._h, C.byref(n), C.byref(f), C.byref(tc)))
+        return {"tokens": n.value, "exact_fallback": f.value, "tensor_cores": bool(tc.value)}
 
     def compress_into_codes(self, embeddings: np.ndarray) -> np.ndarray:
         """codec.rs:260."""

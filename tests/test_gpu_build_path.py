@@ -48,6 +48,11 @@ def test_encode_chunk_bit_exact(oracle, npb, dim, nbits, K):
     want_packed = oracle.quantize_residuals(res, cut, nbits)
     codec = npb.ResidualCodec(nbits, cent, cut)
     codes, packed = codec.encode_chunk(emb)
+    st = codec.last_assign_stats()
+    assert st["tokens"] == 1500
+    assert st["tensor_cores"] == (dim in (64, 96, 128) and K >= 256)
+    if st["tensor_cores"]:
+        assert st["exact_fallback"] < 150, st     # the certified tcgen05 shortlist decides >90 % of the tokens
     assert codes.tolist() == want_codes.tolist()
     assert codes[7] == max(3, K // 2)
     assert np.array_equal(packed, want_packed)
@@ -105,3 +110,28 @@ def test_gpu_built_index_serves_searches(oracle, npb):
         assert r.passage_ids.tolist() == w.passage_ids.tolist() and np.array_equal(r.scores, w.scores)
         hits += int(len(r.passage_ids) and r.passage_ids[0] == s)
     assert hits >= 7
+
+
+def test_tensor_core_filter_is_exact_on_hard_inputs(oracle, npb):
+    # near ties inside the bf16 error band, duplicated centroids, non-unit norms and a NaN token:
+    # whatever the tcgen05 shortlist cannot certify must fall back to the exact kernel
+    rng = np.random.default_rng(7)
+    K, dim = 2048, 128
+    cent = rng.standard_normal((K, dim)).astype(np.float32)
+    cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+    cent[1000:1016] = cent[5] + 1e-4 * rng.standard_normal((16, dim)).astype(np.float32)   # a tight cluster
+    cent[1500] = cent[7]                                                                  # exact duplicate
+    cent[1600:1700] *= 3.0                                                                # non-unit norms
+    emb = cent[rng.integers(0, K, 4000)] + 0.2 * rng.standard_normal((4000, dim)).astype(np.float32) / np.sqrt(dim)
+    emb[:300] = cent[5] + 1e-3 * rng.standard_normal((300, dim)).astype(np.float32)        # all land in the cluster
+    emb[300:320] = cent[7]
+    emb[320] = np.nan
+    emb[321] *= 1e-6
+    emb[322] *= 1e4
+    want = oracle.compress_into_codes(emb, cent)
+    codec = npb.ResidualCodec(4, cent)
+    got = codec.compress_into_codes(emb)
+    st = codec.last_assign_stats()
+    assert st["tensor_cores"] and 300 <= st["exact_fallback"] < 1200, st
+    assert got.tolist() == want.tolist()
+    assert got[300] == 1500
