@@ -1271,7 +1271,7 @@ struct pb_codec {
 };
 
 static size_t smem_assign_tc(int dim) {
-    return (size_t)PB_TC_M * dim * 2 + (size_t)PB_TC_STAGES * PB_TC_N * dim * 2 + (2 * PB_TC_STAGES + 4) * 8 + 16;
+    return (size_t)2 * PB_TC_M * dim * 2 + (size_t)PB_TC_STAGES * PB_TC_N * dim * 2 + (2 * PB_TC_STAGES + 4) * 8 + 16;
 }
 
 static size_t smem_assign(int dim) { return (size_t)((dim <= 128 ? 2 : 1) * PB_TOK_TILE + 64) * (dim + 4) * sizeof(float); }
@@ -1312,7 +1312,7 @@ extern "C" pb_status pb_codec_open(int32_t device, const float *centroids, int64
         c->has_cutoffs = true;
     }
     // tensor-core filter: bf16 copy of the centroids, their largest norm, finiteness
-    c->use_tc = (dim == 64 || dim == 96 || dim == 128) && K >= PB_TC_N && !getenv("PB_ASSIGN_EXACT") &&
+    c->use_tc = (dim == 64 || dim == 96 || dim == 128) && K >= 256 && !getenv("PB_ASSIGN_EXACT") &&
                 smem_assign_tc(dim) <= 227 * 1024;
     if (c->use_tc) {
         CKS(c->cent_bf16.ensure((size_t)K * dim * 2));
@@ -1357,14 +1357,14 @@ static pb_status assign_codes(pb_codec *c, const float *dX, long long m, long lo
     CKS(fl.ensure((size_t)m * 8));
     CK(cudaMemset(nfb.p, 0, 4));
     k_rows_to_bf16<<<c->sm_count * 8, 256>>>(dX, m, c->dim, xb.as<__nv_bfloat16>(), xn.as<float>());
-    const unsigned blocks = (unsigned)((m + PB_TC_M - 1) / PB_TC_M);
+    const unsigned blocks = (unsigned)((m + 2 * PB_TC_M - 1) / (2 * PB_TC_M));
     const size_t sm = smem_assign_tc(c->dim);
     switch (c->dim) {
 #define PB_TC_CASE(DV)                                                                                     \
     case DV: {                                                                                             \
         auto kern = k_assign_tc<DV>;                                                                       \
         CKS(set_smem(kern, sm));                                                                           \
-        kern<<<blocks, 192, sm>>>(xb.as<__nv_bfloat16>(), m, c->cent_bf16.as<__nv_bfloat16>(), c->K, ts.as<float>(), \
+        kern<<<blocks, 320, sm>>>(xb.as<__nv_bfloat16>(), m, c->cent_bf16.as<__nv_bfloat16>(), c->K, ts.as<float>(), \
                                   ti.as<uint32_t>());                                                      \
     } break;
         PB_TC_CASE(64) PB_TC_CASE(96) PB_TC_CASE(128)
