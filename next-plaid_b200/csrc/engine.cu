@@ -1271,7 +1271,7 @@ struct pb_codec {
 };
 
 static size_t smem_assign_tc(int dim) {
-    return (size_t)2 * PB_TC_M * dim * 2 + (size_t)PB_TC_STAGES * PB_TC_N * dim * 2 + (2 * PB_TC_STAGES + 4) * 8 + 16;
+    return (size_t)2 * PB_TC_M * dim * 2 + (size_t)PB_TC_STAGES * PB_TC_N * dim * 2 + (2 * PB_TC_STAGES + 5) * 8 + 16;
 }
 
 static size_t smem_assign(int dim) { return (size_t)((dim <= 128 ? 2 : 1) * PB_TOK_TILE + 64) * (dim + 4) * sizeof(float); }
@@ -1315,7 +1315,9 @@ extern "C" pb_status pb_codec_open(int32_t device, const float *centroids, int64
     c->use_tc = (dim == 64 || dim == 96 || dim == 128) && K >= 256 && !getenv("PB_ASSIGN_EXACT") &&
                 smem_assign_tc(dim) <= 227 * 1024;
     if (c->use_tc) {
-        CKS(c->cent_bf16.ensure((size_t)K * dim * 2));
+        const size_t kpad = (size_t)((K + 127) / 128) * 128;  // tile order, zero padded
+        CKS(c->cent_bf16.ensure(kpad * dim * 2));
+        CK(cudaMemset(c->cent_bf16.p, 0, kpad * dim * 2));
         CKS(c->cent_norm.ensure((size_t)K * 4));
         k_rows_to_bf16<<<c->sm_count * 8, 256>>>(c->centroids.as<float>(), K, dim, c->cent_bf16.as<__nv_bfloat16>(),
                                                  c->cent_norm.as<float>());
@@ -1349,7 +1351,9 @@ static pb_status assign_codes(pb_codec *c, const float *dX, long long m, long lo
         return launch_assign(c->dim, c->sm_count, dX, m, c->centroids.as<float>(), c->K, nullptr, dcodes, nullptr, 0);
     }
     DevBuf xb, xn, ts, ti, nfb, fl;
-    CKS(xb.ensure((size_t)m * c->dim * 2));
+    const size_t mpad = (size_t)((m + 255) / 256) * 256;  // two 128-token tiles per CTA, zero padded
+    CKS(xb.ensure(mpad * c->dim * 2));
+    CK(cudaMemset(xb.p, 0, mpad * c->dim * 2));
     CKS(xn.ensure((size_t)m * 4));
     CKS(ts.ensure((size_t)m * 16));
     CKS(ti.ensure((size_t)m * 16));
