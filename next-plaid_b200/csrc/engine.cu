@@ -171,7 +171,7 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
-        exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2, cand3, ncand3, ub, theta, rel,
+        exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2, cand3, ncand3, ub, theta, rel, cellbits,
         gkeys, krank, payload, gfkeys, gpayload;
     HostBuf hq, hres, hcounts;
     pb_status init() {
@@ -181,6 +181,7 @@ struct Workspace {
         maxkey.zero_on_grow = true;
         subset_bits.zero_on_grow = true;
         elig.zero_on_grow = true;
+        cellbits.zero_on_grow = true;
         return PB_OK;
     }
     ~Workspace() {
@@ -660,14 +661,17 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             else n_probe = (int)scaled;
         }
     }
-    if (!all_eligible && n_probe > 64)
-        return pb_fail(PB_ERR_UNSUPPORTED, "effective n_ivf_probe %d exceeds this build's limit of 64", n_probe);
+    // effective n_ivf_probe beyond the streaming lists: row-wise radix select (dense variant only; the
+    // batched variant's heap-order threshold rule is tied to the streaming formulation)
+    const bool big_probe = !all_eligible && n_probe > 64;
+    if (big_probe && batched)
+        return pb_fail(PB_ERR_UNSUPPORTED, "n_ivf_probe %d > 64 with the batched variant is not built", n_probe);
 
     // ---- sub-batching: bound the transposed score matrix ----
     int nq_max_all = 0;
     for (int64_t b = 0; b < Bt; ++b) nq_max_all = std::max<int>(nq_max_all, (int)(io.q_off[b + 1] - io.q_off[b]));
     const int QS_all = std::max(8, (nq_max_all + 7) & ~7);
-    if (!all_eligible && (long long)QS_all * n_probe > 8192)
+    if (!all_eligible && !big_probe && (long long)QS_all * n_probe > 8192)
         return pb_fail(PB_ERR_UNSUPPORTED, "query tokens x n_ivf_probe = %lld exceeds 8192", (long long)QS_all * n_probe);
     size_t per_q = (size_t)ix->K * QS_all * sizeof(float);
     if (per_q >= ((size_t)1 << 32))
@@ -734,6 +738,19 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
                                                           ws.qoff.as<int>(), ix->K, QS, p->has_centroid_score_threshold,
                                                           p->centroid_score_threshold, cells_cap, ws.cells.as<uint32_t>(),
                                                           ws.ncells.as<int>());
+            CK(cudaGetLastError());
+            L[PB_STAGE_PROBE] += 2;
+        } else if (big_probe) {
+            cells_cap = (int)std::min<long long>((long long)QS * n_probe, ix->K);
+            CKS(ws.cellbits.ensure((size_t)B * Wk * 4));
+            CKS(ws.cells.ensure((size_t)B * cells_cap * 4));
+            CKS(ws.ncells.ensure((size_t)B * 4 + 16));
+            k_topn_select_row<<<dim3(QS, B), 256, 0, ws.stream>>>(ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, n_probe,
+                                                                  d_elig, ws.cellbits.as<uint32_t>(), Wk);
+            k_cells_from_query_bits<<<B, 1024, 0, ws.stream>>>(ws.cellbits.as<uint32_t>(), Wk, ws.ST.as<float>(),
+                                                               ws.qoff.as<int>(), ix->K, QS, p->has_centroid_score_threshold,
+                                                               p->centroid_score_threshold, cells_cap, ws.cells.as<uint32_t>(),
+                                                               ws.ncells.as<int>());
             CK(cudaGetLastError());
             L[PB_STAGE_PROBE] += 2;
         } else {

@@ -140,6 +140,7 @@ def test_subset_prefilter(oracle, npb, corpus):
     docs, ix, qs, src, gpu = corpus
     rng = np.random.default_rng(0)
     subsets = [list(range(0, 3000, 2)),                      # 50% -> scaled probe 16
+               list(range(0, 3000, 20)),                     # 5% -> scaled probe 160 (row-wise radix select)
                sorted(rng.choice(3000, 40, replace=False)),  # tiny -> every eligible centroid
                [5, 5, 17, 10 ** 7, -3],                      # duplicates and out-of-range ids
                []]
@@ -165,8 +166,8 @@ def test_edge_cases(oracle, npb, corpus):
         w = oracle.search_one(ix, q, po)
         assert len(r.passage_ids) == len(w.passage_ids) <= 64
         assert r.passage_ids.tolist() == w.passage_ids.tolist()
-    # n_ivf_probe = 1 and 64
-    for n in (1, 64):
+    # n_ivf_probe = 1, 64 and (dense variant only) beyond the streaming lists
+    for n in (1, 64, 100, 600):
         pg, po = _params(npb, oracle, top_k=10, n_ivf_probe=n, n_full_scores=128)
         for q, r in zip(qs[:3], gpu.search_batch(qs[:3], pg)):
             w = oracle.search_one(ix, q, po)
@@ -273,3 +274,18 @@ def test_two_pass_approx_with_massive_ties_and_odd_ranges(oracle, npb):
                 assert r.passage_ids.tolist() == w.passage_ids.tolist(), (kw, mode)
                 assert np.array_equal(r.scores, w.scores, equal_nan=True), (kw, mode)
     gpu.close()
+
+
+def test_deep_cut_and_large_top_k(oracle, npb, corpus):
+    # BASELINE config E shape: recall@1000 -> top_k = 1000, n_full_scores = 16384 -> 4096 docs exact-scored
+    docs, ix, qs, src, gpu = corpus
+    for kw in (dict(top_k=1000, n_full_scores=16384, centroid_score_threshold=None, n_ivf_probe=16),
+               dict(top_k=1000, n_full_scores=2048, centroid_score_threshold=None),
+               dict(top_k=64, n_full_scores=8192, n_ivf_probe=32, centroid_batch_size=128)):
+        pg, po = _params(npb, oracle, **kw)
+        for q, r in zip(qs[:4], gpu.search_batch(qs[:4], pg)):
+            w = oracle.search_one(ix, q, po)
+            assert r.passage_ids.tolist() == w.passage_ids.tolist(), kw
+            assert np.array_equal(r.scores, w.scores), kw
+    with pytest.raises(npb.PlaidError):      # stated limit: > 16384 docs to exact-score
+        gpu.search_batch(qs[:1], npb.SearchParameters(top_k=10, n_full_scores=4 * 16385))
