@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--recall-queries", type=int, default=8)
     ap.add_argument("--cpu-queries", type=int, default=8, help="queries in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--threads", type=int, default=2, help="host threads for the extra concurrent-callers measurement")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--docs-per-topic", type=int, default=1024)
     ap.add_argument("--pool", type=int, default=256, help="centroids per topic pool")
@@ -336,6 +337,31 @@ def run_b200(args):
     e2e_s = time.perf_counter() - t1
     clocks = sampler.stop()
 
+    # ---- the reference's deployment model: several host threads share one index (state.rs:24-47).
+    #      Same K steps, issued from T threads; reported next to the headline, not instead of it ----
+    concurrent = None
+    if world == 1 and args.threads > 1:
+        def worker(tid):
+            bufs = (np.zeros_like(h_ids), np.zeros_like(h_sc), np.zeros_like(h_cn))
+            for i in range(tid, args.steps, args.threads):
+                st = L.pb_search_batch(gpu._h, C.c_void_p(pinned[(args.warmup + i) % n_batches].data_ptr()),
+                                       offs.ctypes.data_as(C.c_void_p), args.batch, C.byref(pc), None, 0,
+                                       bufs[0].ctypes.data_as(C.c_void_p), bufs[1].ctypes.data_as(C.c_void_p),
+                                       bufs[2].ctypes.data_as(C.c_void_p))
+                if st != 0:
+                    raise RuntimeError(L.pb_last_error().decode())
+        for rep in range(2):          # first repetition creates the extra workspaces
+            ths = [threading.Thread(target=worker, args=(t,)) for t in range(args.threads)]
+            torch.cuda.synchronize(dev)
+            tc0 = time.perf_counter()
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+            torch.cuda.synchronize(dev)
+            tc = time.perf_counter() - tc0
+        concurrent = {"host_threads": args.threads, "value": args.batch * args.steps / tc, "unit": "queries/s",
+                      "ms_per_step": 1e3 * tc / args.steps,
+                      "note": "same steps through pb_search_batch (host buffers) from T threads on one handle"}
+
     # ---- CPU baseline + parity on a bounded sample ----
     cpu = None
     parity = None
@@ -413,7 +439,7 @@ def run_b200(args):
                 "h2d_bytes_per_step": int(flat[0].nbytes + offs.nbytes),
                 "d2h_bytes_per_step": int(h_ids.nbytes + h_sc.nbytes + h_cn.nbytes), "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_all": per_stage,
-        "cpu_baseline": cpu, "parity": parity,
+        "cpu_baseline": cpu, "parity": parity, "concurrent": concurrent,
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
         "work_per_step": {k: v / args.steps for k, v in work.items()},
         "index_build_s": t_build,
