@@ -257,6 +257,11 @@ PB_API pb_status pb_codec_compress_and_residuals(pb_codec *c, const float *embed
  * codec.rs:356-411) */
 PB_API pb_status pb_codec_encode_chunk(pb_codec *c, const float *embeddings, int64_t n, int64_t *out_codes,
                                        uint8_t *out_residuals_packed);
+/* find_outliers (update.rs:490-608, the numeric kernel of update_centroids): ascending row indices whose
+ * minimum squared L2 distance to every centroid exceeds threshold_sq, including the f64 re-check of
+ * borderline rows.  out_indices must hold n entries. */
+PB_API pb_status pb_codec_find_outliers(pb_codec *c, const float *embeddings, int64_t n, float threshold_sq,
+                                        int64_t *out_indices, int64_t *out_count);
 /* compute_kmeans' inner fit + L2 normalisation (kmeans.rs:319-419): out_centroids [K][dim] */
 PB_API pb_status pb_kmeans_fit(int32_t device, const float *samples, int64_t n, int32_t dim, int64_t num_centroids,
                                int32_t niters, uint64_t seed, float *out_centroids);

@@ -1519,3 +1519,42 @@ extern "C" pb_status pb_kmeans_fit(int32_t device, const float *samples, int64_t
     CK(cudaMemcpy(out_centroids, dC.p, (size_t)K * dim * 4, cudaMemcpyDeviceToHost));
     return PB_OK;
 }
+
+// find_outliers (update.rs:490-608) on the codec's centroids
+extern "C" pb_status pb_codec_find_outliers(pb_codec *c, const float *embeddings, int64_t n, float threshold_sq,
+                                            int64_t *out_indices, int64_t *out_count) {
+    if (!c || (!embeddings && n) || !out_count || (!out_indices && n)) return pb_fail(PB_ERR_INVALID, "null argument");
+    *out_count = 0;
+    if (n <= 0) return n == 0 ? PB_OK : pb_fail(PB_ERR_INVALID, "negative size");
+    CK(cudaSetDevice(c->device));
+    DevBuf cn, dX, xn, md, fl;
+    CKS(cn.ensure((size_t)c->K * 4));
+    k_squared_norms_ref<<<c->sm_count * 4, 256>>>(c->centroids.as<float>(), c->K, c->dim, cn.as<float>());
+    const long long slab = 1ll << 20;
+    CKS(dX.ensure((size_t)std::min<long long>(n, slab) * c->dim * 4));
+    CKS(xn.ensure((size_t)std::min<long long>(n, slab) * 4));
+    CKS(md.ensure((size_t)std::min<long long>(n, slab) * 4));
+    CKS(fl.ensure((size_t)std::min<long long>(n, slab)));
+    std::vector<uint8_t> hf((size_t)std::min<long long>(n, slab));
+    int64_t cnt = 0;
+    for (long long o = 0; o < n; o += slab) {
+        const long long m = std::min(slab, n - o);
+        CK(cudaMemcpy(dX.p, embeddings + (size_t)o * c->dim, (size_t)m * c->dim * 4, cudaMemcpyHostToDevice));
+        k_squared_norms_ref<<<c->sm_count * 4, 256>>>(dX.as<float>(), m, c->dim, xn.as<float>());
+        const unsigned blocks = (unsigned)((m + 63) / 64);
+        PB_DIM_SWITCH(c->dim, {
+            auto kern = k_min_dist<DIM>;
+            CKS(set_smem(kern, smem_assign(DIM)));
+            kern<<<blocks, 256, smem_assign(DIM)>>>(dX.as<float>(), m, xn.as<float>(), c->centroids.as<float>(), c->K,
+                                                    cn.as<float>(), md.as<float>());
+        });
+        k_outlier_decide<<<c->sm_count * 8, 256>>>(dX.as<float>(), m, c->dim, c->centroids.as<float>(), c->K, md.as<float>(),
+                                                   threshold_sq, fl.as<uint8_t>());
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(hf.data(), fl.p, (size_t)m, cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < m; ++i)
+            if (hf[i]) out_indices[cnt++] = o + i;
+    }
+    *out_count = cnt;
+    return PB_OK;
+}

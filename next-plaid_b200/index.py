@@ -76,7 +76,7 @@ EXPORTS = [
     "pb_last_work_counters", "pb_search_batch_device", "pb_last_error", "pb_version",
     "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init", "pb_set_fast_approx",
     "pb_codec_open", "pb_codec_close", "pb_codec_compress_into_codes", "pb_codec_compress_and_residuals",
-    "pb_codec_encode_chunk", "pb_kmeans_fit", "pb_codec_last_assign_stats",
+    "pb_codec_encode_chunk", "pb_kmeans_fit", "pb_codec_last_assign_stats", "pb_codec_find_outliers",
 ]
 
 _lib = None
@@ -125,6 +125,7 @@ def load_library():
                                     C.POINTER(C.c_void_p)]
         L.pb_codec_close.argtypes = [C.c_void_p]
         L.pb_codec_close.restype = None
+        L.pb_codec_find_outliers.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
         L.pb_codec_last_assign_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pb_codec_compress_into_codes.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.pb_codec_compress_and_residuals.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
@@ -449,6 +450,15 @@ class ResidualCodec:
         res = np.zeros_like(e)
         _check(load_library().pb_codec_compress_and_residuals(self._h, _ptr(e), e.shape[0], _ptr(codes), _ptr(res)))
         return codes, res
+
+    def find_outliers(self, embeddings: np.ndarray, threshold_sq: float) -> np.ndarray:
+        """update.rs:490: row indices farther than sqrt(threshold_sq) from every centroid."""
+        e = np.ascontiguousarray(embeddings, np.float32)
+        out = np.zeros(max(e.shape[0], 1), np.int64)
+        cnt = C.c_int64()
+        _check(load_library().pb_codec_find_outliers(self._h, _ptr(e), e.shape[0], float(threshold_sq), _ptr(out),
+                                                     C.byref(cnt)))
+        return out[:cnt.value].copy()
 
     def encode_chunk(self, embeddings: np.ndarray):
         """encode_index_chunk (index.rs:289): (codes i64 [n], packed residuals u8 [n, dim*nbits/8])."""

@@ -331,6 +331,17 @@ def quantiles(arr: np.ndarray, qs: Sequence[float]) -> np.ndarray:
     return out
 
 
+def find_outliers(embeddings: np.ndarray, centroids: np.ndarray, threshold_sq: float) -> np.ndarray:
+    """update.rs:490-608: rows whose min squared L2 distance to any centroid exceeds threshold_sq."""
+    e, c = _f32(embeddings), _f32(centroids)
+    out = np.zeros(max(e.shape[0], 1), np.int64)
+    L = lib()
+    L.po_find_outliers.restype = C.c_int64
+    m = L.po_find_outliers(_p(e), C.c_int64(e.shape[0]), _p(c), C.c_int64(c.shape[0]), C.c_int(c.shape[1]),
+                           C.c_float(threshold_sq), _p(out))
+    return out[:m].copy()
+
+
 def byte_reversed_bits_map(nbits: int) -> np.ndarray:
     out = np.zeros(256, np.uint8)
     lib().po_byte_reversed_bits_map(C.c_int(nbits), _p(out))

@@ -762,3 +762,73 @@ PO_EXPORT int po_num_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------- */
+/* update path: find_outliers, update.rs:427-608                               */
+/* ------------------------------------------------------------------------- */
+
+/* squared_norm, update.rs:427-449: four partial sums, plain mul + add (Rust does not fuse) */
+static float squared_norm_ref(const float *row, int dim) {
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int i = 0;
+    while (i + 4 <= dim) {
+        s0 += row[i] * row[i];
+        s1 += row[i + 1] * row[i + 1];
+        s2 += row[i + 2] * row[i + 2];
+        s3 += row[i + 3] * row[i + 3];
+        i += 4;
+    }
+    float total = s0 + s1 + s2 + s3;
+    while (i < dim) {
+        total += row[i] * row[i];
+        ++i;
+    }
+    return total;
+}
+
+/* min_distance_sq_precise, update.rs:456-473 */
+static float min_distance_sq_precise(const float *row, const float *C, int64_t K, int dim) {
+    float m = INFINITY;
+    for (int64_t c = 0; c < K; ++c) {
+        double d2 = 0.0;
+        for (int d = 0; d < dim; ++d) {
+            double diff = (double)row[d] - (double)C[(size_t)c * dim + d];
+            d2 += diff * diff;
+        }
+        m = fminf(m, (float)d2);
+    }
+    return m;
+}
+
+/* find_outliers, update.rs:490-608.  The per-(row, centroid) dot is a sequential mul+add over the
+ * dimension in both the tiled and the tail loop, so the tiling does not change any value.
+ * out_idx must hold n entries; returns the number of outliers (ascending row indices). */
+PO_EXPORT int64_t po_find_outliers(const float *emb, int64_t n, const float *C, int64_t K, int dim,
+                                   float threshold_sq, int64_t *out_idx) {
+    if (n == 0 || K == 0) return 0;
+    float *cn = (float *)malloc((size_t)K * sizeof(float));
+    for (int64_t c = 0; c < K; ++c) cn[c] = squared_norm_ref(C + (size_t)c * dim, dim);
+    uint8_t *flag = (uint8_t *)calloc((size_t)n, 1);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t r = 0; r < n; ++r) {
+        const float *row = emb + (size_t)r * dim;
+        const float en = squared_norm_ref(row, dim);
+        float md = INFINITY;
+        for (int64_t c = 0; c < K; ++c) {
+            const float *cen = C + (size_t)c * dim;
+            float dot = 0.0f;
+            for (int d = 0; d < dim; ++d) dot += row[d] * cen[d]; /* -ffp-contract=off: not fused */
+            float dist = en + cn[c] - 2.0f * dot;
+            md = fminf(md, dist);
+        }
+        float band = fmaxf(fabsf(threshold_sq), 1.0f) * 1e-5f; /* OUTLIER_THRESHOLD_RECHECK_REL_EPS */
+        float fin = (fabsf(md - threshold_sq) <= band) ? min_distance_sq_precise(row, C, K, dim) : md;
+        flag[r] = fin > threshold_sq;
+    }
+    int64_t m = 0;
+    for (int64_t r = 0; r < n; ++r)
+        if (flag[r]) out_idx[m++] = r;
+    free(flag);
+    free(cn);
+    return m;
+}

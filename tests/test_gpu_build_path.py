@@ -135,3 +135,32 @@ def test_tensor_core_filter_is_exact_on_hard_inputs(oracle, npb):
     assert st["tensor_cores"] and 300 <= st["exact_fallback"] < 1200, st
     assert got.tolist() == want.tolist()
     assert got[300] == 1500
+
+
+@pytest.mark.parametrize("dim,K", [(128, 700), (64, 129), (256, 90), (32, 8)])
+def test_find_outliers_identical_to_oracle(oracle, npb, dim, K):
+    # update.rs:490-608; includes rows placed inside the 1e-5 re-check band around the threshold
+    rng = np.random.default_rng(dim + K)
+    cent = rng.standard_normal((K, dim)).astype(np.float32)
+    cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+    emb = cent[rng.integers(0, K, 3000)] + rng.uniform(0.0, 1.2, (3000, 1)).astype(np.float32) * \
+        rng.standard_normal((3000, dim)).astype(np.float32) / np.sqrt(dim)
+    d2 = ((emb[:, None, :].astype(np.float64) - cent[None, :64].astype(np.float64)) ** 2).sum(-1).min(1)
+    thr = float(np.median(d2))
+    # nudge a few rows onto the threshold so the f64 path decides them
+    for r in range(40):
+        j = int(rng.integers(0, K))
+        v = rng.standard_normal(dim).astype(np.float32)
+        v /= np.linalg.norm(v)
+        emb[r] = cent[j] + np.float32(np.sqrt(thr) * (1.0 + (r - 20) * 1e-7)) * v
+    want = oracle.find_outliers(emb, cent, thr)
+    got = npb.ResidualCodec(4, cent).find_outliers(emb, thr)
+    assert 100 < len(want) < 2900
+    assert got.tolist() == want.tolist()
+
+
+def test_find_outliers_reference_kat(npb):
+    # update.rs:1170-1185, padded to a built dimension
+    c = np.zeros((2, 32), np.float32); c[1, :2] = 1.0
+    e = np.zeros((3, 32), np.float32); e[0, :2] = 0.1; e[1, :2] = 0.9; e[2, :2] = 5.0
+    assert npb.ResidualCodec(4, c).find_outliers(e, 1.0).tolist() == [2]

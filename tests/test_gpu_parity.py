@@ -289,3 +289,41 @@ def test_deep_cut_and_large_top_k(oracle, npb, corpus):
             assert np.array_equal(r.scores, w.scores), kw
     with pytest.raises(npb.PlaidError):      # stated limit: > 16384 docs to exact-score
         gpu.search_batch(qs[:1], npb.SearchParameters(top_k=10, n_full_scores=4 * 16385))
+
+
+def test_randomized_search_parity(oracle, npb):
+    """Seeded sweep over index shapes and search parameters: ids and scores bit-identical to the oracle."""
+    rng = np.random.default_rng(20260923)
+    checked = 0
+    for case in range(24):
+        dim = int(rng.choice([32, 64, 96, 128]))
+        nbits = int(rng.choice([1, 2, 4, 8]))
+        n_docs = int(rng.integers(150, 900))
+        doclen = int(rng.integers(3, 50))
+        K = int(rng.choice([32, 64, 128, 256]))
+        docs = oracle.synthetic_corpus(n_docs, doclen, dim=dim, seed=1000 + case, ragged=bool(rng.integers(2)))
+        ix = oracle.create_index(docs, nbits=nbits, seed=case, num_partitions=K, kmeans_niters=2)
+        gpu = _gpu_index(npb, ix)
+        nqs = [int(rng.integers(1, 49)) for _ in range(3)]
+        qs = [oracle.synthetic_queries(docs, 1, nq=nq, seed=case * 7 + j)[0][0] for j, nq in enumerate(nqs)]
+        for trial in range(2):
+            kw = dict(top_k=int(rng.integers(1, 200)), n_ivf_probe=int(rng.integers(1, 33)),
+                      n_full_scores=int(rng.integers(16, 2048)),
+                      centroid_batch_size=int(rng.choice([0, max(ix.num_centroids // 3, 1), 100_000])),
+                      centroid_score_threshold=None if rng.integers(3) == 0 else float(rng.uniform(0.2, 0.5)))
+            subset = None
+            if rng.integers(4) == 0:
+                subset = sorted(rng.choice(n_docs, int(rng.integers(1, n_docs)), replace=False).tolist())
+            pg, po = _params(npb, oracle, **kw)
+            try:
+                res = gpu.search_batch(qs, pg, subset=subset)
+            except npb.PlaidError as e:
+                assert e.status == 4, e          # only the stated limits may refuse (PB_ERR_UNSUPPORTED)
+                continue
+            for q, r in zip(qs, res):
+                w = oracle.search_one(ix, q, po, subset=subset)
+                assert r.passage_ids.tolist() == w.passage_ids.tolist(), (case, dim, nbits, kw, subset is not None)
+                assert np.array_equal(r.scores, w.scores), (case, dim, nbits, kw)
+                checked += 1
+        gpu.close()
+    assert checked >= 100

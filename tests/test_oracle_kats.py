@@ -148,3 +148,16 @@ def test_pinned_dot_matches_float64_to_1e5(oracle):
     for (i, j) in [(0, 0), (3, 17), (31, 499)]:
         s = L.po_dot(q[i].ctypes.data_as(C.c_void_p), c[j].ctypes.data_as(C.c_void_p), 128)
         assert np.float32(s) == S[i, j]
+
+
+def test_find_outliers_kat(oracle):
+    # update.rs:1170-1185 test_find_outliers: centroids (0,0), (1,1); embeddings near each and one at
+    # (5,5); threshold_sq = 1.0 -> only row 2 is an outlier
+    c = np.array([[0, 0], [1, 1]], np.float32)
+    e = np.array([[0.1, 0.1], [0.9, 0.9], [5.0, 5.0]], np.float32)
+    assert oracle.find_outliers(e, c, 1.0).tolist() == [2]
+    # borderline rows take the f64 recheck (update.rs:592-599): exactly on the threshold is not an outlier
+    c2 = np.zeros((1, 4), np.float32)
+    e2 = np.array([[1, 0, 0, 0], [1.0000001, 0, 0, 0], [1.01, 0, 0, 0]], np.float32)
+    assert oracle.find_outliers(e2, c2, 1.0).tolist() == [1, 2]
+    assert oracle.find_outliers(np.zeros((0, 4), np.float32), c2, 1.0).tolist() == []
