@@ -145,7 +145,8 @@ def test_find_outliers_identical_to_oracle(oracle, npb, dim, K):
     cent /= np.linalg.norm(cent, axis=1, keepdims=True)
     emb = cent[rng.integers(0, K, 3000)] + rng.uniform(0.0, 1.2, (3000, 1)).astype(np.float32) * \
         rng.standard_normal((3000, dim)).astype(np.float32) / np.sqrt(dim)
-    d2 = ((emb[:, None, :].astype(np.float64) - cent[None, :64].astype(np.float64)) ** 2).sum(-1).min(1)
+    e64, c64 = emb.astype(np.float64), cent.astype(np.float64)
+    d2 = ((e64 * e64).sum(1)[:, None] + (c64 * c64).sum(1)[None, :] - 2.0 * e64 @ c64.T).min(1)
     thr = float(np.median(d2))
     # nudge a few rows onto the threshold so the f64 path decides them
     for r in range(40):
