@@ -452,10 +452,46 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def _total_key(scores):
+    """search.rs:110-133 as a sortable integer: finite by total_cmp, every non-finite lowest."""
+    a = np.asarray(scores, np.float32)
+    bits = a.view(np.int32).astype(np.int64)
+    key = np.where(bits < 0, bits ^ 0x7FFFFFFF, bits)
+    return np.where(np.isfinite(a), key, -(2 ** 40))
+
+
+def cpu_search_sharded(oracle, shards, bases, q, p):
+    """The reference algorithm over a doc-sharded corpus on the CPU, one shard after the other: per shard
+    a2-a5 (oracle), the GLOBAL n_full_scores/4 cut on the approximate score (search.rs:460-469), exact
+    MaxSim of the survivors (oracle), stable final sort (search.rs:496).  Same result as searching the
+    concatenated index (tests/test_sharded_protocol.py)."""
+    if len(shards) == 1:
+        r = oracle.search_one(shards[0], q, p)
+        return r.passage_ids, r.scores
+    M = min(p.n_full_scores, max(p.n_full_scores // 4, p.top_k))
+    keys = []
+    for sh, base in zip(shards, bases):
+        _, tr = oracle.search_one(sh, q, p, trace=True)
+        gid = tr.candidates + base
+        k = _total_key(tr.approx)
+        order = np.lexsort((gid, -k))[:M]
+        keys += [(int(k[i]), int(gid[i])) for i in order]
+    keys.sort(key=lambda t: (-t[0], t[1]))
+    trip = []
+    for rank, (_, g) in enumerate(keys[:M]):
+        si = max(i for i, b in enumerate(bases) if b <= g)
+        ex = oracle.maxsim_score(q, oracle.get_document_embeddings(shards[si], g - bases[si]))
+        trip.append((float(ex), rank, g))
+    trip.sort(key=lambda t: (-int(_total_key([t[0]])[0]), t[1]))
+    trip = trip[:p.top_k]
+    return np.array([t[2] for t in trip], np.int64), np.array([t[0] for t in trip], np.float32)
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path.  The reference is Rust and this image has
     no cargo/rustc, so oracle/_ref cannot exist; the timed code is the C restatement (oracle/), on all
-    host threads, same index generator, same queries and parameters as the b200 arm."""
+    host threads, same index generator, same queries and parameters as the b200 arm.  With N > 1 the
+    corpus is the same N x docs-per-GPU corpus, held in host memory shard by shard."""
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
@@ -464,24 +500,29 @@ def run_reference(args):
     import next_plaid_b200 as npb
     from oracle import oracle
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
-    tens = make_index_tensors(args, dev, 0)
-    gpu = open_index(npb, tens, args, dev.index or 0, 0)          # only to draw the same queries
-    queries, _ = make_queries(gpu, args, max(args.steps + args.warmup, 4) * args.batch, seed=args.seed + 7)
-    gpu.close()
-    hix = host_index_from_tensors(oracle, tens, args)
-    del tens
-    torch.cuda.empty_cache()
+    torch.cuda.set_device(dev)
+    shards, bases, queries = [], [], None
+    for g in range(world):
+        tens = make_index_tensors(args, dev, g)
+        if g == 0:  # the b200 arm draws its queries from shard 0
+            gpu = open_index(npb, tens, args, dev.index or 0, 0)
+            queries, _ = make_queries(gpu, args, min(max(args.steps + args.warmup, 4), 16) * args.batch, seed=args.seed + 7)
+            gpu.close()
+        shards.append(host_index_from_tensors(oracle, tens, args))
+        bases.append(g * args.docs)
+        del tens
+        torch.cuda.empty_cache()
     po = oracle.SearchParameters(top_k=args.top_k, n_ivf_probe=args.n_ivf_probe, n_full_scores=args.n_full_scores,
                                  centroid_score_threshold=args.threshold)
-    per_step = max(1, args.cpu_queries)
+    per_step = max(1, args.cpu_queries // world)      # bounded sample: CPU work per query grows with the corpus
     step_q = lambda i: queries[(i * args.batch) % len(queries):][:per_step]   # noqa: E731
     for i in range(args.warmup):
         for q in step_q(i):
-            oracle.search_one(hix, q, po)
+            cpu_search_sharded(oracle, shards, bases, q, po)
     t0 = time.perf_counter()
     for i in range(args.steps):
         for q in step_q(args.warmup + i):
-            oracle.search_one(hix, q, po)
+            cpu_search_sharded(oracle, shards, bases, q, po)
     s = time.perf_counter() - t0
     qps = per_step * args.steps / s
     cores = oracle.lib().po_num_threads()
@@ -490,7 +531,7 @@ def run_reference(args):
         "impl": "reference", "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (codec-domain index, seed 42)",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
