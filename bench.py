@@ -452,41 +452,6 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def _total_key(scores):
-    """search.rs:110-133 as a sortable integer: finite by total_cmp, every non-finite lowest."""
-    a = np.asarray(scores, np.float32)
-    bits = a.view(np.int32).astype(np.int64)
-    key = np.where(bits < 0, bits ^ 0x7FFFFFFF, bits)
-    return np.where(np.isfinite(a), key, -(2 ** 40))
-
-
-def cpu_search_sharded(oracle, shards, bases, q, p):
-    """The reference algorithm over a doc-sharded corpus on the CPU, one shard after the other: per shard
-    a2-a5 (oracle), the GLOBAL n_full_scores/4 cut on the approximate score (search.rs:460-469), exact
-    MaxSim of the survivors (oracle), stable final sort (search.rs:496).  Same result as searching the
-    concatenated index (tests/test_sharded_protocol.py)."""
-    if len(shards) == 1:
-        r = oracle.search_one(shards[0], q, p)
-        return r.passage_ids, r.scores
-    M = min(p.n_full_scores, max(p.n_full_scores // 4, p.top_k))
-    keys = []
-    for sh, base in zip(shards, bases):
-        _, tr = oracle.search_one(sh, q, p, trace=True)
-        gid = tr.candidates + base
-        k = _total_key(tr.approx)
-        order = np.lexsort((gid, -k))[:M]
-        keys += [(int(k[i]), int(gid[i])) for i in order]
-    keys.sort(key=lambda t: (-t[0], t[1]))
-    trip = []
-    for rank, (_, g) in enumerate(keys[:M]):
-        si = max(i for i, b in enumerate(bases) if b <= g)
-        ex = oracle.maxsim_score(q, oracle.get_document_embeddings(shards[si], g - bases[si]))
-        trip.append((float(ex), rank, g))
-    trip.sort(key=lambda t: (-int(_total_key([t[0]])[0]), t[1]))
-    trip = trip[:p.top_k]
-    return np.array([t[2] for t in trip], np.int64), np.array([t[0] for t in trip], np.float32)
-
-
 def run_reference(args):
     """The reference's own CPU implementation of the path.  The reference is Rust and this image has
     no cargo/rustc, so oracle/_ref cannot exist; the timed code is the C restatement (oracle/), on all
@@ -518,11 +483,11 @@ def run_reference(args):
     step_q = lambda i: queries[(i * args.batch) % len(queries):][:per_step]   # noqa: E731
     for i in range(args.warmup):
         for q in step_q(i):
-            cpu_search_sharded(oracle, shards, bases, q, po)
+            oracle.search_sharded(shards, bases, q, po)
     t0 = time.perf_counter()
     for i in range(args.steps):
         for q in step_q(args.warmup + i):
-            cpu_search_sharded(oracle, shards, bases, q, po)
+            oracle.search_sharded(shards, bases, q, po)
     s = time.perf_counter() - t0
     qps = per_step * args.steps / s
     cores = oracle.lib().po_num_threads()

@@ -237,6 +237,25 @@ def search_one(index: Index, query: np.ndarray, params: SearchParameters,
     return res
 
 
+def search_sharded(shards: Sequence[Index], bases: Sequence[int], query: np.ndarray, params: SearchParameters):
+    """po_search_sharded: the reference search over a corpus held as doc-contiguous shards sharing the
+    centroids; equal to search_one on the concatenated index."""
+    L = lib()
+    L.po_search_sharded.restype = C.c_int64
+    q = _f32(query).reshape(-1, shards[0].dim)
+    k = max(int(params.top_k), 1)
+    ids = np.zeros(k, dtype=np.int64)
+    sc = np.zeros(k, dtype=np.float32)
+    cs = [s._c() for s in shards]
+    arr = (C.POINTER(_POIndex) * len(cs))(*[C.pointer(c) for c in cs])
+    b = np.ascontiguousarray(bases, dtype=np.int64)
+    cp = params._c()
+    n = L.po_search_sharded(arr, _p(b), C.c_int(len(cs)), _p(q), C.c_int(q.shape[0]), C.byref(cp), _p(ids), _p(sc))
+    if n < 0:
+        raise ValueError("po_search_sharded rejected its arguments")
+    return QueryResult(0, ids[:n].copy(), sc[:n].copy())
+
+
 def search_batch(index: Index, queries: Sequence[np.ndarray], params: SearchParameters,
                  subset: Optional[Sequence[int]] = None) -> List[QueryResult]:
     """MmapIndex::search_batch -> search_many_mmap (index.rs:1279, search.rs:643)."""

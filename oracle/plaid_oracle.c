@@ -832,3 +832,113 @@ PO_EXPORT int64_t po_find_outliers(const float *emb, int64_t n, const float *C, 
     free(cn);
     return m;
 }
+
+/* ------------------------------------------------------------------------- */
+/* The same search over a corpus held as several doc-contiguous shards that share the centroids      */
+/* (bench.py --impl reference --gpus N: the N x 1M-doc corpus of the sharded GPU run, on the CPU).   */
+/* Identical in result to po_search_one on the concatenated index: S and the probe are computed     */
+/* once, candidates / approximate scores per shard, then the GLOBAL cut (search.rs:460-469), exact   */
+/* scores and the stable final sort (search.rs:496).  No subset support.                             */
+/* ------------------------------------------------------------------------- */
+PO_EXPORT int64_t po_search_sharded(const po_index *const *shards, const int64_t *bases, int n_shards,
+                                    const float *Q, int nq, const po_params *p, int64_t *out_ids,
+                                    float *out_scores) {
+    if (n_shards < 1 || p->n_ivf_probe < 1 || p->top_k < 0) return -1;
+    const po_index *ix0 = shards[0];
+    int64_t K = ix0->num_centroids;
+    int dim = ix0->dim;
+    int batched = p->centroid_batch_size > 0 && K > p->centroid_batch_size;
+    float *S = (float *)malloc((size_t)(nq > 0 ? nq : 1) * (size_t)K * sizeof(float));
+    po_centroid_scores(Q, nq, ix0->centroids, K, dim, S);
+    int64_t n_cells = 0;
+    int64_t *cells = batched ? probe_batched(ix0, S, nq, p, &n_cells)
+                             : probe_dense(ix0, S, nq, p, NULL, 0, 0, &n_cells);
+    /* candidates of every shard, global ids ascending because shards are doc-contiguous and ordered */
+    int64_t total = 0;
+    int64_t **cand = (int64_t **)malloc((size_t)n_shards * sizeof(int64_t *));
+    int64_t *ncand = (int64_t *)malloc((size_t)n_shards * sizeof(int64_t));
+    for (int s = 0; s < n_shards; ++s) {
+        cand[s] = get_candidates(shards[s], cells, n_cells, &ncand[s]);
+        total += ncand[s];
+    }
+    free(cells);
+    if (total == 0) {
+        for (int s = 0; s < n_shards; ++s) free(cand[s]);
+        free(cand);
+        free(ncand);
+        free(S);
+        return 0;
+    }
+    scored *ap = (scored *)malloc((size_t)total * sizeof(scored));
+    int64_t off = 0;
+    for (int s = 0; s < n_shards; ++s) {
+        const po_index *ix = shards[s];
+        const int64_t *cs = cand[s];
+        const int64_t n = ncand[s], base = bases[s];
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int64_t i = 0; i < n; ++i) {
+            int64_t d = cs[i];
+            float score = 0.0f;
+            for (int q = 0; q < nq; ++q) {
+                float m = -INFINITY;
+                const float *row = S + (size_t)q * K;
+                for (int64_t t = ix->doc_offsets[d]; t < ix->doc_offsets[d + 1]; ++t) {
+                    float v = row[ix->codes[t]];
+                    if (v > m) m = v;
+                }
+                if (m > -INFINITY) score += m;
+            }
+            ap[off + i].s = score;
+            ap[off + i].id = base + d;
+            ap[off + i].pos = off + i;
+        }
+        off += n;
+        free(cand[s]);
+    }
+    free(cand);
+    free(ncand);
+    free(S);
+    qsort(ap, (size_t)total, sizeof(scored), cmp_scored_desc_stable);
+    int64_t n_top = total < p->n_full_scores ? total : p->n_full_scores;
+    int64_t n_dec = p->n_full_scores / 4 > p->top_k ? p->n_full_scores / 4 : p->top_k;
+    int64_t n_keep = n_top < n_dec ? n_top : n_dec;
+    if (n_keep == 0) {
+        free(ap);
+        return 0;
+    }
+    scored *ex = (scored *)malloc((size_t)n_keep * sizeof(scored));
+#pragma omp parallel
+    {
+        float *buf = NULL;
+        int64_t cap = 0;
+#pragma omp for schedule(dynamic, 8)
+        for (int64_t i = 0; i < n_keep; ++i) {
+            int64_t g = ap[i].id;
+            int s = n_shards - 1;
+            while (s > 0 && bases[s] > g) --s;
+            const po_index *ix = shards[s];
+            int64_t d = g - bases[s];
+            int64_t t0 = ix->doc_offsets[d], T = ix->doc_offsets[d + 1] - t0;
+            if (T > cap) {
+                free(buf);
+                cap = T;
+                buf = (float *)malloc((size_t)cap * dim * sizeof(float));
+            }
+            po_decompress(ix->centroids, dim, ix->nbits, ix->bucket_weights,
+                          ix->residuals + (size_t)t0 * (size_t)(dim * ix->nbits / 8), ix->codes + t0, T, buf);
+            ex[i].s = po_maxsim(Q, nq, buf, T, dim);
+            ex[i].id = g;
+            ex[i].pos = i;
+        }
+        free(buf);
+    }
+    free(ap);
+    qsort(ex, (size_t)n_keep, sizeof(scored), cmp_scored_desc_stable);
+    int64_t n_res = p->top_k < n_keep ? p->top_k : n_keep;
+    for (int64_t i = 0; i < n_res; ++i) {
+        out_ids[i] = ex[i].id;
+        out_scores[i] = ex[i].s;
+    }
+    free(ex);
+    return n_res;
+}

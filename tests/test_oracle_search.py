@@ -164,3 +164,19 @@ def test_index_dir_roundtrip(oracle, small, tmp_path):
     p = oracle.SearchParameters(top_k=10, n_full_scores=128)
     r1, r2 = oracle.search_one(ix, qs[0], p), oracle.search_one(ix2, qs[0], p)
     assert r1.passage_ids.tolist() == r2.passage_ids.tolist()
+
+
+def test_sharded_oracle_search_equals_unsharded(oracle, small):
+    # po_search_sharded (the --impl reference arm at N > 1) == po_search_one on the concatenated index
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import sharded_protocol as sp
+    docs, ix, qs, src = small
+    for G in (2, 3):
+        sh = [sp.make_shard(oracle, ix, g, G) for g in range(G)]
+        for cbs in (100_000, 16):
+            p = oracle.SearchParameters(top_k=10, n_ivf_probe=4, n_full_scores=64, centroid_batch_size=cbs)
+            for q in qs:
+                r = oracle.search_sharded([s[0] for s in sh], [s[1] for s in sh], q, p)
+                w = oracle.search_one(ix, q, p)
+                assert r.passage_ids.tolist() == w.passage_ids.tolist() and np.array_equal(r.scores, w.scores)
