@@ -415,10 +415,17 @@ def run_b200(args):
             ent["fp32_tflops"] = flops[st] / max(args.steps, 1) / (ms1 * 1e-3) / 1e12
             ent["frac_of_fp32_fma_peak"] = ent["fp32_tflops"] / 74.4   # 148 SMs x 128 FMA x 2 x 1.965 GHz
         per_stage[st] = ent
+    # dram__bytes_read.sum + dram__bytes_write.sum of the stage's main kernel, one launch, from the committed
+    # `ncu --set full` capture of this exact workload (profiles/r01_ncu_full_top4_raw.csv); null for other shapes
+    ncu_traffic = {"exact": 1.349412e9 + 0.009592e9, "approx": 2.260998e9 + 0.018709e9,
+                   "centroid_scores": 0.138181e9 + 1.555811e9, "probe": 1.073790e9 + 0.017651e9}
+    default_shape = (args.docs, args.doclen, args.dim, args.nbits, args.log2k, args.batch, args.nq, args.top_k,
+                     args.n_ivf_probe, args.n_full_scores) == (1_000_000, 300, 128, 4, 18, 32, 32, 100, 8, 4096)
     dom = max(kern_stages, key=kern_stages.get)
     d = per_stage[dom]
     roof = {"bound": "hbm", "kernel": d["kernel"], "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": d["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src, "ms_per_launch": d["ms_per_step"],
+            "frac": d["frac_of_hbm_peak"], "traffic": ncu_traffic.get(dom) if (default_shape and world == 1) else None,
+            "peak_source": peak_src, "ms_per_launch": d["ms_per_step"],
             "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_step"],
             "note": "k_exact and k_centroid_scores are fp32-FMA bound by design (pinned accumulation order, "
                     "DESIGN.md Numerics): see fp32_tflops in roofline_all",
