@@ -598,10 +598,20 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
     std::unique_ptr<Workspace> wsp;
     CKS(ix->acquire(wsp));
     Workspace &ws = *wsp;
+    // A workspace goes back to the pool only after a search that ran to completion: its scratch
+    // invariants (cleared bitmaps, zeroed maxima) are restored by the kernels themselves, so a call that
+    // fails half way must not hand its buffers to the next caller.
     struct Releaser {
         pb_index *ix;
         std::unique_ptr<Workspace> &w;
-        ~Releaser() { ix->release(w); }
+        bool ok = false;
+        ~Releaser() {
+            if (ok) ix->release(w);
+            else {
+                cudaStreamSynchronize(w->stream);
+                w.reset();
+            }
+        }
     } rel{ix, wsp};
 
     auto zero_counts = [&](int64_t b0, int64_t nb) -> pb_status {
@@ -612,6 +622,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
     if (empty_all) {
         CKS(zero_counts(0, Bt));
         CK(cudaStreamSynchronize(ws.stream));
+        rel.ok = true;
         return PB_OK;
     }
 
@@ -649,6 +660,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             if (n_elig == 0) {  // every per-token pool is empty -> no cells -> empty results
                 CKS(zero_counts(0, Bt));
                 CK(cudaStreamSynchronize(ws.stream));
+                rel.ok = true;
                 return PB_OK;
             }
             unsigned long long scaled = io.n_subset > 0 ? (unsigned long long)p->n_ivf_probe * (unsigned long long)ix->D /
@@ -1027,6 +1039,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             }
         }
     }
+    rel.ok = true;
     return PB_OK;
 }
 
