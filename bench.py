@@ -398,12 +398,14 @@ def run_b200(args):
         "probe": nq_tot * K * 4,                                   # S streamed once
         # one u32 code per (candidate, distinct code) + each 16-bit S entry once
         "approx": work.get("n_candidate_tokens", 0) * 4 + nq_tot * K * 2,
-        "exact": work.get("n_exact_tokens", 0) * (packed + 4),     # packed residual + code per token
+        # packed residual + code per token: once for every kept doc in the tensor-core filter (k_exact_tc), once
+        # more for the survivors the fp32 kernel scores (k_exact)
+        "exact": (work.get("n_exact_tokens", 0) + work.get("n_filter_tokens", 0)) * (packed + 4),
         "cut": work.get("n_candidates", 0) * 8, "candidates": 0, "topk": 0,
     }
     flops = {"centroid_scores": 2.0 * nq_tot * K * args.dim,
              "exact": 2.0 * work.get("n_exact_tokens", 0) * args.nq * args.dim}
-    names = {"approx": "k_approx16 (+k_select_u32, k_approx re-check)", "exact": "k_exact", "centroid_scores": "k_centroid_scores",
+    names = {"approx": "k_approx16 (+k_select_u32, k_approx re-check)", "exact": "k_exact_tc (tcgen05 filter) + k_exact (survivors)", "centroid_scores": "k_centroid_scores",
              "probe": "k_topn_partial (+merge, k_cells)", "cut": "k_cut", "candidates": "k_mark/k_compact", "topk": "k_topk"}
     per_stage = {}
     for st, ms_tot in kern_stages.items():
@@ -417,7 +419,7 @@ def run_b200(args):
         per_stage[st] = ent
     # dram__bytes_read.sum + dram__bytes_write.sum of the stage's main kernel, one launch, from the committed
     # `ncu --set full` capture of this exact workload (profiles/r01_ncu_full_top4_raw.csv); null for other shapes
-    ncu_traffic = {"exact": 1.349412e9 + 0.009592e9, "approx": 2.260998e9 + 0.018709e9,
+    ncu_traffic = {"approx": 2.260998e9 + 0.018709e9,
                    "centroid_scores": 0.138181e9 + 1.555811e9, "probe": 1.073790e9 + 0.017651e9}
     default_shape = (args.docs, args.doclen, args.dim, args.nbits, args.log2k, args.batch, args.nq, args.top_k,
                      args.n_ivf_probe, args.n_full_scores) == (1_000_000, 300, 128, 4, 18, 32, 32, 100, 8, 4096)

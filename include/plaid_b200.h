@@ -204,6 +204,12 @@ enum {
  * All three produce the reference's cut bit for bit; tests compare them. */
 PB_API void pb_set_fast_approx(pb_index *ix, int32_t enabled);
 
+/* Diagnostic switch for the exact stage (default on): 1 = an fp16 tcgen05 estimate with a certified error bound
+ * first picks the kept docs that can still reach the top_k, and only those are scored exactly; 0 = every kept
+ * doc is scored exactly.  Same results bit for bit; tests compare both.  (PB_FAST_EXACT=0 in the environment
+ * sets the default.)  The filter applies when dim is 64/96/128, queries have <= 32 tokens and no trace is asked. */
+PB_API void pb_set_fast_exact(pb_index *ix, int32_t enabled);
+
 /* Enable per-stage CUDA-event timing for subsequent searches on this handle (adds event
  * records only, no synchronisation inside the path). */
 PB_API void pb_set_profiling(pb_index *ix, int32_t enabled);
@@ -218,8 +224,10 @@ typedef struct pb_work_counters {
     int64_t n_cells;
     int64_t n_candidates;
     int64_t n_candidate_tokens;
-    int64_t n_exact_docs;
+    int64_t n_exact_docs;      /* docs / tokens scored exactly (the filter's survivors when it is on) */
     int64_t n_exact_tokens;
+    int64_t n_filter_docs;     /* docs / tokens estimated by the tensor-core filter (0 when off) */
+    int64_t n_filter_tokens;
 } pb_work_counters;
 PB_API pb_status pb_last_work_counters(pb_index *ix, pb_work_counters *out);
 

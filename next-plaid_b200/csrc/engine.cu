@@ -172,7 +172,7 @@ struct Workspace {
     cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2, cand3, ncand3, ub, theta, rel, cellbits,
-        gkeys, krank, payload, gfkeys, gpayload;
+        gkeys, krank, payload, gfkeys, gpayload, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -210,6 +210,9 @@ struct pb_index {
     bool fast_approx = true;   // two-pass approximate stage (exact cut either way)
     bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
                                // the cut sits well above the background score level
+    bool fast_exact = true;    // tcgen05 certified filter in front of the exact stage (same results either way)
+    float vmin = 0.0f;         // smallest pre-normalisation token norm |c + w| over the index (error bound of the filter)
+    DevBuf centroids_f16;      // [K][dim] fp16 copy for the filter
     bool profiling = false;
     size_t st_budget = (size_t)4 << 30;
     ncclComm_t comm = nullptr;  // doc-sharded deployment: one rank per GPU
@@ -427,6 +430,26 @@ pb_status pb_index_finalize(pb_index *ix) {
         ix->cmax = sqrtf(m2);
         if (const char *e = getenv("PB_FAST_APPROX")) ix->fast_approx = atoi(e) != 0;
         if (const char *e = getenv("PB_CASCADE")) ix->cascade = atoi(e) != 0;
+        if (const char *e = getenv("PB_FAST_EXACT")) ix->fast_exact = atoi(e) != 0;
+    }
+    if ((ix->dim == 64 || ix->dim == 96 || ix->dim == 128) && ix->N > 0 && ix->K > 0) {
+        // operands of the tensor-core filter (k_exact_tc): fp16 centroids and the smallest token norm
+        CKS(ix->centroids_f16.ensure((size_t)ix->K * ix->dim * 2));
+        k_rows_to_f16_plain<<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->K * (long long)ix->dim,
+                                                      ix->centroids_f16.as<__half>());
+        CK(cudaGetLastError());
+        DevBuf mn;
+        CKS(mn.ensure(16));
+        const float big = 3.0e38f;
+        CK(cudaMemcpy(mn.p, &big, 4, cudaMemcpyHostToDevice));
+        switch (ix->dim) {
+            case 64: k_min_vnorm<64><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>()); break;
+            case 96: k_min_vnorm<96><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>()); break;
+            default: k_min_vnorm<128><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>()); break;
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(&ix->vmin, mn.p, 4, cudaMemcpyDeviceToHost));
+        if (!(ix->vmin < 1e30f)) ix->vmin = 0.0f;
     }
     ix->n_ucodes = uoff[ix->D];
     CKS(upload(ix->udoc_off, uoff.data(), uoff.size() * 8, PB_MEM_HOST));
@@ -488,6 +511,9 @@ extern "C" void pb_set_fast_approx(pb_index *ix, int32_t enabled) {
     ix->fast_approx = enabled != 0;  // 0 = single exact pass, 1 = two-pass, 2 = two-pass behind the pruning cascade
     ix->cascade = enabled == 2;
 }
+extern "C" void pb_set_fast_exact(pb_index *ix, int32_t enabled) {
+    if (ix) ix->fast_exact = enabled != 0;
+}
 extern "C" void pb_set_profiling(pb_index *ix, int32_t enabled) {
     if (ix) ix->profiling = enabled != 0;
 }
@@ -525,9 +551,15 @@ static pb_status launch_centroid_scores(pb_index *ix, Workspace &ws, int B, int 
     return PB_OK;
 }
 
-static pb_status launch_exact(pb_index *ix, Workspace &ws, int B, int QS, int Mcap, int kept_shared,
-                              long long max_tokens, int *launches, int nq_max = 1 << 30) {
-    (void)nq_max;
+struct KeptView {  // the docs the exact stage scores: the cut's output, or the filter's survivors
+    uint32_t *kept;
+    int *nkept;
+    long long *tokp;
+    uint32_t *krank;  // global approximate rank (sharded) or nullptr
+};
+
+static pb_status launch_exact(pb_index *ix, Workspace &ws, const KeptView &kv, int B, int QS, int Mcap, int kept_shared,
+                              long long max_tokens, int *launches) {
     // each CTA owns a contiguous range of chunks; aim for 8 waves of 2 CTAs/SM over the whole grid
     long long chunks = (max_tokens + PB_TOK_TILE - 1) / PB_TOK_TILE;
     long long want = std::max<long long>(1, ((long long)ix->sm_count * 16 + B - 1) / B);
@@ -538,11 +570,63 @@ static pb_status launch_exact(pb_index *ix, Workspace &ws, int B, int QS, int Mc
         kern<<<dim3(gx, B), 128, smem_exact(DIM, ix->packed), ws.stream>>>(
             ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits,
             ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->doc_off.as<long long>(), nullptr,
-            ws.kept.as<uint32_t>(), ws.nkept.as<int>(), ws.tokp.as<long long>(), Mcap, kept_shared,
-            ws.maxkey.as<uint32_t>());
+            kv.kept, kv.nkept, kv.tokp, Mcap, kept_shared, ws.maxkey.as<uint32_t>());
     });
     CK(cudaGetLastError());
     if (launches) ++*launches;
+    return PB_OK;
+}
+
+static size_t smem_exact_tc(int dim, int packed) {
+    return (size_t)(dim / 8) * PB_XTC_LBO + (size_t)32 * dim * 2 + (size_t)128 * packed + 128 * 4 + 256 * 4 + 64;
+}
+
+// error of one fp16 tensor-core similarity relative to |q| (derivation above k_exact_tc); 0 = filter unusable
+static float filter_eps_unit(const pb_index *ix) {
+    const float u = 1.0f / 2048.0f;  // fp16 unit roundoff
+    const float vmin = ix->vmin * 0.9999f;
+    if (!(vmin > u * ix->cmax) || !(ix->cmax < 3.0e4f)) return 0.0f;  // centroids must fit fp16
+    const float dterm = u * ix->cmax / (vmin - 0.5f * u * ix->cmax);  // |D - D~| (Dunkl-Williams)
+    return u + (1.0f + u) * (dterm + u) + 4e-5f;
+}
+
+// a7': tensor-core estimate of every kept doc, then the survivors that can still reach the top_k
+static pb_status launch_filter(pb_index *ix, Workspace &ws, const KeptView &in, const KeptView &out, int B, int QS, int Mcap,
+                               int top_k, long long max_tokens, float eps_unit, int *launches) {
+    long long chunks = (max_tokens + 127) / 128;
+    long long want = std::max<long long>(1, ((long long)ix->sm_count * 32 + B - 1) / B);
+    int gx = (int)std::max<long long>(1, std::min<long long>(chunks, want));
+    const size_t sm = smem_exact_tc(ix->dim, ix->packed);
+#define PB_TC_LAUNCH(DV)                                                                                               \
+    {                                                                                                                  \
+        auto kern = k_exact_tc<DV>;                                                                                    \
+        CKS(set_smem(kern, sm));                                                                                       \
+        kern<<<dim3(gx, B), 128, sm, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS,                             \
+                                                  ix->centroids_f16.as<__half>(), ix->w_rev.as<float>(),               \
+                                                  ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(),    \
+                                                  ix->doc_off.as<long long>(), in.kept, in.nkept, in.tokp, Mcap,       \
+                                                  ws.maxkey.as<uint32_t>());                                           \
+    }
+    switch (ix->dim) {
+        case 64: PB_TC_LAUNCH(64) break;
+        case 96: PB_TC_LAUNCH(96) break;
+        case 128: PB_TC_LAUNCH(128) break;
+        default: return pb_fail(PB_ERR_UNSUPPORTED, "filter: unsupported dim");
+    }
+#undef PB_TC_LAUNCH
+    CK(cudaGetLastError());
+    k_tc_finalize<<<dim3((Mcap + 7) / 8, B), 256, 0, ws.stream>>>(ws.maxkey.as<uint32_t>(), ws.qoff.as<int>(), QS, in.nkept,
+                                                                  Mcap, in.tokp, ws.est.as<float>());
+    CK(cudaGetLastError());
+    int Pm = 1;
+    while (Pm < Mcap) Pm <<= 1;
+    CKS(set_smem(k_tc_select, (size_t)Pm * 8));
+    k_tc_select<<<B, 1024, (size_t)Pm * 8, ws.stream>>>(ws.est.as<float>(), in.kept, in.krank, in.nkept, Mcap, top_k,
+                                                        ws.qoff.as<int>(), ws.qnmax.as<float>(), eps_unit,
+                                                        ix->doc_off.as<long long>(), out.kept, out.krank, out.nkept,
+                                                        out.tokp, ws.ktok2.as<long long>());
+    CK(cudaGetLastError());
+    if (launches) *launches += 3;
     return PB_OK;
 }
 
@@ -717,7 +801,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
                 CK(cudaMemcpyAsync(ws.Q.p, ws.hq.p, (size_t)R * ix->dim * 4, cudaMemcpyHostToDevice, ws.stream));
             }
         }
-        CKS(ws.hcounts.ensure((size_t)(B + 1) * 4 + (size_t)B * 16 * 4 + (size_t)(B + 2) * 8 + 64));
+        CKS(ws.hcounts.ensure((size_t)(B + 1) * 4 + (size_t)B * 16 * 4 + (size_t)(B + 2) * 8 + 64 + (size_t)B * 12 + 16));
         memcpy(ws.hcounts.p, qoff.data(), (size_t)(B + 1) * 4);
         CK(cudaMemcpyAsync(ws.qoff.p, ws.hcounts.p, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ws.stream));
         if (prof) CK(cudaEventRecord(ws.ev[1], ws.stream));
@@ -911,15 +995,37 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         CKS(ws.maxkey.ensure((size_t)B * Mcap * QS * 4));
         CKS(ws.exact.ensure((size_t)B * Mcap * 4));
         CKS(ws.fkeys.ensure((size_t)B * Mcap * 8));
-        CKS(launch_exact(ix, ws, B, QS, Mcap, 0, (long long)Mcap * std::max(ix->max_doclen, 1), &L[PB_STAGE_EXACT], nq_max));
+        KeptView kv{ws.kept.as<uint32_t>(), ws.nkept.as<int>(), ws.tokp.as<long long>(),
+                    sharded ? ws.krank.as<uint32_t>() : nullptr};
+        // only the top_k need exact scores: the tensor-core filter drops the docs that provably cannot reach them
+        const float eps_unit = filter_eps_unit(ix);
+        const bool filt = ix->fast_exact && !io.trace && ix->centroids_f16.p && eps_unit > 0.0f && nq_max <= 32 &&
+                          top_k < Mcap && ix->packed % 4 == 0;
+        if (filt) {
+            CKS(ws.est.ensure((size_t)B * Mcap * 4));
+            CKS(ws.kept2.ensure((size_t)B * Mcap * 4));
+            CKS(ws.krank2.ensure((size_t)B * Mcap * 4));
+            CKS(ws.nkept2.ensure((size_t)B * 4 + 16));
+            CKS(ws.tokp2.ensure((size_t)B * (Mcap + 1) * 8));
+            CKS(ws.ktok2.ensure((size_t)B * 8 + 16));
+            CKS(ws.qnmax.ensure((size_t)B * 4 + 16));
+            k_query_norm_max<<<B, 32, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), ix->dim, ws.qnmax.as<float>());
+            CK(cudaGetLastError());
+            KeptView kv2{ws.kept2.as<uint32_t>(), ws.nkept2.as<int>(), ws.tokp2.as<long long>(), ws.krank2.as<uint32_t>()};
+            CKS(launch_filter(ix, ws, kv, kv2, B, QS, Mcap, top_k, (long long)Mcap * std::max(ix->max_doclen, 1), eps_unit,
+                              &L[PB_STAGE_EXACT]));
+            L[PB_STAGE_EXACT] += 1;
+            kv = kv2;
+            if (!sharded) kv.krank = nullptr;  // survivors keep their order, so position breaks ties the same way
+        }
+        CKS(launch_exact(ix, ws, kv, B, QS, Mcap, 0, (long long)Mcap * std::max(ix->max_doclen, 1), &L[PB_STAGE_EXACT]));
         if (sharded) {
             CKS(ws.payload.ensure((size_t)B * Mcap * 8));
             CK(cudaMemsetAsync(ws.fkeys.p, 0xff, (size_t)B * Mcap * 8, ws.stream));  // ~0 = no entry
         }
         k_exact_finalize<<<dim3((Mcap + 7) / 8, B), 256, 0, ws.stream>>>(
-            ws.maxkey.as<uint32_t>(), ws.qoff.as<int>(), QS, ws.nkept.as<int>(), Mcap, 0, ws.exact.as<float>(),
-            ws.fkeys.as<u64>(), sharded ? ws.krank.as<uint32_t>() : nullptr, ws.kept.as<uint32_t>(),
-            (uint32_t)ix->doc_id_base, sharded ? ws.payload.as<u64>() : nullptr);
+            ws.maxkey.as<uint32_t>(), ws.qoff.as<int>(), QS, kv.nkept, Mcap, 0, ws.exact.as<float>(),
+            ws.fkeys.as<u64>(), kv.krank, kv.kept, (uint32_t)ix->doc_id_base, sharded ? ws.payload.as<u64>() : nullptr);
         CK(cudaGetLastError());
         L[PB_STAGE_EXACT] += 1;
         if (prof) CK(cudaEventRecord(ws.ev[7], ws.stream));
@@ -956,8 +1062,8 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             L[PB_STAGE_TOPK] += 3;
         } else {
             CKS(set_smem(k_topk, (size_t)Pm * 8));
-            k_topk<<<B, 1024, (size_t)Pm * 8, ws.stream>>>(ws.fkeys.as<u64>(), ws.exact.as<float>(), ws.kept.as<uint32_t>(),
-                                                           ws.nkept.as<int>(), Mcap, top_k, ix->doc_id_base, d_ids, d_sc, d_cn);
+            k_topk<<<B, 1024, (size_t)Pm * 8, ws.stream>>>(ws.fkeys.as<u64>(), ws.exact.as<float>(), kv.kept, kv.nkept, Mcap,
+                                                           top_k, ix->doc_id_base, d_ids, d_sc, d_cn);
             CK(cudaGetLastError());
             L[PB_STAGE_TOPK] += 1;
         }
@@ -971,6 +1077,12 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         unsigned long long *hcnt = reinterpret_cast<unsigned long long *>(hc + 4 * B);  // 8-byte aligned: (B+1+4B) ints
         if ((reinterpret_cast<uintptr_t>(hcnt) & 7) != 0) hcnt = reinterpret_cast<unsigned long long *>(hc + 4 * B + 1);
         CK(cudaMemcpyAsync(hcnt, ws.counters.p, (size_t)(B + 2) * 8, cudaMemcpyDeviceToHost, ws.stream));
+        long long *hsurv_tok = reinterpret_cast<long long *>(hcnt + (B + 2));  // [B] survivors' tokens, then [B] ints
+        int *hsurv = reinterpret_cast<int *>(hsurv_tok + B);
+        if (filt) {
+            CK(cudaMemcpyAsync(hsurv_tok, ws.ktok2.p, (size_t)B * 8, cudaMemcpyDeviceToHost, ws.stream));
+            CK(cudaMemcpyAsync(hsurv, ws.nkept2.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
+        }
         if (!io.out_on_device) {
             size_t bytes = (size_t)B * top_k * 12 + (size_t)B * 4;
             CKS(ws.hres.ensure(bytes));
@@ -999,8 +1111,15 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         for (int b = 0; b < B; ++b) {
             g_stats.work.n_cells += hc[b];
             g_stats.work.n_candidates += hc[B + b];
-            g_stats.work.n_exact_docs += hc[2 * B + b];
-            g_stats.work.n_exact_tokens += (long long)hcnt[1 + b];
+            if (filt) {
+                g_stats.work.n_filter_docs += hc[2 * B + b];
+                g_stats.work.n_filter_tokens += (long long)hcnt[1 + b];
+                g_stats.work.n_exact_docs += hsurv[b];
+                g_stats.work.n_exact_tokens += hsurv_tok[b];
+            } else {
+                g_stats.work.n_exact_docs += hc[2 * B + b];
+                g_stats.work.n_exact_tokens += (long long)hcnt[1 + b];
+            }
         }
         // ---- optional trace (tests only; synchronous copies) ----
         if (io.trace) {
@@ -1242,7 +1361,8 @@ extern "C" pb_status pb_exhaustive_scores(pb_index *ix, const float *queries, co
             k_fill_identity<<<64, 256, 0, ws.stream>>>(ws.kept.as<uint32_t>(), nd, (uint32_t)d0);
             k_range_prefix<<<64, 256, 0, ws.stream>>>(ix->doc_off.as<long long>(), d0, nd, ws.tokp.as<long long>());
             CK(cudaMemcpyAsync(ws.nkept.p, &nd, 4, cudaMemcpyHostToDevice, ws.stream));
-            CKS(launch_exact(ix, ws, B, QS, Mblk, 1, doff[d0 + nd] - doff[d0], nullptr, nq_max));
+            const KeptView kv{ws.kept.as<uint32_t>(), ws.nkept.as<int>(), ws.tokp.as<long long>(), nullptr};
+            CKS(launch_exact(ix, ws, kv, B, QS, Mblk, 1, doff[d0 + nd] - doff[d0], nullptr));
             k_exact_finalize<<<dim3((Mblk + 7) / 8, B), 256, 0, ws.stream>>>(ws.maxkey.as<uint32_t>(), ws.qoff.as<int>(), QS,
                                                                            ws.nkept.as<int>(), Mblk, 1, ws.exact.as<float>(),
                                                                            nullptr, nullptr, nullptr, 0u, nullptr);

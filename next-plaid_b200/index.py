@@ -64,7 +64,8 @@ class _Trace(C.Structure):
 
 class _Work(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_queries", "n_query_tokens", "n_cells", "n_candidates",
-                                         "n_candidate_tokens", "n_exact_docs", "n_exact_tokens")]
+                                         "n_candidate_tokens", "n_exact_docs", "n_exact_tokens",
+                                         "n_filter_docs", "n_filter_tokens")]
 
 
 EXPORTS = [
@@ -74,7 +75,7 @@ EXPORTS = [
     "pb_search_batch", "pb_search_batch_traced", "pb_centroid_scores", "pb_decompress_documents",
     "pb_maxsim_scores", "pb_exhaustive_scores", "pb_set_profiling", "pb_last_stage_stats",
     "pb_last_work_counters", "pb_search_batch_device", "pb_last_error", "pb_version",
-    "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init", "pb_set_fast_approx",
+    "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init", "pb_set_fast_approx", "pb_set_fast_exact",
     "pb_codec_open", "pb_codec_close", "pb_codec_compress_into_codes", "pb_codec_compress_and_residuals",
     "pb_codec_encode_chunk", "pb_kmeans_fit", "pb_codec_last_assign_stats", "pb_codec_find_outliers",
 ]
@@ -106,6 +107,8 @@ def load_library():
         L.pb_set_profiling.restype = None
         L.pb_set_fast_approx.argtypes = [C.c_void_p, C.c_int32]
         L.pb_set_fast_approx.restype = None
+        L.pb_set_fast_exact.argtypes = [C.c_void_p, C.c_int32]
+        L.pb_set_fast_exact.restype = None
         L.pb_index_load.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
         L.pb_index_open.argtypes = [C.POINTER(_Desc), C.POINTER(C.c_void_p)]
         L.pb_search_batch_traced.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
@@ -369,6 +372,10 @@ class MmapIndex:
     def set_fast_approx(self, mode):
         """0/False = single exact pass, 1/True = two-pass (default), 2 = two-pass + pruning cascade."""
         load_library().pb_set_fast_approx(self._h, int(mode))
+
+    def set_fast_exact(self, on: bool):
+        """tcgen05 certified filter in front of the exact stage (default on); same results either way."""
+        load_library().pb_set_fast_exact(self._h, 1 if on else 0)
 
     def set_profiling(self, on: bool):
         load_library().pb_set_profiling(self._h, 1 if on else 0)

@@ -327,3 +327,52 @@ def test_randomized_search_parity(oracle, npb):
                 checked += 1
         gpu.close()
     assert checked >= 100
+
+
+def test_tensor_core_filter_equals_full_exact_stage(oracle, npb, corpus):
+    # DESIGN.md "a7' certified filter": the fp16 tcgen05 estimate may only drop docs that provably cannot reach
+    # the top_k, so results with the filter on / off / the oracle's are the same bits
+    docs, ix, qs, src, gpu = corpus
+    for kw in (dict(top_k=5, n_full_scores=2048), dict(top_k=100, n_full_scores=4096, centroid_score_threshold=None),
+               dict(top_k=1, n_full_scores=512, n_ivf_probe=16), dict(top_k=30, n_full_scores=400, centroid_batch_size=128)):
+        pg, po = _params(npb, oracle, **kw)
+        gpu.set_fast_exact(True)
+        on = gpu.search_batch(qs, pg)
+        work = gpu.last_work_counters()
+        gpu.set_fast_exact(False)
+        off = gpu.search_batch(qs, pg)
+        work_off = gpu.last_work_counters()
+        gpu.set_fast_exact(True)
+        assert work["n_filter_docs"] > 0 and work_off["n_filter_docs"] == 0, kw
+        assert work["n_filter_docs"] == work_off["n_exact_docs"], kw
+        assert 0 < work["n_exact_docs"] < work["n_filter_docs"], (kw, work)   # it did filter
+        for q, a, b in zip(qs, on, off):
+            w = oracle.search_one(ix, q, po)
+            assert a.passage_ids.tolist() == b.passage_ids.tolist() == w.passage_ids.tolist(), kw
+            assert np.array_equal(a.scores, w.scores) and np.array_equal(b.scores, w.scores), kw
+
+
+def test_tensor_core_filter_with_ties_scaled_and_nonfinite_queries(oracle, npb):
+    # byte-identical docs tie exactly at the top_k boundary: all of them must survive the filter so that the
+    # approximate-rank tie-break (search.rs:496-515, stable sort) decides; odd query norms scale the bound
+    base = oracle.synthetic_corpus(40, 40, dim=128, seed=15)
+    docs = [base[i % 5] if i % 3 else base[i % 40] for i in range(700)]
+    docs[17] = docs[17][:0]                      # a doc without tokens scores 0
+    ix = oracle.create_index(docs, nbits=2, seed=3, num_partitions=64)
+    qs, _ = oracle.synthetic_queries(docs, 5, nq=24, seed=8)
+    qs.append(qs[0] * 9.0)
+    qs.append(qs[1] * 1e-4)
+    bad = qs[2].copy(); bad[1, 7] = np.nan
+    qs.append(bad)
+    gpu = _gpu_index(npb, ix)
+    for kw in (dict(top_k=10, n_full_scores=1024, centroid_score_threshold=None, n_ivf_probe=16),
+               dict(top_k=3, n_full_scores=2800, centroid_score_threshold=None, n_ivf_probe=64),
+               dict(top_k=60, n_full_scores=600, centroid_score_threshold=0.2)):
+        pg, po = _params(npb, oracle, **kw)
+        for on in (True, False):
+            gpu.set_fast_exact(on)
+            for q, r in zip(qs, gpu.search_batch(qs, pg)):
+                w = oracle.search_one(ix, q, po)
+                assert r.passage_ids.tolist() == w.passage_ids.tolist(), (kw, on)
+                assert np.array_equal(r.scores, w.scores, equal_nan=True), (kw, on)
+    gpu.close()
