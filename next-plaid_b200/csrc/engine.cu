@@ -578,7 +578,7 @@ static pb_status launch_exact(pb_index *ix, Workspace &ws, const KeptView &kv, i
 }
 
 static size_t smem_exact_tc(int dim, int packed) {
-    return (size_t)(dim / 8) * PB_XTC_LBO + (size_t)32 * dim * 2 + (size_t)128 * packed + 128 * 4 + 256 * 4 + 64;
+    return (size_t)(dim / 8) * PB_XTC_LBO + (size_t)32 * dim * 2 + (size_t)128 * packed + 256 * 4 + 64;
 }
 
 // error of one fp16 tensor-core similarity relative to |q| (derivation above k_exact_tc); 0 = filter unusable
@@ -587,7 +587,8 @@ static float filter_eps_unit(const pb_index *ix) {
     const float vmin = ix->vmin * 0.9999f;
     if (!(vmin > u * ix->cmax) || !(ix->cmax < 3.0e4f)) return 0.0f;  // centroids must fit fp16
     const float dterm = u * ix->cmax / (vmin - 0.5f * u * ix->cmax);  // |D - D~| (Dunkl-Williams)
-    return u + (1.0f + u) * (dterm + u) + 4e-5f;
+    const float sub = sqrtf((float)ix->dim) * 2.98e-8f / vmin;        // fp16 subnormal spacing 2^-25 per component of v
+    return u + (1.0f + u) * (dterm + u) + sub + 4e-5f;
 }
 
 // a7': tensor-core estimate of every kept doc, then the survivors that can still reach the top_k
@@ -597,22 +598,30 @@ static pb_status launch_filter(pb_index *ix, Workspace &ws, const KeptView &in, 
     long long want = std::max<long long>(1, ((long long)ix->sm_count * 32 + B - 1) / B);
     int gx = (int)std::max<long long>(1, std::min<long long>(chunks, want));
     const size_t sm = smem_exact_tc(ix->dim, ix->packed);
-#define PB_TC_LAUNCH(DV)                                                                                               \
+#define PB_TC_LAUNCH(DV, NB)                                                                                           \
     {                                                                                                                  \
-        auto kern = k_exact_tc<DV>;                                                                                    \
+        auto kern = k_exact_tc<DV, NB>;                                                                                \
         CKS(set_smem(kern, sm));                                                                                       \
         kern<<<dim3(gx, B), 128, sm, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS,                             \
                                                   ix->centroids_f16.as<__half>(), ix->w_rev.as<float>(),               \
-                                                  ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(),    \
+                                                  ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(),               \
                                                   ix->doc_off.as<long long>(), in.kept, in.nkept, in.tokp, Mcap,       \
                                                   ws.maxkey.as<uint32_t>());                                           \
     }
+#define PB_TC_NBITS(DV)                                                                                                \
+    switch (ix->nbits) {                                                                                               \
+        case 1: PB_TC_LAUNCH(DV, 1) break;                                                                             \
+        case 2: PB_TC_LAUNCH(DV, 2) break;                                                                             \
+        case 4: PB_TC_LAUNCH(DV, 4) break;                                                                             \
+        default: PB_TC_LAUNCH(DV, 8) break;                                                                            \
+    }
     switch (ix->dim) {
-        case 64: PB_TC_LAUNCH(64) break;
-        case 96: PB_TC_LAUNCH(96) break;
-        case 128: PB_TC_LAUNCH(128) break;
+        case 64: PB_TC_NBITS(64) break;
+        case 96: PB_TC_NBITS(96) break;
+        case 128: PB_TC_NBITS(128) break;
         default: return pb_fail(PB_ERR_UNSUPPORTED, "filter: unsupported dim");
     }
+#undef PB_TC_NBITS
 #undef PB_TC_LAUNCH
     CK(cudaGetLastError());
     k_tc_finalize<<<dim3((Mcap + 7) / 8, B), 256, 0, ws.stream>>>(ws.maxkey.as<uint32_t>(), ws.qoff.as<int>(), QS, in.nkept,
