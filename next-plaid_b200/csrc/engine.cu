@@ -172,7 +172,7 @@ struct Workspace {
     cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2, cand3, ncand3, ub, theta, rel, cellbits,
-        gkeys, krank, payload, gfkeys, gpayload, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax;
+        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -210,6 +210,7 @@ struct pb_index {
     bool fast_approx = true;   // two-pass approximate stage (exact cut either way)
     bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
                                // the cut sits well above the background score level
+    bool probe16 = true;       // a3 threshold-first selection on the 16-bit table (PB_PROBE16=0: per-lane lists only)
     bool fast_exact = true;    // tcgen05 certified filter in front of the exact stage (same results either way)
     float vmin = 0.0f;         // smallest pre-normalisation token norm |c + w| over the index (error bound of the filter)
     DevBuf centroids_f16;      // [K][dim] fp16 copy for the filter
@@ -431,6 +432,7 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_FAST_APPROX")) ix->fast_approx = atoi(e) != 0;
         if (const char *e = getenv("PB_CASCADE")) ix->cascade = atoi(e) != 0;
         if (const char *e = getenv("PB_FAST_EXACT")) ix->fast_exact = atoi(e) != 0;
+        if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
     }
     if ((ix->dim == 64 || ix->dim == 96 || ix->dim == 128) && ix->N > 0 && ix->K > 0) {
         // operands of the tensor-core filter (k_exact_tc): fp16 centroids and the smallest token norm
@@ -868,10 +870,36 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             CKS(ws.ncells.ensure((size_t)B * 4 + 16));
             size_t sm1 = (size_t)4 * n * 32 * 8;
             CKS(set_smem(k_topn_partial, sm1));
+            // threshold-first selection on the 16-bit table when there is one (k_chunkmax16 / k_collect16);
+            // the per-lane list scan of k_topn_partial otherwise, or when the device raises `fallback`
+            const int GQ = QS / 8;
+            const bool thr_path = fast && !d_elig && ix->probe16 && (GQ & (GQ - 1)) == 0 && GQ <= 32 && n_chunks >= n && n <= 64;
+            int *d_fallback = nullptr;
+            if (thr_path) {
+                const int cap = n * std::max(1, 128 / n);
+                CKS(ws.cmax16.ensure((size_t)B * n_chunks * QS * 2));
+                CKS(ws.tau16.ensure((size_t)B * QS * 4));
+                CKS(ws.plist.ensure((size_t)B * QS * cap * 8));
+                CKS(ws.pcount.ensure((size_t)B * QS * 4 + 16));
+                CK(cudaMemsetAsync(ws.plist.p, 0, (size_t)B * QS * cap * 8, ws.stream));
+                CK(cudaMemsetAsync(ws.pcount.p, 0, (size_t)B * QS * 4 + 16, ws.stream));
+                d_fallback = ws.pcount.as<int>() + (size_t)B * QS;
+                k_chunkmax16<<<dim3((n_chunks + 3) / 4, B), 128, 0, ws.stream>>>(ws.ST16.as<unsigned short>(), ix->K, QS, n_chunks,
+                                                                                 ws.cmax16.as<unsigned short>());
+                k_tau16<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.cmax16.as<unsigned short>(), ws.qoff.as<int>(), QS, n, n_chunks,
+                                                          ws.qflag.as<int>(), ws.tau16.as<uint32_t>(), d_fallback);
+                k_collect16<<<dim3((n_chunks + 3) / 4, B), 128, 0, ws.stream>>>(
+                    ws.ST16.as<unsigned short>(), ws.ST.as<float>(), ix->K, QS, n_chunks, ws.tau16.as<uint32_t>(), cap,
+                    ws.pcount.as<int>(), ws.plist.as<u64>(), d_fallback);
+                k_topn_merge<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.plist.as<u64>(), ws.qoff.as<int>(), QS, n, cap / n,
+                                                              ws.sel.as<u64>(), d_fallback, 0);
+                CK(cudaGetLastError());
+                L[PB_STAGE_PROBE] += 4;
+            }
             k_topn_partial<<<dim3((n_chunks + 3) / 4, B, (QS + 31) / 32), 128, sm1, ws.stream>>>(
-                ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, n, d_elig, ws.partial.as<u64>(), n_chunks);
+                ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, n, d_elig, ws.partial.as<u64>(), n_chunks, d_fallback, 1);
             k_topn_merge<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.partial.as<u64>(), ws.qoff.as<int>(), QS, n, n_chunks,
-                                                          ws.sel.as<u64>());
+                                                          ws.sel.as<u64>(), d_fallback, 1);
             int P = 1;
             while (P < std::max(nq_max * n, 1)) P <<= 1;
             size_t sm2 = (size_t)P * 12;

@@ -376,3 +376,27 @@ def test_tensor_core_filter_with_ties_scaled_and_nonfinite_queries(oracle, npb):
                 assert r.passage_ids.tolist() == w.passage_ids.tolist(), (kw, on)
                 assert np.array_equal(r.scores, w.scores, equal_nan=True), (kw, on)
     gpu.close()
+
+
+def test_probe_threshold_path_and_its_fallbacks(oracle, npb, corpus, monkeypatch):
+    # a3 on the 16-bit table (k_chunkmax16 / k_collect16): same cells as the per-lane list scan and the oracle, including
+    # the device-side fallback (a zero query token ties every centroid -> more than `cap` entries reach the threshold)
+    docs, ix, qs, src, gpu = corpus
+    zero_tok = qs[1].copy(); zero_tok[5] = 0.0
+    dup = qs[2].copy(); dup[7] = dup[3]
+    batch = [qs[0], zero_tok, dup, qs[3] * 3.0, qs[4][:9]]
+    monkeypatch.setenv("PB_PROBE16", "0")
+    plain = _gpu_index(npb, ix)
+    monkeypatch.delenv("PB_PROBE16")
+    for kw in (dict(top_k=10, n_ivf_probe=8, n_full_scores=256), dict(top_k=10, n_ivf_probe=1, n_full_scores=64),
+               dict(top_k=20, n_ivf_probe=32, n_full_scores=512, centroid_score_threshold=None),
+               dict(top_k=10, n_ivf_probe=8, n_full_scores=256, centroid_batch_size=128, centroid_score_threshold=0.3)):
+        pg, po = _params(npb, oracle, **kw)
+        for sub in (batch, [batch[0], batch[3]]):          # with and without the query that forces the fallback
+            a = gpu.search_batch(sub, pg)
+            b = plain.search_batch(sub, pg)
+            for q, x, y in zip(sub, a, b):
+                w = oracle.search_one(ix, q, po)
+                assert x.passage_ids.tolist() == y.passage_ids.tolist() == w.passage_ids.tolist(), kw
+                assert np.array_equal(x.scores, w.scores) and np.array_equal(y.scores, w.scores), kw
+    plain.close()
