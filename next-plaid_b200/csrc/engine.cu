@@ -210,9 +210,11 @@ struct pb_index {
     bool fast_approx = true;   // two-pass approximate stage (exact cut either way)
     bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
                                // the cut sits well above the background score level
+    bool cs256 = false;        // 8-warp k_centroid_scores (PB_CS256=1)
     bool probe16 = true;       // a3 threshold-first selection on the 16-bit table (PB_PROBE16=0: per-lane lists only)
     bool fast_exact = true;    // tcgen05 certified filter in front of the exact stage (same results either way)
     float vmin = 0.0f;         // smallest pre-normalisation token norm |c + w| over the index (error bound of the filter)
+    float wmax = 0.0f;         // largest residual norm |w| over the index (same)
     DevBuf centroids_f16;      // [K][dim] fp16 copy for the filter
     bool profiling = false;
     size_t st_budget = (size_t)4 << 30;
@@ -433,6 +435,7 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_CASCADE")) ix->cascade = atoi(e) != 0;
         if (const char *e = getenv("PB_FAST_EXACT")) ix->fast_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
+        if (const char *e = getenv("PB_CS256")) ix->cs256 = atoi(e) != 0;
     }
     if ((ix->dim == 64 || ix->dim == 96 || ix->dim == 128) && ix->N > 0 && ix->K > 0) {
         // operands of the tensor-core filter (k_exact_tc): fp16 centroids and the smallest token norm
@@ -442,16 +445,18 @@ pb_status pb_index_finalize(pb_index *ix) {
         CK(cudaGetLastError());
         DevBuf mn;
         CKS(mn.ensure(16));
-        const float big = 3.0e38f;
-        CK(cudaMemcpy(mn.p, &big, 4, cudaMemcpyHostToDevice));
+        const float init[2] = {3.0e38f, 0.0f};
+        CK(cudaMemcpy(mn.p, init, 8, cudaMemcpyHostToDevice));
         switch (ix->dim) {
             case 64: k_min_vnorm<64><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>()); break;
             case 96: k_min_vnorm<96><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>()); break;
             default: k_min_vnorm<128><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>()); break;
         }
         CK(cudaGetLastError());
-        CK(cudaMemcpy(&ix->vmin, mn.p, 4, cudaMemcpyDeviceToHost));
-        if (!(ix->vmin < 1e30f)) ix->vmin = 0.0f;
+        float got[2] = {0.f, 0.f};
+        CK(cudaMemcpy(got, mn.p, 8, cudaMemcpyDeviceToHost));
+        ix->vmin = got[0] < 1e30f ? got[0] : 0.0f;
+        ix->wmax = got[1];
     }
     ix->n_ucodes = uoff[ix->D];
     CKS(upload(ix->udoc_off, uoff.data(), uoff.size() * 8, PB_MEM_HOST));
@@ -539,15 +544,27 @@ static pb_status launch_centroid_scores(pb_index *ix, Workspace &ws, int B, int 
     const int tiles = (int)((ix->K + PB_TOK_TILE - 1) / PB_TOK_TILE);
     // enough CTAs to fill the machine twice over; each CTA keeps its centroid tile in smem and walks queries
     int groups = std::max(1, std::min(B, (4 * ix->sm_count + tiles - 1) / tiles));
-    PB_DIM_SWITCH(ix->dim, {
-        auto kern = k_centroid_scores<DIM>;
-        CKS(set_smem(kern, smem_scores(DIM)));
-        kern<<<dim3(tiles, groups), 128, smem_scores(DIM), ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), B, QS,
-                                                                        ix->centroids.as<float>(), ix->K,
-                                                                        ws.ST.as<float>(),
-                                                                        with16 ? ws.ST16.as<unsigned short>() : nullptr,
-                                                                        ws.qrange.as<float2>(), ws.qflag.as<int>());
-    });
+    if (ix->cs256) {
+        PB_DIM_SWITCH(ix->dim, {
+            auto kern = k_centroid_scores256<DIM>;
+            CKS(set_smem(kern, smem_scores(DIM)));
+            kern<<<dim3(tiles, groups), 256, smem_scores(DIM), ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), B, QS,
+                                                                            ix->centroids.as<float>(), ix->K,
+                                                                            ws.ST.as<float>(),
+                                                                            with16 ? ws.ST16.as<unsigned short>() : nullptr,
+                                                                            ws.qrange.as<float2>(), ws.qflag.as<int>());
+        });
+    } else {
+        PB_DIM_SWITCH(ix->dim, {
+            auto kern = k_centroid_scores<DIM>;
+            CKS(set_smem(kern, smem_scores(DIM)));
+            kern<<<dim3(tiles, groups), 128, smem_scores(DIM), ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), B, QS,
+                                                                            ix->centroids.as<float>(), ix->K,
+                                                                            ws.ST.as<float>(),
+                                                                            with16 ? ws.ST16.as<unsigned short>() : nullptr,
+                                                                            ws.qrange.as<float2>(), ws.qflag.as<int>());
+        });
+    }
     CK(cudaGetLastError());
     if (launches) ++*launches;
     return PB_OK;
@@ -580,17 +597,19 @@ static pb_status launch_exact(pb_index *ix, Workspace &ws, const KeptView &kv, i
 }
 
 static size_t smem_exact_tc(int dim, int packed) {
-    return (size_t)(dim / 8) * PB_XTC_LBO + (size_t)32 * dim * 2 + (size_t)128 * packed + 256 * 4 + 64;
+    const int nbits = packed * 8 / dim;
+    return (size_t)(dim / 8) * PB_XTC_LBO + (size_t)32 * dim * 2 + (size_t)128 * packed + (size_t)256 * (8 / nbits) * 2 + 64;
 }
 
 // error of one fp16 tensor-core similarity relative to |q| (derivation above k_exact_tc); 0 = filter unusable
 static float filter_eps_unit(const pb_index *ix) {
     const float u = 1.0f / 2048.0f;  // fp16 unit roundoff
-    const float vmin = ix->vmin * 0.9999f;
-    if (!(vmin > u * ix->cmax) || !(ix->cmax < 3.0e4f)) return 0.0f;  // centroids must fit fp16
-    const float dterm = u * ix->cmax / (vmin - 0.5f * u * ix->cmax);  // |D - D~| (Dunkl-Williams)
-    const float sub = sqrtf((float)ix->dim) * 2.98e-8f / vmin;        // fp16 subnormal spacing 2^-25 per component of v
-    return u + (1.0f + u) * (dterm + u) + sub + 4e-5f;
+    const float vmin = ix->vmin * 0.9999f, wmax = ix->wmax * 1.0001f;
+    if (!(vmin > 0.0f) || !(ix->cmax < 3.0e4f) || !(wmax < 3.0e4f)) return 0.0f;  // operands must fit fp16
+    const float rho = u * ((ix->cmax + wmax) / vmin + 1.0f) * (1.0f + 2.0f * u);  // |v - v~| / |v|
+    if (!(rho < 0.25f)) return 0.0f;
+    const float sub = 3.0f * sqrtf((float)ix->dim) * 2.98e-8f / vmin;  // fp16 subnormal spacing 2^-25: h(c), h(w), their sum
+    return u + (1.0f + u) * rho / (1.0f - 0.5f * rho) + sub + 4e-5f;
 }
 
 // a7': tensor-core estimate of every kept doc, then the survivors that can still reach the top_k
