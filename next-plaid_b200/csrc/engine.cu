@@ -210,7 +210,6 @@ struct pb_index {
     bool fast_approx = true;   // two-pass approximate stage (exact cut either way)
     bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
                                // the cut sits well above the background score level
-    bool cs256 = false;        // 8-warp k_centroid_scores (PB_CS256=1)
     bool probe16 = true;       // a3 threshold-first selection on the 16-bit table (PB_PROBE16=0: per-lane lists only)
     bool fast_exact = true;    // tcgen05 certified filter in front of the exact stage (same results either way)
     float vmin = 0.0f;         // smallest pre-normalisation token norm |c + w| over the index (error bound of the filter)
@@ -435,7 +434,6 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_CASCADE")) ix->cascade = atoi(e) != 0;
         if (const char *e = getenv("PB_FAST_EXACT")) ix->fast_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
-        if (const char *e = getenv("PB_CS256")) ix->cs256 = atoi(e) != 0;
     }
     if ((ix->dim == 64 || ix->dim == 96 || ix->dim == 128) && ix->N > 0 && ix->K > 0) {
         // operands of the tensor-core filter (k_exact_tc): fp16 centroids and the smallest token norm
@@ -544,27 +542,15 @@ static pb_status launch_centroid_scores(pb_index *ix, Workspace &ws, int B, int 
     const int tiles = (int)((ix->K + PB_TOK_TILE - 1) / PB_TOK_TILE);
     // enough CTAs to fill the machine twice over; each CTA keeps its centroid tile in smem and walks queries
     int groups = std::max(1, std::min(B, (4 * ix->sm_count + tiles - 1) / tiles));
-    if (ix->cs256) {
-        PB_DIM_SWITCH(ix->dim, {
-            auto kern = k_centroid_scores256<DIM>;
-            CKS(set_smem(kern, smem_scores(DIM)));
-            kern<<<dim3(tiles, groups), 256, smem_scores(DIM), ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), B, QS,
-                                                                            ix->centroids.as<float>(), ix->K,
-                                                                            ws.ST.as<float>(),
-                                                                            with16 ? ws.ST16.as<unsigned short>() : nullptr,
-                                                                            ws.qrange.as<float2>(), ws.qflag.as<int>());
-        });
-    } else {
-        PB_DIM_SWITCH(ix->dim, {
-            auto kern = k_centroid_scores<DIM>;
-            CKS(set_smem(kern, smem_scores(DIM)));
-            kern<<<dim3(tiles, groups), 128, smem_scores(DIM), ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), B, QS,
-                                                                            ix->centroids.as<float>(), ix->K,
-                                                                            ws.ST.as<float>(),
-                                                                            with16 ? ws.ST16.as<unsigned short>() : nullptr,
-                                                                            ws.qrange.as<float2>(), ws.qflag.as<int>());
-        });
-    }
+    PB_DIM_SWITCH(ix->dim, {
+        auto kern = k_centroid_scores<DIM>;
+        CKS(set_smem(kern, smem_scores(DIM)));
+        kern<<<dim3(tiles, groups), 128, smem_scores(DIM), ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), B, QS,
+                                                                        ix->centroids.as<float>(), ix->K,
+                                                                        ws.ST.as<float>(),
+                                                                        with16 ? ws.ST16.as<unsigned short>() : nullptr,
+                                                                        ws.qrange.as<float2>(), ws.qflag.as<int>());
+    });
     CK(cudaGetLastError());
     if (launches) ++*launches;
     return PB_OK;
@@ -598,7 +584,7 @@ static pb_status launch_exact(pb_index *ix, Workspace &ws, const KeptView &kv, i
 
 static size_t smem_exact_tc(int dim, int packed) {
     const int nbits = packed * 8 / dim;
-    return (size_t)(dim / 8) * PB_XTC_LBO + (size_t)32 * dim * 2 + (size_t)128 * packed + (size_t)256 * (8 / nbits) * 2 + 64;
+    return (size_t)(dim / 8) * PB_XTC_LBO + (size_t)32 * dim * 2 + (size_t)256 * (8 / nbits) * 2 + 64;
 }
 
 // error of one fp16 tensor-core similarity relative to |q| (derivation above k_exact_tc); 0 = filter unusable

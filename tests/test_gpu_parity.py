@@ -401,17 +401,3 @@ def test_probe_threshold_path_and_its_fallbacks(oracle, npb, corpus, monkeypatch
                 assert np.array_equal(x.scores, w.scores) and np.array_equal(y.scores, w.scores), kw
     plain.close()
 
-
-def test_eight_warp_centroid_scores_variant(oracle, npb, corpus, monkeypatch):
-    # PB_CS256=1 selects k_centroid_scores256 (4 q x 4 c per lane, 8 warps): same sequential-j FMA per dot
-    docs, ix, qs, src, gpu = corpus
-    monkeypatch.setenv("PB_CS256", "1")
-    alt = _gpu_index(npb, ix)
-    monkeypatch.delenv("PB_CS256")
-    for q in (qs[0], qs[1][:5], qs[2][:19]):
-        assert np.array_equal(alt.centroid_scores(q), oracle.centroid_scores(q, ix.centroids))
-    pg, po = _params(npb, oracle, top_k=10, n_full_scores=256)
-    for q, r in zip(qs, alt.search_batch(qs, pg)):
-        w = oracle.search_one(ix, q, po)
-        assert r.passage_ids.tolist() == w.passage_ids.tolist() and np.array_equal(r.scores, w.scores)
-    alt.close()
