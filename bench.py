@@ -395,7 +395,7 @@ def run_b200(args):
     alg = {
         # C read once per launch, fp32 S written once, 16-bit copy written once
         "centroid_scores": args.steps * K * args.dim * 4 + nq_tot * K * 6,
-        "probe": nq_tot * K * 4,                                   # S streamed once
+        "probe": 2 * nq_tot * K * 2,                               # 16-bit S streamed twice (chunk maxima, collect)
         # one u32 code per (candidate, distinct code) + each 16-bit S entry once
         "approx": work.get("n_candidate_tokens", 0) * 4 + nq_tot * K * 2,
         # packed residual + code per token: once for every kept doc in the tensor-core filter (k_exact_tc), once
@@ -406,7 +406,7 @@ def run_b200(args):
     flops = {"centroid_scores": 2.0 * nq_tot * K * args.dim,
              "exact": 2.0 * work.get("n_exact_tokens", 0) * args.nq * args.dim}
     names = {"approx": "k_approx16 (+k_select_u32, k_approx re-check)", "exact": "k_exact_tc (tcgen05 filter) + k_exact (survivors)", "centroid_scores": "k_centroid_scores",
-             "probe": "k_topn_partial (+merge, k_cells)", "cut": "k_cut", "candidates": "k_mark/k_compact", "topk": "k_topk"}
+             "probe": "k_chunkmax16 + k_collect16 (+k_tau16, k_topn_merge, k_cells)", "cut": "k_cut", "candidates": "k_mark/k_compact", "topk": "k_topk"}
     per_stage = {}
     for st, ms_tot in kern_stages.items():
         ms1 = ms_tot / max(args.steps, 1)
@@ -418,9 +418,10 @@ def run_b200(args):
             ent["frac_of_fp32_fma_peak"] = ent["fp32_tflops"] / 74.4   # 148 SMs x 128 FMA x 2 x 1.965 GHz
         per_stage[st] = ent
     # dram__bytes_read.sum + dram__bytes_write.sum of the stage's main kernel, one launch, from the committed
-    # `ncu --set full` capture of this exact workload (profiles/r01_ncu_full_top4_raw.csv); null for other shapes
-    ncu_traffic = {"approx": 2.260998e9 + 0.018709e9,
-                   "centroid_scores": 0.138181e9 + 1.555811e9, "probe": 1.073790e9 + 0.017651e9}
+    # `ncu --set full` captures of this exact workload (profiles/r01_ncu_full_top2_raw.csv for k_approx16 and
+    # k_exact_tc, r01_ncu_full_top4_raw.csv for k_centroid_scores); null for other shapes
+    ncu_traffic = {"approx": 2.269352e9 + 0.012187e9, "exact": 0.966227e9 + 0.008221e9,
+                   "centroid_scores": 0.138181e9 + 1.555811e9}
     default_shape = (args.docs, args.doclen, args.dim, args.nbits, args.log2k, args.batch, args.nq, args.top_k,
                      args.n_ivf_probe, args.n_full_scores) == (1_000_000, 300, 128, 4, 18, 32, 32, 100, 8, 4096)
     dom = max(kern_stages, key=kern_stages.get)
@@ -429,7 +430,9 @@ def run_b200(args):
             "frac": d["frac_of_hbm_peak"], "traffic": ncu_traffic.get(dom) if (default_shape and world == 1) else None,
             "peak_source": peak_src, "ms_per_launch": d["ms_per_step"],
             "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_step"],
-            "note": "k_exact and k_centroid_scores are fp32-FMA bound by design (pinned accumulation order, "
+            "note": "k_approx16 gathers 64-byte rows of the 16-bit score table out of L2 (86 % hit rate): it is bound by "
+                    "the L1 tag / request path (l1tex 79 % busy, profiles/r01_summary.md), not by HBM bytes; "
+                    "k_exact and k_centroid_scores are fp32-FMA bound by design (pinned accumulation order, "
                     "DESIGN.md Numerics): see fp32_tflops in roofline_all",
             "fp32_tflops": d.get("fp32_tflops"), "frac_of_fp32_fma_peak": d.get("frac_of_fp32_fma_peak")}
 
