@@ -210,6 +210,8 @@ struct pb_index {
     bool fast_approx = true;   // two-pass approximate stage (exact cut either way)
     bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
                                // the cut sits well above the background score level
+    int approx_grid = 8;       // k_approx16 CTAs per SM and query (PB_APPROX_GRID)
+    int xtc_grid = 32;         // k_exact_tc CTAs per SM across the batch (PB_XTC_GRID)
     bool probe16 = true;       // a3 threshold-first selection on the 16-bit table (PB_PROBE16=0: per-lane lists only)
     bool fast_exact = true;    // tcgen05 certified filter in front of the exact stage (same results either way)
     float vmin = 0.0f;         // smallest pre-normalisation token norm |c + w| over the index (error bound of the filter)
@@ -434,6 +436,8 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_CASCADE")) ix->cascade = atoi(e) != 0;
         if (const char *e = getenv("PB_FAST_EXACT")) ix->fast_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
+        if (const char *e = getenv("PB_APPROX_GRID")) ix->approx_grid = std::max(1, atoi(e));
+        if (const char *e = getenv("PB_XTC_GRID")) ix->xtc_grid = std::max(1, atoi(e));
     }
     if ((ix->dim == 64 || ix->dim == 96 || ix->dim == 128) && ix->N > 0 && ix->K > 0) {
         // operands of the tensor-core filter (k_exact_tc): fp16 centroids and the smallest token norm
@@ -602,7 +606,7 @@ static float filter_eps_unit(const pb_index *ix) {
 static pb_status launch_filter(pb_index *ix, Workspace &ws, const KeptView &in, const KeptView &out, int B, int QS, int Mcap,
                                int top_k, long long max_tokens, float eps_unit, int *launches) {
     long long chunks = (max_tokens + 127) / 128;
-    long long want = std::max<long long>(1, ((long long)ix->sm_count * 32 + B - 1) / B);
+    long long want = std::max<long long>(1, ((long long)ix->sm_count * ix->xtc_grid + B - 1) / B);
     int gx = (int)std::max<long long>(1, std::min<long long>(chunks, want));
     const size_t sm = smem_exact_tc(ix->dim, ix->packed);
 #define PB_TC_LAUNCH(DV, NB)                                                                                           \
@@ -942,7 +946,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             CKS(ws.lsum.ensure((size_t)B * ix->D * 4));
             CKS(ws.cand2.ensure((size_t)B * ix->D * 4));
             CKS(ws.ncand2.ensure((size_t)B * 4 + 16));
-            const dim3 ga(ix->sm_count * 8, B);
+            const dim3 ga(ix->sm_count * ix->approx_grid, B);
             const unsigned short *st16 = ws.ST16.as<unsigned short>();
             const uint32_t *list = ws.cand.as<uint32_t>();
             const int *list_n = ws.ncand.as<int>();
