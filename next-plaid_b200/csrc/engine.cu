@@ -172,7 +172,7 @@ struct Workspace {
     cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2, cand3, ncand3, ub, theta, rel, cellbits,
-        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax;
+        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -210,6 +210,8 @@ struct pb_index {
     bool fast_approx = true;   // two-pass approximate stage (exact cut either way)
     bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
                                // the cut sits well above the background score level
+    bool fma2 = false;         // FFMA2 (fma.rn.f32x2) variant of k_centroid_scores (PB_FMA2=1; same bits)
+    bool approx_cg = false;    // k_approx16 row gathers bypass L1 allocation (PB_APPROX_CG=1)
     int approx_grid = 8;       // k_approx16 CTAs per SM and query (PB_APPROX_GRID)
     int xtc_grid = 32;         // k_exact_tc CTAs per SM across the batch (PB_XTC_GRID)
     bool probe16 = true;       // a3 threshold-first selection on the 16-bit table (PB_PROBE16=0: per-lane lists only)
@@ -436,6 +438,8 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_CASCADE")) ix->cascade = atoi(e) != 0;
         if (const char *e = getenv("PB_FAST_EXACT")) ix->fast_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
+        if (const char *e = getenv("PB_FMA2")) ix->fma2 = atoi(e) != 0;
+        if (const char *e = getenv("PB_APPROX_CG")) ix->approx_cg = atoi(e) != 0;
         if (const char *e = getenv("PB_APPROX_GRID")) ix->approx_grid = std::max(1, atoi(e));
         if (const char *e = getenv("PB_XTC_GRID")) ix->xtc_grid = std::max(1, atoi(e));
     }
@@ -546,8 +550,26 @@ static pb_status launch_centroid_scores(pb_index *ix, Workspace &ws, int B, int 
     const int tiles = (int)((ix->K + PB_TOK_TILE - 1) / PB_TOK_TILE);
     // enough CTAs to fill the machine twice over; each CTA keeps its centroid tile in smem and walks queries
     int groups = std::max(1, std::min(B, (4 * ix->sm_count + tiles - 1) / tiles));
+    if (ix->fma2) {
+        // FFMA2 variant (PB_FMA2=1): query rows interleaved pairwise, one packed FMA per two dots
+        CKS(ws.Qi.ensure((size_t)B * QS * ix->dim * 4));
+        k_interleave_query_rows<<<dim3(8, B), 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->dim,
+                                                                   ws.Qi.as<float>());
+        PB_DIM_SWITCH(ix->dim, {
+            auto kern = k_centroid_scores<DIM, true>;
+            CKS(set_smem(kern, smem_scores(DIM)));
+            kern<<<dim3(tiles, groups), 128, smem_scores(DIM), ws.stream>>>(ws.Qi.as<float>(), ws.qoff.as<int>(), B, QS,
+                                                                            ix->centroids.as<float>(), ix->K,
+                                                                            ws.ST.as<float>(),
+                                                                            with16 ? ws.ST16.as<unsigned short>() : nullptr,
+                                                                            ws.qrange.as<float2>(), ws.qflag.as<int>());
+        });
+        CK(cudaGetLastError());
+        if (launches) *launches += 2;
+        return PB_OK;
+    }
     PB_DIM_SWITCH(ix->dim, {
-        auto kern = k_centroid_scores<DIM>;
+        auto kern = k_centroid_scores<DIM, false>;
         CKS(set_smem(kern, smem_scores(DIM)));
         kern<<<dim3(tiles, groups), 128, smem_scores(DIM), ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), B, QS,
                                                                         ix->centroids.as<float>(), ix->K,
@@ -972,7 +994,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
                 k_select_u32<<<B, 1024, 0, ws.stream>>>(ws.ub.as<uint32_t>(), list_n, 2 * M, 0, ws.ub.as<uint32_t>(), list,
                                                         list_n, ix->D, ws.qoff.as<int>(), ws.qflag.as<int>(),
                                                         ws.cand2.as<uint32_t>(), ws.ncand2.as<int>());
-                k_approx16<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
+                (ix->approx_cg ? k_approx16<true> : k_approx16<false>)<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
                                                       ix->udoc_off.as<long long>(), ws.cand2.as<uint32_t>(), ix->D,
                                                       ws.ncand2.as<int>(), ws.lsum.as<uint32_t>(), cnt + B + 1);
                 // list2 = every candidate whose upper bound reaches tau' - W
@@ -984,7 +1006,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
                 list = ws.cand3.as<uint32_t>();
                 list_n = ws.ncand3.as<int>();
             }
-            k_approx16<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
+            (ix->approx_cg ? k_approx16<true> : k_approx16<false>)<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
                                                   ix->udoc_off.as<long long>(), list, ix->D, list_n, ws.lsum.as<uint32_t>(),
                                                   cascade ? cnt + B + 1 : cnt);
             k_select_u32<<<B, 1024, 0, ws.stream>>>(ws.lsum.as<uint32_t>(), list_n, M, 4, ws.lsum.as<uint32_t>(), list, list_n,
