@@ -210,7 +210,7 @@ struct pb_index {
     bool fast_approx = true;   // two-pass approximate stage (exact cut either way)
     bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
                                // the cut sits well above the background score level
-    bool fma2 = false;         // FFMA2 (fma.rn.f32x2) variant of k_centroid_scores (PB_FMA2=1; same bits)
+    bool fma2 = true;          // FFMA2 (fma.rn.f32x2) k_centroid_scores; PB_FMA2=0 selects the scalar-FFMA twin (same bits)
     bool approx_cg = false;    // k_approx16 row gathers bypass L1 allocation (PB_APPROX_CG=1)
     int approx_grid = 8;       // k_approx16 CTAs per SM and query (PB_APPROX_GRID)
     int xtc_grid = 32;         // k_exact_tc CTAs per SM across the batch (PB_XTC_GRID)
@@ -551,7 +551,7 @@ static pb_status launch_centroid_scores(pb_index *ix, Workspace &ws, int B, int 
     // enough CTAs to fill the machine twice over; each CTA keeps its centroid tile in smem and walks queries
     int groups = std::max(1, std::min(B, (4 * ix->sm_count + tiles - 1) / tiles));
     if (ix->fma2) {
-        // FFMA2 variant (PB_FMA2=1): query rows interleaved pairwise, one packed FMA per two dots
+        // FFMA2 variant (default): query rows interleaved pairwise, one packed FMA per two dots
         CKS(ws.Qi.ensure((size_t)B * QS * ix->dim * 4));
         k_interleave_query_rows<<<dim3(8, B), 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->dim,
                                                                    ws.Qi.as<float>());
