@@ -211,6 +211,7 @@ struct pb_index {
     bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
                                // the cut sits well above the background score level
     bool fma2 = true;          // FFMA2 (fma.rn.f32x2) k_centroid_scores; PB_FMA2=0 selects the scalar-FFMA twin (same bits)
+    bool fma2_exact = false;   // FFMA2 dots in k_exact (PB_FMA2_EXACT=1; prepared, to be measured)
     bool approx_cg = false;    // k_approx16 row gathers bypass L1 allocation (PB_APPROX_CG=1)
     int approx_grid = 8;       // k_approx16 CTAs per SM and query (PB_APPROX_GRID)
     int xtc_grid = 32;         // k_exact_tc CTAs per SM across the batch (PB_XTC_GRID)
@@ -439,6 +440,7 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_FAST_EXACT")) ix->fast_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
         if (const char *e = getenv("PB_FMA2")) ix->fma2 = atoi(e) != 0;
+        if (const char *e = getenv("PB_FMA2_EXACT")) ix->fma2_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_APPROX_CG")) ix->approx_cg = atoi(e) != 0;
         if (const char *e = getenv("PB_APPROX_GRID")) ix->approx_grid = std::max(1, atoi(e));
         if (const char *e = getenv("PB_XTC_GRID")) ix->xtc_grid = std::max(1, atoi(e));
@@ -596,7 +598,7 @@ static pb_status launch_exact(pb_index *ix, Workspace &ws, const KeptView &kv, i
     long long want = std::max<long long>(1, ((long long)ix->sm_count * 16 + B - 1) / B);
     int gx = (int)std::max<long long>(1, std::min<long long>(chunks, want));
     PB_DIM_SWITCH(ix->dim, {
-        auto kern = k_exact<DIM, false>;
+        auto kern = ix->fma2_exact ? k_exact<DIM, false, true> : k_exact<DIM, false, false>;
         CKS(set_smem(kern, smem_exact(DIM, ix->packed)));
         kern<<<dim3(gx, B), 128, smem_exact(DIM, ix->packed), ws.stream>>>(
             ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits,
@@ -1370,7 +1372,7 @@ extern "C" pb_status pb_maxsim_scores(int32_t device, const float *query, int32_
     switch (dim) {
 #define PB_CASE(DV)                                                                                              \
     case DV: {                                                                                                   \
-        auto kern = k_exact<DV, true>;                                                                           \
+        auto kern = k_exact<DV, true, false>;                                                                           \
         CKS(set_smem(kern, smem_exact(DV, 0)));                                                                  \
         kern<<<dim3(gx, 1), 128, smem_exact(DV, 0)>>>(dQ.as<float>(), dqoff.as<int>(), QS, nullptr, nullptr, 8, nullptr, \
                                                    nullptr, nullptr, dtok.as<float>(), dkept.as<uint32_t>(),    \

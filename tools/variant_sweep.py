@@ -1,0 +1,54 @@
+"""One GPU call, every measurement knob: runs bench.py under each environment setting and prints the stage
+times side by side (run on the GPU box: `python tools/variant_sweep.py [--steps 10]`).  All variants produce
+the same results; the bench's parity block (kept on for the first run of each knob) confirms it."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VARIANTS = [
+    ("default", {}),
+    ("scalar FFMA centroid scores", {"PB_FMA2": "0"}),
+    ("FFMA2 in k_exact", {"PB_FMA2_EXACT": "1"}),
+    ("ld.global.cg gathers", {"PB_APPROX_CG": "1"}),
+    ("approx grid x4", {"PB_APPROX_GRID": "4"}),
+    ("filter off", {"PB_FAST_EXACT": "0"}),
+    ("FFMA2 in k_exact, filter off", {"PB_FMA2_EXACT": "1", "PB_FAST_EXACT": "0"}),
+    ("list-scan probe", {"PB_PROBE16": "0"}),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--only", default="", help="comma-separated substrings of variant names")
+    args = ap.parse_args()
+    rows = []
+    for name, env in VARIANTS:
+        if args.only and not any(s in name for s in args.only.split(",")):
+            continue
+        e = dict(os.environ, **env)
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(args.steps), "--warmup", "3",
+               "--recall-queries", "0"]
+        out = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=600)
+        line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if out.returncode != 0 or not line:
+            rows.append((name, None, out.stderr[-300:]))
+            continue
+        d = json.loads(line[-1])
+        rows.append((name, d, ""))
+    for name, d, err in rows:
+        if d is None:
+            print(f"{name:34s} FAILED {err}")
+            continue
+        st = d["stage_ms_per_step"]
+        par = d.get("parity") or {}
+        print(f"{name:34s} {d['value']:8.0f} q/s  " + "  ".join(f"{k}={st[k]:.3f}" for k in
+              ("centroid_scores", "probe", "approx", "exact")) +
+              f"  parity {par.get('ids_identical')}/{par.get('queries')} dmax={par.get('max_abs_score_diff')}")
+
+
+if __name__ == "__main__":
+    main()
