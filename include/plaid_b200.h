@@ -228,6 +228,8 @@ typedef struct pb_work_counters {
     int64_t n_exact_tokens;
     int64_t n_filter_docs;     /* docs / tokens estimated by the tensor-core filter (0 when off) */
     int64_t n_filter_tokens;
+    int64_t k1_tc_max_code_diff; /* PB_K1_TC_DIAG=1 only: largest difference between the exact 16-bit score table and
+                                  * its split-fp16 tensor-core twin (diagnostic; 0 otherwise) */
 } pb_work_counters;
 PB_API pb_status pb_last_work_counters(pb_index *ix, pb_work_counters *out);
 

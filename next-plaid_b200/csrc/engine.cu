@@ -172,7 +172,7 @@ struct Workspace {
     cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2, cand3, ncand3, ub, theta, rel, cellbits,
-        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax;
+        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -211,6 +211,9 @@ struct pb_index {
     bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
                                // the cut sits well above the background score level
     bool fma2 = true;          // FFMA2 (fma.rn.f32x2) k_centroid_scores; PB_FMA2=0 selects the scalar-FFMA twin (same bits)
+    bool k1_diag = false;      // run the split-fp16 tensor-core score table next to the exact one and report the
+                               // largest code difference (PB_K1_TC_DIAG=1; stage 1 of the certified a2, diagnostic only)
+    DevBuf cent_h16t, cent_l16t;  // its centroid operands: fp16 hi / lo, UMMA tile order
     bool fma2_exact = false;   // FFMA2 dots in k_exact (PB_FMA2_EXACT=1; prepared, to be measured)
     bool approx_cg = false;    // k_approx16 row gathers bypass L1 allocation (PB_APPROX_CG=1)
     int approx_grid = 8;       // k_approx16 CTAs per SM and query (PB_APPROX_GRID)
@@ -441,6 +444,7 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
         if (const char *e = getenv("PB_FMA2")) ix->fma2 = atoi(e) != 0;
         if (const char *e = getenv("PB_FMA2_EXACT")) ix->fma2_exact = atoi(e) != 0;
+        if (const char *e = getenv("PB_K1_TC_DIAG")) ix->k1_diag = atoi(e) != 0;
         if (const char *e = getenv("PB_APPROX_CG")) ix->approx_cg = atoi(e) != 0;
         if (const char *e = getenv("PB_APPROX_GRID")) ix->approx_grid = std::max(1, atoi(e));
         if (const char *e = getenv("PB_XTC_GRID")) ix->xtc_grid = std::max(1, atoi(e));
@@ -461,6 +465,16 @@ pb_status pb_index_finalize(pb_index *ix) {
             default: k_min_vnorm<128><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>()); break;
         }
         CK(cudaGetLastError());
+        if (ix->k1_diag) {
+            const size_t elems = (size_t)((ix->K + 127) / 128) * 128 * ix->dim;
+            CKS(ix->cent_h16t.ensure(elems * 2));
+            CKS(ix->cent_l16t.ensure(elems * 2));
+            CK(cudaMemset(ix->cent_h16t.p, 0, elems * 2));
+            CK(cudaMemset(ix->cent_l16t.p, 0, elems * 2));
+            k_rows_to_f16_split_tiles<<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->K, ix->dim,
+                                                                ix->cent_h16t.as<__half>(), ix->cent_l16t.as<__half>());
+            CK(cudaGetLastError());
+        }
         float got[2] = {0.f, 0.f};
         CK(cudaMemcpy(got, mn.p, 8, cudaMemcpyDeviceToHost));
         ix->vmin = got[0] < 1e30f ? got[0] : 0.0f;
@@ -548,7 +562,50 @@ extern "C" pb_status pb_last_work_counters(pb_index *, pb_work_counters *out) {
 // ------------------------------------------------------------------------------------------
 // kernel launch helpers shared by the search pipeline and the stage entry points
 // ------------------------------------------------------------------------------------------
+static pb_status launch_centroid_scores_exact(pb_index *ix, Workspace &ws, int B, int QS, int *launches, bool with16);
+
+// diagnostic twin of the score table on the tensor cores (k_scores16_tc), compared code by code
+static pb_status launch_k1_diag(pb_index *ix, Workspace &ws, int B, int QS) {
+    const int n_groups = (int)(((long long)B * QS + 127) / 128);
+    const size_t qelems = (size_t)n_groups * 128 * ix->dim;
+    CKS(ws.Qh16t.ensure(qelems * 2));
+    CKS(ws.Ql16t.ensure(qelems * 2));
+    CKS(ws.ST16b.ensure((size_t)B * ix->K * QS * 2));
+    CKS(ws.k1diag.ensure((size_t)(B + 4) * 4));
+    CK(cudaMemsetAsync(ws.k1diag.p, 0, (size_t)(B + 4) * 4, ws.stream));
+    k_query_split_tiles<<<ix->sm_count, 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), B, QS, ix->dim,
+                                                             ws.Qh16t.as<__half>(), ws.Ql16t.as<__half>());
+    const int tiles = (int)((ix->K + 127) / 128);
+    const size_t sm = (size_t)6 * 128 * ix->dim * 2 + 128;
+#define PB_K1_LAUNCH(DV)                                                                                               \
+    {                                                                                                                  \
+        auto kern = k_scores16_tc<DV>;                                                                                 \
+        CKS(set_smem(kern, sm));                                                                                       \
+        kern<<<tiles, 192, sm, ws.stream>>>(ix->cent_h16t.as<__half>(), ix->cent_l16t.as<__half>(), ix->K,             \
+                                            ws.Qh16t.as<__half>(), ws.Ql16t.as<__half>(), n_groups, B, QS,             \
+                                            ws.qoff.as<int>(), ws.qrange.as<float2>(), ws.ST16b.as<unsigned short>(),  \
+                                            ws.k1diag.as<int>() + 4);                                                  \
+    }
+    switch (ix->dim) {
+        case 64: PB_K1_LAUNCH(64) break;
+        case 96: PB_K1_LAUNCH(96) break;
+        case 128: PB_K1_LAUNCH(128) break;
+        default: return PB_OK;
+    }
+#undef PB_K1_LAUNCH
+    k_diff16<<<dim3(ix->sm_count, B), 256, 0, ws.stream>>>(ws.ST16.as<unsigned short>(), ws.ST16b.as<unsigned short>(),
+                                                          ws.qoff.as<int>(), ix->K, QS, ws.k1diag.as<int>());
+    CK(cudaGetLastError());
+    return PB_OK;
+}
+
 static pb_status launch_centroid_scores(pb_index *ix, Workspace &ws, int B, int QS, int *launches, bool with16 = false) {
+    CKS(launch_centroid_scores_exact(ix, ws, B, QS, launches, with16));
+    if (with16 && ix->k1_diag && ix->cent_h16t.p) CKS(launch_k1_diag(ix, ws, B, QS));
+    return PB_OK;
+}
+
+static pb_status launch_centroid_scores_exact(pb_index *ix, Workspace &ws, int B, int QS, int *launches, bool with16) {
     const int tiles = (int)((ix->K + PB_TOK_TILE - 1) / PB_TOK_TILE);
     // enough CTAs to fill the machine twice over; each CTA keeps its centroid tile in smem and walks queries
     int groups = std::max(1, std::min(B, (4 * ix->sm_count + tiles - 1) / tiles));
@@ -1175,6 +1232,11 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
                 CK(cudaEventElapsedTime(&ms, ws.ev[s], ws.ev[s + 1]));
                 g_stats.ms[s] += ms;
             }
+        if (fast && ix->k1_diag && ws.k1diag.p) {
+            int worst = 0;
+            CK(cudaMemcpy(&worst, ws.k1diag.p, 4, cudaMemcpyDeviceToHost));
+            g_stats.work.k1_tc_max_code_diff = std::max<long long>(g_stats.work.k1_tc_max_code_diff, worst);
+        }
         g_stats.work.n_queries += B;
         g_stats.work.n_query_tokens += R;
         g_stats.work.n_candidate_tokens += (long long)hcnt[0];

@@ -17,6 +17,7 @@ VARIANTS = [
     ("filter off", {"PB_FAST_EXACT": "0"}),
     ("FFMA2 in k_exact, filter off", {"PB_FMA2_EXACT": "1", "PB_FAST_EXACT": "0"}),
     ("list-scan probe", {"PB_PROBE16": "0"}),
+    ("K1 tensor-core twin (diagnostic)", {"PB_K1_TC_DIAG": "1"}),
 ]
 
 
@@ -47,7 +48,8 @@ def main():
         par = d.get("parity") or {}
         print(f"{name:34s} {d['value']:8.0f} q/s  " + "  ".join(f"{k}={st[k]:.3f}" for k in
               ("centroid_scores", "probe", "approx", "exact")) +
-              f"  parity {par.get('ids_identical')}/{par.get('queries')} dmax={par.get('max_abs_score_diff')}")
+              f"  parity {par.get('ids_identical')}/{par.get('queries')} dmax={par.get('max_abs_score_diff')}"
+              f"  k1_code_diff={d.get('work_per_step', {}).get('k1_tc_max_code_diff')}")
 
 
 if __name__ == "__main__":
