@@ -230,6 +230,8 @@ typedef struct pb_work_counters {
     int64_t n_filter_tokens;
     int64_t k1_tc_max_code_diff; /* PB_K1_TC_DIAG=1 only: largest difference between the exact 16-bit score table and
                                   * its split-fp16 tensor-core twin (diagnostic; 0 otherwise) */
+    int64_t k1_rows_mismatch;    /* PB_K1_TC_DIAG=1 only: words of the sparse exact-row kernel (k_exact_rows, on the probe's
+                                  * cells) that differ from the dense score table; 0 expected */
 } pb_work_counters;
 PB_API pb_status pb_last_work_counters(pb_index *ix, pb_work_counters *out);
 

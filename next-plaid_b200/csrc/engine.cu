@@ -172,7 +172,7 @@ struct Workspace {
     cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2, cand3, ncand3, ub, theta, rel, cellbits,
-        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax;
+        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -1001,6 +1001,22 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             CK(cudaGetLastError());
             L[PB_STAGE_PROBE] += 3;
         }
+        if (fast && ix->k1_diag && ix->fma2 && ws.k1diag.p && cells_cap > 0) {
+            // diagnostic: the sparse exact-row kernel on the probe's cells must reproduce the dense table's rows
+            CKS(ws.k1rows.ensure((size_t)B * cells_cap * QS * 4));
+            const size_t smr = (size_t)(PB_TOK_TILE * (ix->dim + 4) + PB_Q_TILE * ix->dim) * sizeof(float);
+            PB_DIM_SWITCH(ix->dim, {
+                auto kern = k_exact_rows<DIM>;
+                CKS(set_smem(kern, smr));
+                kern<<<dim3((cells_cap + PB_TOK_TILE - 1) / PB_TOK_TILE, B), 128, smr, ws.stream>>>(
+                    ws.Qi.as<float>(), ws.qoff.as<int>(), QS, ix->centroids.as<float>(), ix->K, ws.cells.as<uint32_t>(),
+                    ws.ncells.as<int>(), cells_cap, 1, ws.k1rows.as<float>());
+            });
+            k_cmp_rows<<<dim3(32, B), 256, 0, ws.stream>>>(ws.ST.as<float>(), ws.k1rows.as<float>(), ws.qoff.as<int>(), ix->K, QS,
+                                                          ws.cells.as<uint32_t>(), ws.ncells.as<int>(), cells_cap,
+                                                          ws.k1diag.as<int>() + 1);
+            CK(cudaGetLastError());
+        }
         if (prof) CK(cudaEventRecord(ws.ev[3], ws.stream));
 
         // ---- a4 candidates ----
@@ -1233,9 +1249,10 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
                 g_stats.ms[s] += ms;
             }
         if (fast && ix->k1_diag && ws.k1diag.p) {
-            int worst = 0;
-            CK(cudaMemcpy(&worst, ws.k1diag.p, 4, cudaMemcpyDeviceToHost));
-            g_stats.work.k1_tc_max_code_diff = std::max<long long>(g_stats.work.k1_tc_max_code_diff, worst);
+            int got[2] = {0, 0};
+            CK(cudaMemcpy(got, ws.k1diag.p, 8, cudaMemcpyDeviceToHost));
+            g_stats.work.k1_tc_max_code_diff = std::max<long long>(g_stats.work.k1_tc_max_code_diff, got[0]);
+            g_stats.work.k1_rows_mismatch += got[1];
         }
         g_stats.work.n_queries += B;
         g_stats.work.n_query_tokens += R;

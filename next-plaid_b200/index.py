@@ -65,7 +65,8 @@ class _Trace(C.Structure):
 class _Work(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_queries", "n_query_tokens", "n_cells", "n_candidates",
                                          "n_candidate_tokens", "n_exact_docs", "n_exact_tokens",
-                                         "n_filter_docs", "n_filter_tokens", "k1_tc_max_code_diff")]
+                                         "n_filter_docs", "n_filter_tokens", "k1_tc_max_code_diff",
+                                         "k1_rows_mismatch")]
 
 
 EXPORTS = [

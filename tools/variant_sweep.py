@@ -49,7 +49,8 @@ def main():
         print(f"{name:34s} {d['value']:8.0f} q/s  " + "  ".join(f"{k}={st[k]:.3f}" for k in
               ("centroid_scores", "probe", "approx", "exact")) +
               f"  parity {par.get('ids_identical')}/{par.get('queries')} dmax={par.get('max_abs_score_diff')}"
-              f"  k1_code_diff={d.get('work_per_step', {}).get('k1_tc_max_code_diff')}")
+              f"  k1_code_diff={d.get('work_per_step', {}).get('k1_tc_max_code_diff')}"
+              f"  k1_rows_mismatch={d.get('work_per_step', {}).get('k1_rows_mismatch')}")
 
 
 if __name__ == "__main__":
