@@ -9,7 +9,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libplaid_b200.so")
 SOURCES = ["engine.cu", "loader.cpp"]
-DEPS = SOURCES + ["kernels.cuh", "common.cuh", "engine_internal.h", os.path.join("..", "..", "include", "plaid_b200.h")]
+DEPS = SOURCES + sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + \
+    [os.path.join("..", "..", "include", "plaid_b200.h")]
 NVCC_FLAGS = [
     "-shared", "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,0 +1,358 @@
+// k_approx16.cuh -- a5 two-pass form: 16-bit first pass, band select, pruning cascade.
+// Part of kernels.cuh (included from there, in order; not a standalone header).
+// ------------------------------------------------------------------------------------------
+// a5, two-pass form.  The approximate score only decides WHICH docs make the cut (search.rs:460-469),
+// so a first pass ranks every candidate on a 16-bit fixed-point copy of S (half the L2 bytes per
+// gather) and only the docs that could still be in the top M -- the M-th largest code sum minus a
+// certified band -- get the exact fp32 pass (k_approx).  The cut is therefore EXACTLY the reference's.
+//   code(v) = floor(fl(v*scale + R*scale)), monotone in v, |v| <= R = max|c| * max|q| * (1+1e-4)
+//   true per-token max in [(code-1)/scale - R, (code+2)/scale - R]; fp32 sum error <= nq*R*2^-18
+//   => doc X certainly outranks doc Y when L_X - L_Y > 3.25*nq; band W = 4*nq + 8 code units.
+// Queries whose scores leave [-R, R] or are non-finite (qflag) skip the shortcut entirely.
+// ------------------------------------------------------------------------------------------
+__global__ void k_query_range(const float *__restrict__ Q, const int *__restrict__ q_off, int dim, float cmax,
+                              float2 *__restrict__ qrange, int *__restrict__ qflag) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int r0 = q_off[b], nq = q_off[b + 1] - r0;
+    float best = 0.0f;
+    bool bad = false;
+    for (int r = 0; r < nq; ++r) {
+        float p = 0.0f;
+        for (int j = lane; j < dim; j += 32) {
+            const float v = Q[(size_t)(r0 + r) * dim + j];
+            p = fmaf(v, v, p);
+        }
+        for (int m = 16; m >= 1; m >>= 1) p += __shfl_xor_sync(PB_FULL, p, m);
+        bad |= !(p <= 3.0e38f);
+        best = fmaxf(best, p);
+    }
+    if (lane == 0) {
+        float R = cmax * sqrtf(best) * 1.0001f;
+        if (!(R > 1e-30f) || !(R < 1e30f) || bad) {
+            R = 1.0f;
+            qflag[b] = nq > 0 ? 1 : 0;
+        } else qflag[b] = 0;
+        const float scale = 65535.0f / (2.0f * R);
+        qrange[b] = make_float2(R * scale, scale);
+    }
+}
+
+__global__ void k_max_row_norm(const float *__restrict__ C, long long K, int dim, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    float best = 0.0f;
+    for (long long c = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < K; c += nw) {
+        float p = 0.0f;
+        for (int j = lane; j < dim; j += 32) {
+            const float v = C[(size_t)c * dim + j];
+            p = fmaf(v, v, p);
+        }
+        for (int m = 16; m >= 1; m >>= 1) p += __shfl_xor_sync(PB_FULL, p, m);
+        best = fmaxf(best, p == p ? p : 3.4e38f);
+    }
+    if (lane == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(best));  // best >= 0
+}
+
+// First-pass kernel.  The gather stage is bound by load-instruction / L2 request rate, not bytes, so one
+// load instruction fetches FOUR table rows: lane = 8*r + s reads the 8 bytes (4 query tokens) s of the
+// row of code r of each group of four codes; maxima stay packed (u16x2 SIMD max).
+PB_DEV uint32_t pick4(const uint4 &c, int r) { return r == 0 ? c.x : (r == 1 ? c.y : (r == 2 ? c.z : c.w)); }
+
+template <bool CG>
+PB_DEV uint4 gather16(const char *p) {
+    return CG ? __ldcg(reinterpret_cast<const uint4 *>(p)) : *reinterpret_cast<const uint4 *>(p);
+}
+// CG: row gathers with ld.global.cg (no L1 allocation; PB_APPROX_CG=1, to be measured)
+template <bool CG>
+__global__ void __launch_bounds__(256, 4)
+k_approx16(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
+           const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off,
+           const uint32_t *__restrict__ cand, long long cand_cap, const int *__restrict__ n_cand,
+           uint32_t *__restrict__ lsum, unsigned long long *__restrict__ tok_counter) {
+    const int b = blockIdx.y;
+    const int nq = q_off[b + 1] - q_off[b];
+    const int n = n_cand[b];
+    const int lane = threadIdx.x & 31, r = lane >> 2, sl = lane & 3;  // 8 row groups x 4 lanes x 16 bytes
+    const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    const char *STb = reinterpret_cast<const char *>(ST16 + (size_t)b * K * QS);
+    const unsigned rowb = (unsigned)QS * 2u;
+    unsigned long long my_tokens = 0;
+    int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t d = 0;
+    long long t0 = 0, t1 = 0;
+    if (i < n) {
+        d = cand[(size_t)b * cand_cap + i];
+        t0 = udoc_off[d];
+        t1 = udoc_off[d + 1];
+    }
+    for (; i < n; i += warps_per_grid) {
+        const int i2 = i + warps_per_grid;
+        uint32_t dn = 0;
+        long long t0n = 0, t1n = 0;
+        if (i2 < n) {
+            dn = cand[(size_t)b * cand_cap + i2];
+            t0n = udoc_off[dn];
+            t1n = udoc_off[dn + 1];
+        }
+        my_tokens += (unsigned long long)(t1 - t0);
+        uint32_t total = 0;
+        for (int qc = 0; qc < nq; qc += 32) {
+            const bool in_row = qc + 8 * sl < QS;  // QS is a multiple of 8: groups past the row are skipped
+            const char *col = STb + (in_row ? (qc + 8 * sl) * 2 : 0);
+            uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;  // packed maxima of query tokens 8s .. 8s+7
+            // 64 codes per step: two coalesced loads (lane = code), handed to the eight row groups by shuffle; a row
+            // is 4 lanes x 16 bytes.  (Lists are padded to 8 with the last code; indices past the end repeat it,
+            // a max does not care.  The uniform 16-byte code loads this replaces cost one L1 tag lookup each --
+            // a fifth of all lookups of a kernel that is bound by them.)
+            for (long long t = t0; t < t1; t += 64) {
+                const uint32_t cl0 = ucodes[min(t + lane, t1 - 1)], cl1 = ucodes[min(t + 32 + lane, t1 - 1)];
+                if (t + 64 <= t1) {
+                    uint4 v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        v[e] = gather16<CG>(col + (size_t)__shfl_sync(PB_FULL, e < 4 ? cl0 : cl1, 8 * (e & 3) + r) * rowb);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        m0 = __vmaxu2(m0, v[e].x);
+                        m1 = __vmaxu2(m1, v[e].y);
+                        m2 = __vmaxu2(m2, v[e].z);
+                        m3 = __vmaxu2(m3, v[e].w);
+                    }
+                } else {
+                    const int ne = (int)((t1 - t + 7) >> 3);
+                    for (int e = 0; e < ne; ++e) {
+                        const uint4 va = gather16<CG>(col + (size_t)__shfl_sync(PB_FULL, e < 4 ? cl0 : cl1, 8 * (e & 3) + r) * rowb);
+                        m0 = __vmaxu2(m0, va.x);
+                        m1 = __vmaxu2(m1, va.y);
+                        m2 = __vmaxu2(m2, va.z);
+                        m3 = __vmaxu2(m3, va.w);
+                    }
+                }
+            }
+            // combine the eight row groups, then add up this lane's (real) query tokens
+#pragma unroll
+            for (int m = 4; m < 32; m <<= 1) {
+                m0 = __vmaxu2(m0, __shfl_xor_sync(PB_FULL, m0, m));
+                m1 = __vmaxu2(m1, __shfl_xor_sync(PB_FULL, m1, m));
+                m2 = __vmaxu2(m2, __shfl_xor_sync(PB_FULL, m2, m));
+                m3 = __vmaxu2(m3, __shfl_xor_sync(PB_FULL, m3, m));
+            }
+            const int q0 = qc + 8 * sl;
+            uint32_t part = 0;
+            if (in_row && r == 0) {
+                const uint32_t mm[4] = {m0, m1, m2, m3};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (q0 + 2 * j < nq) part += mm[j] & 0xffffu;
+                    if (q0 + 2 * j + 1 < nq) part += mm[j] >> 16;
+                }
+            }
+            total += __reduce_add_sync(PB_FULL, part);
+        }
+        if (lane == 0) lsum[(size_t)b * cand_cap + i] = total;
+        d = dn;
+        t0 = t0n;
+        t1 = t1n;
+    }
+    if (lane == 0 && my_tokens) atomicAdd(tok_counter, my_tokens);
+}
+
+// Generic "N-th largest with a band" selection used by the pruning cascade.  Per query:
+//   tau = N-th largest of sel_keys[0..sel_n) (0 when sel_n < N or the query is flagged),
+//   thr = tau - (band_per_q * nq + 8) (0 when band_per_q < 0 ... see callers), and the output is every
+//   entry of filt_list whose filt_key >= thr (unordered).  grid = B, 1024 threads.
+__global__ void __launch_bounds__(1024)
+k_select_u32(const uint32_t *__restrict__ sel_keys, const int *__restrict__ sel_n, int N, int band_per_q,
+             const uint32_t *__restrict__ filt_keys, const uint32_t *__restrict__ filt_list,
+             const int *__restrict__ filt_n, long long stride, const int *__restrict__ q_off,
+             const int *__restrict__ qflag, uint32_t *__restrict__ out_list, int *__restrict__ out_n) {
+    __shared__ int hist[256];
+    __shared__ uint32_t prefix_s, mask_s;
+    __shared__ int remaining_s, fill_s;
+    const int b = blockIdx.x;
+    const int ns = sel_n[b], nf = filt_n[b];
+    const int nq = q_off[b + 1] - q_off[b];
+    const uint32_t *L = sel_keys + (size_t)b * stride;
+    const uint32_t *F = filt_keys + (size_t)b * stride;
+    const uint32_t *cin = filt_list + (size_t)b * stride;
+    uint32_t *cout = out_list + (size_t)b * stride;
+    uint32_t thr = 0;  // keep everything
+    if (ns >= N && N > 0 && !qflag[b]) {
+        if (threadIdx.x == 0) {
+            prefix_s = 0u;
+            mask_s = 0u;
+            remaining_s = N;
+        }
+        for (int pass = 3; pass >= 0; --pass) {  // N-th smallest of ~L == N-th largest of L
+            const int shift = pass * 8;
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            const uint32_t prefix = prefix_s, mask = mask_s;
+            for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+                const uint32_t k = ~L[i];
+                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int rem = remaining_s, cum = 0, d = 0;
+                for (; d < 256; ++d) {
+                    if (cum + hist[d] >= rem) break;
+                    cum += hist[d];
+                }
+                remaining_s = rem - cum;
+                prefix_s = prefix | ((uint32_t)d << shift);
+                mask_s = mask | (255u << shift);
+            }
+            __syncthreads();
+        }
+        const uint32_t tau = ~prefix_s;
+        const uint32_t W = band_per_q > 0 ? (uint32_t)band_per_q * (uint32_t)nq + 8u : 0u;
+        thr = tau > W ? tau - W : 0u;
+    }
+    if (threadIdx.x == 0) fill_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < nf; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool keep = i < nf && F[i] >= thr;
+        const unsigned bal = __ballot_sync(PB_FULL, keep);
+        int off = 0;
+        if (lane == 0 && bal) off = atomicAdd(&fill_s, __popc(bal));
+        off = __shfl_sync(PB_FULL, off, 0);
+        if (keep) cout[off + __popc(bal & ((1u << lane) - 1u))] = cin[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out_n[b] = fill_s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Pruning cascade in front of the approximate score (DESIGN.md "a5").  Bound per query: with
+// REL = {c : max_q code16(S[q,c]) >= theta16}, every centroid outside REL scores below theta on every
+// query token, so  code16(max_t S[q,code_t]) <= max(theta16, max over the doc's REL codes)  and the
+// sum over q, ub16(doc), is >= the exact 16-bit code sum lsum(doc) of k_approx16.  ub16 needs row
+// gathers only for the doc's REL codes (a per-query bitmap test in shared memory picks them).
+//   1. ub16 for every candidate                         (k_theta16, k_relevant_bits, k_approx_ub)
+//   2. S' = top 2M by ub16; lsum on S'; tau' = M-th largest (a lower bound of the true tau)
+//   3. list2 = {ub16 >= tau' - W} (superset of everything k_select on full lsum would keep)
+//   4. lsum on list2, tau = M-th largest, list3 = {lsum >= tau - W}; exact fp32 pass on list3
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_theta16(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
+          uint32_t *__restrict__ theta16) {
+    __shared__ int hist[4096];
+    const int b = blockIdx.x;
+    const int nq = q_off[b + 1] - q_off[b];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long stride = max(1ll, K / 32768);  // a sample of <= 32k centroids fixes the efficiency knob
+    const unsigned short *STb = ST16 + (size_t)b * K * QS;
+    int n_samples = 0;
+    for (long long c = (long long)w * stride; c < K; c += (long long)nw * stride) {
+        uint32_t m = 0;
+        for (int q = lane; q < nq; q += 32) m = max(m, (uint32_t)STb[(size_t)c * QS + q]);
+        m = __reduce_max_sync(PB_FULL, m);
+        if (lane == 0) atomicAdd(&hist[m >> 4], 1);
+        ++n_samples;
+    }
+    __shared__ int total_s;
+    if (threadIdx.x == 0) total_s = 0;
+    __syncthreads();
+    if (lane == 0) atomicAdd(&total_s, n_samples);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int target = max(1, total_s / 128);  // ~0.8 % of the centroids count as relevant
+        int cum = 0, bin = 4095;
+        for (; bin > 0; --bin) {
+            cum += hist[bin];
+            if (cum >= target) break;
+        }
+        theta16[b] = max(1u, (uint32_t)bin << 4);
+    }
+}
+
+// bit c of rel[b] = any query token scores >= theta16 on centroid c.  grid = (ceil(K/256), B), 256 thr.
+__global__ void __launch_bounds__(256)
+k_relevant_bits(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
+                const uint32_t *__restrict__ theta16, uint32_t *__restrict__ rel, long long Wk) {
+    const int b = blockIdx.y;
+    const int nq = q_off[b + 1] - q_off[b];
+    const int lane = threadIdx.x & 31;
+    const long long word = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (word >= Wk) return;
+    const uint32_t th = theta16[b];
+    const unsigned short *STb = ST16 + (size_t)b * K * QS;
+    uint32_t bits = 0;
+    for (int j = 0; j < 32; ++j) {
+        const long long c = word * 32 + j;
+        if (c >= K) break;
+        uint32_t m = 0;
+        for (int q = lane; q < nq; q += 32) m = max(m, (uint32_t)STb[(size_t)c * QS + q]);
+        if (__any_sync(PB_FULL, m >= th)) bits |= 1u << j;
+    }
+    if (lane == 0) rel[(size_t)b * Wk + word] = bits;
+}
+
+// ub16 of every candidate.  grid = (blocks, B), 256 threads, dynamic smem = Wk*4 bytes (the bitmap).
+__global__ void __launch_bounds__(256)
+k_approx_ub(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
+            const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off,
+            const uint32_t *__restrict__ cand, long long cand_cap, const int *__restrict__ n_cand,
+            const uint32_t *__restrict__ theta16, const uint32_t *__restrict__ rel, long long Wk,
+            uint32_t *__restrict__ ub, unsigned long long *__restrict__ tok_counter) {
+    extern __shared__ __align__(16) uint32_t rel_s[];
+    const int b = blockIdx.y;
+    const int nq = q_off[b + 1] - q_off[b];
+    const int n = n_cand[b];
+    for (long long i = threadIdx.x; i < Wk; i += blockDim.x) rel_s[i] = rel[(size_t)b * Wk + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    const unsigned short *STb = ST16 + (size_t)b * K * QS;
+    const uint32_t th = theta16[b];
+    unsigned long long my_tokens = 0;
+    int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t d = 0;
+    long long t0 = 0, t1 = 0;
+    if (i < n) {
+        d = cand[(size_t)b * cand_cap + i];
+        t0 = udoc_off[d];
+        t1 = udoc_off[d + 1];
+    }
+    for (; i < n; i += warps_per_grid) {
+        const int i2 = i + warps_per_grid;
+        uint32_t dn = 0;
+        long long t0n = 0, t1n = 0;
+        if (i2 < n) {
+            dn = cand[(size_t)b * cand_cap + i2];
+            t0n = udoc_off[dn];
+            t1n = udoc_off[dn + 1];
+        }
+        my_tokens += (unsigned long long)(t1 - t0);
+        uint32_t total = 0;
+        for (int qc = 0; qc < nq; qc += 32) {
+            const int q = qc + lane;
+            const unsigned short *col = STb + (q < nq ? q : 0);
+            uint32_t m = th;  // every non-relevant code scores below theta16 on every query token
+            for (long long t = t0; t < t1; t += 32) {
+                const uint32_t code = (t + lane < t1) ? ucodes[t + lane] : 0xffffffffu;
+                bool hit = false;
+                if (code != 0xffffffffu) hit = (rel_s[code >> 5] >> (code & 31)) & 1u;
+                unsigned mask = __ballot_sync(PB_FULL, hit);
+                while (mask) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const uint32_t cj = __shfl_sync(PB_FULL, code, j);
+                    m = max(m, (uint32_t)col[(size_t)cj * QS]);
+                }
+            }
+            if (q >= nq) m = 0;
+            total += __reduce_add_sync(PB_FULL, m);
+        }
+        if (lane == 0) ub[(size_t)b * cand_cap + i] = total;
+        d = dn;
+        t0 = t0n;
+        t1 = t1n;
+    }
+    if (lane == 0 && my_tokens) atomicAdd(tok_counter, my_tokens);
+}
