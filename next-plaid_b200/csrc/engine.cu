@@ -172,7 +172,7 @@ struct Workspace {
     cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2, cand3, ncand3, ub, theta, rel, cellbits,
-        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax;
+        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, codebits, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -182,6 +182,7 @@ struct Workspace {
         subset_bits.zero_on_grow = true;
         elig.zero_on_grow = true;
         cellbits.zero_on_grow = true;
+        codebits.zero_on_grow = true;
         return PB_OK;
     }
     ~Workspace() {
@@ -211,6 +212,9 @@ struct pb_index {
     bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
                                // the cut sits well above the background score level
     bool fma2 = true;          // FFMA2 (fma.rn.f32x2) k_centroid_scores; PB_FMA2=0 selects the scalar-FFMA twin (same bits)
+    bool k1_tc = false;        // a2 + a3 + the a5 re-check on the tensor-core score table (PB_K1_TC=1; stage 2 of the
+                               // certified a2: unmeasured, off by default)
+    int k1_margin = 3;         // code units an estimate-built 16-bit code may differ from the exact one (PB_K1_TC_E)
     bool k1_diag = false;      // run the split-fp16 tensor-core score table next to the exact one and report the
                                // largest code difference (PB_K1_TC_DIAG=1; stage 1 of the certified a2, diagnostic only)
     DevBuf cent_h16t, cent_l16t;  // its centroid operands: fp16 hi / lo, UMMA tile order
@@ -445,6 +449,8 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_FMA2")) ix->fma2 = atoi(e) != 0;
         if (const char *e = getenv("PB_FMA2_EXACT")) ix->fma2_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC_DIAG")) ix->k1_diag = atoi(e) != 0;
+        if (const char *e = getenv("PB_K1_TC")) ix->k1_tc = atoi(e) != 0;
+        if (const char *e = getenv("PB_K1_TC_E")) ix->k1_margin = std::max(1, atoi(e));
         if (const char *e = getenv("PB_APPROX_CG")) ix->approx_cg = atoi(e) != 0;
         if (const char *e = getenv("PB_APPROX_GRID")) ix->approx_grid = std::max(1, atoi(e));
         if (const char *e = getenv("PB_XTC_GRID")) ix->xtc_grid = std::max(1, atoi(e));
@@ -465,7 +471,7 @@ pb_status pb_index_finalize(pb_index *ix) {
             default: k_min_vnorm<128><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>()); break;
         }
         CK(cudaGetLastError());
-        if (ix->k1_diag) {
+        if (ix->k1_diag || ix->k1_tc) {
             const size_t elems = (size_t)((ix->K + 127) / 128) * 128 * ix->dim;
             CKS(ix->cent_h16t.ensure(elems * 2));
             CKS(ix->cent_l16t.ensure(elems * 2));
@@ -564,15 +570,13 @@ extern "C" pb_status pb_last_work_counters(pb_index *, pb_work_counters *out) {
 // ------------------------------------------------------------------------------------------
 static pb_status launch_centroid_scores_exact(pb_index *ix, Workspace &ws, int B, int QS, int *launches, bool with16);
 
-// diagnostic twin of the score table on the tensor cores (k_scores16_tc), compared code by code
-static pb_status launch_k1_diag(pb_index *ix, Workspace &ws, int B, int QS) {
+// the 16-bit score table from the split-fp16 UMMA GEMM (k_scores16_tc) into `table`; `flags` gets the per-query
+// out-of-range bits the exact kernel would set in qflag
+static pb_status launch_k1_table(pb_index *ix, Workspace &ws, int B, int QS, unsigned short *table, int *flags) {
     const int n_groups = (int)(((long long)B * QS + 127) / 128);
     const size_t qelems = (size_t)n_groups * 128 * ix->dim;
     CKS(ws.Qh16t.ensure(qelems * 2));
     CKS(ws.Ql16t.ensure(qelems * 2));
-    CKS(ws.ST16b.ensure((size_t)B * ix->K * QS * 2));
-    CKS(ws.k1diag.ensure((size_t)(B + 4) * 4));
-    CK(cudaMemsetAsync(ws.k1diag.p, 0, (size_t)(B + 4) * 4, ws.stream));
     k_query_split_tiles<<<ix->sm_count, 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), B, QS, ix->dim,
                                                              ws.Qh16t.as<__half>(), ws.Ql16t.as<__half>());
     const int tiles = (int)((ix->K + 127) / 128);
@@ -583,19 +587,118 @@ static pb_status launch_k1_diag(pb_index *ix, Workspace &ws, int B, int QS) {
         CKS(set_smem(kern, sm));                                                                                       \
         kern<<<tiles, 192, sm, ws.stream>>>(ix->cent_h16t.as<__half>(), ix->cent_l16t.as<__half>(), ix->K,             \
                                             ws.Qh16t.as<__half>(), ws.Ql16t.as<__half>(), n_groups, B, QS,             \
-                                            ws.qoff.as<int>(), ws.qrange.as<float2>(), ws.ST16b.as<unsigned short>(),  \
-                                            ws.k1diag.as<int>() + 4);                                                  \
+                                            ws.qoff.as<int>(), ws.qrange.as<float2>(), table, flags);                  \
     }
     switch (ix->dim) {
         case 64: PB_K1_LAUNCH(64) break;
         case 96: PB_K1_LAUNCH(96) break;
         case 128: PB_K1_LAUNCH(128) break;
-        default: return PB_OK;
+        default: return pb_fail(PB_ERR_UNSUPPORTED, "tensor-core score table: dim must be 64, 96 or 128");
     }
 #undef PB_K1_LAUNCH
+    CK(cudaGetLastError());
+    return PB_OK;
+}
+
+// diagnostic twin of the score table on the tensor cores, compared code by code with the exact one
+static pb_status launch_k1_diag(pb_index *ix, Workspace &ws, int B, int QS) {
+    if (ix->dim != 64 && ix->dim != 96 && ix->dim != 128) return PB_OK;
+    CKS(ws.ST16b.ensure((size_t)B * ix->K * QS * 2));
+    CKS(ws.k1diag.ensure((size_t)(B + 4) * 4));
+    CK(cudaMemsetAsync(ws.k1diag.p, 0, (size_t)(B + 4) * 4, ws.stream));
+    CKS(launch_k1_table(ix, ws, B, QS, ws.ST16b.as<unsigned short>(), ws.k1diag.as<int>() + 4));
     k_diff16<<<dim3(ix->sm_count, B), 256, 0, ws.stream>>>(ws.ST16.as<unsigned short>(), ws.ST16b.as<unsigned short>(),
                                                           ws.qoff.as<int>(), ix->K, QS, ws.k1diag.as<int>());
     CK(cudaGetLastError());
+    return PB_OK;
+}
+
+// exact pinned-order rows of ST for a list of centroids per query (k_exact_rows, in place)
+static pb_status launch_exact_rows(pb_index *ix, Workspace &ws, int B, int QS, const uint32_t *list, const int *list_n, int cap) {
+    const size_t smr = (size_t)(PB_TOK_TILE * (ix->dim + 4) + PB_Q_TILE * ix->dim) * sizeof(float);
+    PB_DIM_SWITCH(ix->dim, {
+        auto kern = k_exact_rows<DIM>;
+        CKS(set_smem(kern, smr));
+        kern<<<dim3((cap + PB_TOK_TILE - 1) / PB_TOK_TILE, B), 128, smr, ws.stream>>>(
+            ws.Qi.as<float>(), ws.qoff.as<int>(), QS, ix->centroids.as<float>(), ix->K, list, list_n, cap, 0, ws.ST.as<float>());
+    });
+    CK(cudaGetLastError());
+    return PB_OK;
+}
+
+// a2 + a3 with the dense table from the tensor cores (PB_K1_TC=1).  *ok = false -- a flagged query, a probe-list
+// overflow or an unsupported shape -- means nothing was decided and the caller runs the exact path.
+static pb_status try_k1_tc(pb_index *ix, Workspace &ws, const pb_search_params *p, int B, int QS, int nq_max, int n,
+                           bool batched, int *L, bool *ok, int *cells_cap_out) {
+    *ok = false;
+    const int n_chunks = (int)((ix->K + 1023) / 1024), GQ = QS / 8;
+    if ((GQ & (GQ - 1)) != 0 || GQ > 32 || n_chunks < n || n > 64 || !ix->cent_h16t.p) return PB_OK;
+    if (ix->dim != 64 && ix->dim != 96 && ix->dim != 128) return PB_OK;
+    const int E = ix->k1_margin;
+    CKS(ws.Qi.ensure((size_t)B * QS * ix->dim * 4));
+    k_interleave_query_rows<<<dim3(8, B), 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->dim, ws.Qi.as<float>());
+    CKS(launch_k1_table(ix, ws, B, QS, ws.ST16.as<unsigned short>(), ws.qflag.as<int>()));
+    L[PB_STAGE_CENTROID_SCORES] += 3;
+    const int cap = n * std::max(1, 128 / n);
+    const int cells_cap = (int)std::min<long long>((long long)QS * n, ix->K);
+    CKS(ws.cmax16.ensure((size_t)B * n_chunks * QS * 2));
+    CKS(ws.tau16.ensure((size_t)B * QS * 4));
+    CKS(ws.plist.ensure((size_t)B * QS * cap * 8));
+    CKS(ws.pcount.ensure((size_t)B * QS * 4 + 16));
+    CKS(ws.sel.ensure((size_t)B * QS * n * 8));
+    CKS(ws.cells.ensure((size_t)B * cells_cap * 4));
+    CKS(ws.ncells.ensure((size_t)B * 4 + 16));
+    CKS(ws.ulist.ensure((size_t)B * std::max<long long>(ix->K, (long long)QS * n) * 4));
+    CKS(ws.nulist.ensure((size_t)B * 4 + 16));
+    CK(cudaMemsetAsync(ws.plist.p, 0, (size_t)B * QS * cap * 8, ws.stream));
+    CK(cudaMemsetAsync(ws.pcount.p, 0, (size_t)B * QS * 4 + 16, ws.stream));
+    int *d_fallback = ws.pcount.as<int>() + (size_t)B * QS;
+    k_chunkmax16<<<dim3((n_chunks + 3) / 4, B), 128, 0, ws.stream>>>(ws.ST16.as<unsigned short>(), ix->K, QS, n_chunks,
+                                                                     ws.cmax16.as<unsigned short>());
+    k_tau16<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.cmax16.as<unsigned short>(), ws.qoff.as<int>(), QS, n, n_chunks,
+                                              ws.qflag.as<int>(), ws.tau16.as<uint32_t>(), d_fallback);
+    k_collect16_tc<<<dim3((n_chunks + 3) / 4, B), 128, 0, ws.stream>>>(
+        ws.ST16.as<unsigned short>(), ws.Q.as<float>(), ws.qoff.as<int>(), ix->centroids.as<float>(), ix->dim, 2 * E, ix->K, QS,
+        n_chunks, ws.tau16.as<uint32_t>(), cap, ws.pcount.as<int>(), ws.plist.as<u64>(), d_fallback);
+    CK(cudaGetLastError());
+    int fell_back = 0;  // k_tau16 raises it for flagged queries, k_collect16_tc when a list overflows
+    CK(cudaMemcpyAsync(&fell_back, d_fallback, 4, cudaMemcpyDeviceToHost, ws.stream));
+    CK(cudaStreamSynchronize(ws.stream));
+    if (fell_back) return PB_OK;
+    k_topn_merge<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.plist.as<u64>(), ws.qoff.as<int>(), QS, n, cap / n, ws.sel.as<u64>(),
+                                                  nullptr, 0);
+    // exact rows for the selected centroids, then the cells
+    const int lcap = QS * n;
+    k_sel_list<<<B, 256, 0, ws.stream>>>(ws.sel.as<u64>(), ws.qoff.as<int>(), QS, n, lcap, ws.ulist.as<uint32_t>(), ws.nulist.as<int>());
+    CKS(launch_exact_rows(ix, ws, B, QS, ws.ulist.as<uint32_t>(), ws.nulist.as<int>(), lcap));
+    int P = 1;
+    while (P < std::max(nq_max * n, 1)) P <<= 1;
+    const size_t sm2 = (size_t)P * 12;
+    CKS(set_smem(k_cells_tc, sm2));
+    k_cells_tc<<<B, 256, sm2, ws.stream>>>(ws.sel.as<u64>(), ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, n, cells_cap,
+                                           p->has_centroid_score_threshold, p->centroid_score_threshold, batched ? 1 : 0,
+                                           batched ? (long long)p->centroid_batch_size : ix->K, ws.cells.as<uint32_t>(),
+                                           ws.ncells.as<int>(), ws.ST16.as<unsigned short>(), ws.qrange.as<float2>(), E,
+                                           ws.Q.as<float>(), ix->centroids.as<float>(), ix->dim);
+    CK(cudaGetLastError());
+    L[PB_STAGE_PROBE] += 7;
+    *ok = true;
+    *cells_cap_out = cells_cap;
+    return PB_OK;
+}
+
+// a5 in that mode: exact ST rows for every code of the docs that get the exact re-check
+static pb_status k1_tc_recheck_rows(pb_index *ix, Workspace &ws, int B, int QS, const uint32_t *docs, const int *n_docs,
+                                    long long Wk, int *L) {
+    CKS(ws.codebits.ensure((size_t)B * Wk * 4));
+    CKS(ws.ulist.ensure((size_t)B * ix->K * 4));
+    CKS(ws.nulist.ensure((size_t)B * 4 + 16));
+    k_mark_codes<<<dim3(ix->sm_count * 4, B), 256, 0, ws.stream>>>(docs, ix->D, n_docs, ix->ucodes.as<uint32_t>(),
+                                                                  ix->udoc_off.as<long long>(), ws.codebits.as<uint32_t>(), Wk);
+    k_compact<<<B, 1024, 0, ws.stream>>>(ws.codebits.as<uint32_t>(), Wk, ws.ulist.as<uint32_t>(), ix->K, ws.nulist.as<int>());
+    CK(cudaGetLastError());
+    CKS(launch_exact_rows(ix, ws, B, QS, ws.ulist.as<uint32_t>(), ws.nulist.as<int>(), (int)ix->K));
+    L[PB_STAGE_APPROX] += 3;
     return PB_OK;
 }
 
@@ -919,12 +1022,17 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             CK(cudaGetLastError());
             L[PB_STAGE_CENTROID_SCORES] += 1;
         }
-        CKS(launch_centroid_scores(ix, ws, B, QS, &L[PB_STAGE_CENTROID_SCORES], fast));
+        bool tc = false;  // PB_K1_TC=1: dense table from the tensor cores, exact rows only where a consumer needs them
+        int cells_cap = 0;
+        if (ix->k1_tc && fast && ix->fma2 && ix->probe16 && !ix->cascade && !all_eligible && !big_probe && !d_elig)
+            CKS(try_k1_tc(ix, ws, p, B, QS, nq_max, n_probe, batched, L, &tc, &cells_cap));
+        if (!tc) CKS(launch_centroid_scores(ix, ws, B, QS, &L[PB_STAGE_CENTROID_SCORES], fast));
         if (prof) CK(cudaEventRecord(ws.ev[2], ws.stream));
 
         // ---- a3 probe ----
-        int cells_cap;
-        if (all_eligible) {
+        if (tc) {
+            // cells are in place (try_k1_tc)
+        } else if (all_eligible) {
             cells_cap = (int)n_elig;
             CKS(ws.list.ensure((size_t)n_elig * 4 + 16));
             CKS(ws.cells.ensure((size_t)B * cells_cap * 4));
@@ -1084,13 +1192,17 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             (ix->approx_cg ? k_approx16<true> : k_approx16<false>)<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
                                                   ix->udoc_off.as<long long>(), list, ix->D, list_n, ws.lsum.as<uint32_t>(),
                                                   cascade ? cnt + B + 1 : cnt);
-            k_select_u32<<<B, 1024, 0, ws.stream>>>(ws.lsum.as<uint32_t>(), list_n, M, 4, ws.lsum.as<uint32_t>(), list, list_n,
-                                                    ix->D, ws.qoff.as<int>(), ws.qflag.as<int>(), ws.cand2.as<uint32_t>(),
-                                                    ws.ncand2.as<int>());
+            // band per query token in code units: 4 covers an exact table (+-1 code per side and token); an estimate-built
+            // one moves each code by up to k1_margin - 1 more on each side
+            const int band_per_q = tc ? 2 * ix->k1_margin + 2 : 4;
+            k_select_u32<<<B, 1024, 0, ws.stream>>>(ws.lsum.as<uint32_t>(), list_n, M, band_per_q, ws.lsum.as<uint32_t>(), list,
+                                                    list_n, ix->D, ws.qoff.as<int>(), ws.qflag.as<int>(),
+                                                    ws.cand2.as<uint32_t>(), ws.ncand2.as<int>());
             CK(cudaGetLastError());
             L[PB_STAGE_APPROX] += 2;
             cand_list = ws.cand2.as<uint32_t>();
             cand_n = ws.ncand2.as<int>();
+            if (tc) CKS(k1_tc_recheck_rows(ix, ws, B, QS, cand_list, cand_n, Wk, L));
         }
         k_approx<<<dim3(ix->sm_count * 8, B), 256, 0, ws.stream>>>(
             ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(),

@@ -1,4 +1,4 @@
-// k_k1tc_diag.cuh -- a2 on the tensor cores: diagnostic stages (PB_K1_TC_DIAG).
+// k_k1tc.cuh -- a2 on the tensor cores: diagnostic stages (PB_K1_TC_DIAG).
 // Part of kernels.cuh (included from there, in order; not a standalone header).
 // ==========================================================================================
 // a2 on the tensor cores, stage 1 (diagnostic, PB_K1_TC_DIAG=1; not on the product path yet).
@@ -248,4 +248,222 @@ __global__ void k_cmp_rows(const float *__restrict__ ST, const float *__restrict
     }
     bad = __reduce_add_sync(PB_FULL, bad);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
+}
+
+// ------------------------------------------------------------------------------------------
+// a2 on the tensor cores, stage 2 (PB_K1_TC=1, off by default, unmeasured): the consumers of S when the dense
+// table is the 16-bit one from k_scores16_tc and exact fp32 rows exist only where k_exact_rows put them.
+//   k_collect16_tc  a3: thresholds lowered by the code margin, exact selection keys from pinned-order dots
+//   k_sel_list      a3: the selected centroids of a query as a list (for k_exact_rows -> their exact rows)
+//   k_cells_tc      a3: k_cells whose slab-prefix scan (batched variant) ranks on the 16-bit table and settles the
+//                       codes within the margin by exact dots
+//   k_mark_codes    a5: bitmap of the distinct codes of the docs that get the exact re-check (k_compact turns it
+//                       into the list k_exact_rows consumes)
+// Both generated from their exact-table twins in k_probe.cuh, which stay untouched.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_collect16_tc(const unsigned short *__restrict__ ST16, const float *__restrict__ Q, const int *__restrict__ q_off,
+               const float *__restrict__ C, int dim, int code_margin, long long K, int QS, int n_chunks,
+            const uint32_t *__restrict__ tau, int cap, int *__restrict__ counts, u64 *__restrict__ list,
+            int *__restrict__ fallback) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
+    const int chunk = blockIdx.x * 4 + w;
+    if (chunk >= n_chunks || *fallback) return;
+    const int GQ = QS >> 3, g = lane & (GQ - 1);
+    const long long c0 = (long long)chunk * 1024;
+    const int rows = (int)min(1024ll, K - c0);
+    const uint4 *base = reinterpret_cast<const uint4 *>(ST16 + ((size_t)b * K + c0) * QS);
+    const int total = rows * GQ;
+    // this lane's 8 thresholds as packed halfwords; padding rows (tau = 65536) never match
+    uint32_t t2[4], live[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        // thresholds lowered by the margin: an estimate-built code may sit up to code_margin/2 off its exact value
+        uint32_t a = tau[(size_t)b * QS + 8 * g + 2 * e], c = tau[(size_t)b * QS + 8 * g + 2 * e + 1];
+        if (a < 65536u) a = a > (uint32_t)code_margin ? a - (uint32_t)code_margin : 0u;
+        if (c < 65536u) c = c > (uint32_t)code_margin ? c - (uint32_t)code_margin : 0u;
+        t2[e] = min(a, 65535u) | (min(c, 65535u) << 16);
+        live[e] = (a < 65536u ? 0xffffu : 0u) | (c < 65536u ? 0xffff0000u : 0u);
+    }
+    for (int i0 = lane; i0 < total; i0 += 8 * 32) {
+        uint4 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (i0 + 32 * e < total) ? __ldg(base + i0 + 32 * e) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t hx = __vcmpgeu2(v[e].x, t2[0]) & live[0], hy = __vcmpgeu2(v[e].y, t2[1]) & live[1];
+            const uint32_t hz = __vcmpgeu2(v[e].z, t2[2]) & live[2], hw = __vcmpgeu2(v[e].w, t2[3]) & live[3];
+            if ((hx | hy | hz | hw) == 0u || i0 + 32 * e >= total) continue;  // the common case
+            const long long c = c0 + (i0 + 32 * e) / GQ;
+            const uint32_t hits[4] = {hx, hy, hz, hw};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (!((hits[j >> 1] >> (16 * (j & 1))) & 1u)) continue;
+                const int q = 8 * g + j;
+                const int slot = atomicAdd(&counts[(size_t)b * QS + q], 1);
+                if (slot < cap) {  // the exact selection key: pinned-order dot of the query token and the centroid
+                    const float *qrow = Q + (size_t)(q_off[b] + q) * dim, *crow = C + (size_t)c * dim;
+                    float s = 0.0f;
+                    for (int j = 0; j < dim; ++j) s = __fmaf_rn(qrow[j], crow[j], s);
+                    list[((size_t)b * QS + q) * cap + slot] = ((u64)score_key_asc(s) << 32) | (uint32_t)(~(uint32_t)c);
+                }
+                else atomicOr(fallback, 1);
+            }
+        }
+    }
+}
+
+// grid = B, 256 threads: list[b][0..n_list) = centroid ids of the non-empty selection keys (duplicates allowed)
+__global__ void k_sel_list(const u64 *__restrict__ sel, const int *__restrict__ q_off, int QS, int n, int cap,
+                           uint32_t *__restrict__ list, int *__restrict__ list_n) {
+    __shared__ int fill;
+    const int b = blockIdx.x, nq = q_off[b + 1] - q_off[b];
+    if (threadIdx.x == 0) fill = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nq * n; i += blockDim.x) {
+        const u64 k = sel[(size_t)b * QS * n + i];
+        if (k != 0ull) {
+            const int pos = atomicAdd(&fill, 1);
+            if (pos < cap) list[(size_t)b * cap + pos] = (uint32_t)(~(uint32_t)k);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) list_n[b] = min(fill, cap);
+}
+
+// grid = (CTAs, B): one warp per listed doc, one bit per distinct code
+__global__ void __launch_bounds__(256)
+k_mark_codes(const uint32_t *__restrict__ docs, long long stride, const int *__restrict__ n_docs,
+             const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off, uint32_t *__restrict__ bits,
+             long long W) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int n = n_docs[b];
+    uint32_t *bm = bits + (size_t)b * W;
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t d = docs[(size_t)b * stride + i];
+        for (long long t = udoc_off[d] + lane; t < udoc_off[d + 1]; t += 32) {
+            const uint32_t c = ucodes[t];
+            atomicOr(&bm[c >> 5], 1u << (c & 31));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_cells_tc(const u64 *__restrict__ sel, const float *__restrict__ ST, const int *__restrict__ q_off,
+        long long K, int QS, int n, int cells_cap, int has_thr, float thr, int batched,
+        long long slab, uint32_t *__restrict__ cells, int *__restrict__ n_cells,
+        const unsigned short *__restrict__ ST16, const float2 *__restrict__ qrange, int code_margin,
+        const float *__restrict__ Q, const float *__restrict__ C, int dim) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x;
+    const int nq = q_off[b + 1] - q_off[b];
+    const int total = nq * n;
+    const int P = next_pow2(max(total, 1));
+    u64 *s = reinterpret_cast<u64 *>(smem_raw);  // [P] sort buffer, then unique list
+    int *flags = reinterpret_cast<int *>(s + P);  // [P]
+    __shared__ int scan_tmp[33];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        u64 v = ~0ull;
+        if (i < total) {
+            u64 k = sel[(size_t)b * QS * n + i];  // rows q < nq are the first nq*n entries
+            if (k != 0ull) v = (u64)(uint32_t)(~(uint32_t)k);  // centroid id
+        }
+        s[i] = v;
+    }
+    __syncthreads();
+    bitonic_sort_u64(s, P);
+    // unique
+    int nu = 0;
+    for (int base = 0; base < P; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int f = (i < P && s[i] != ~0ull && (i == 0 || s[i - 1] != s[i])) ? 1 : 0;
+        int tot;
+        int pos = block_exclusive_scan(f, scan_tmp, &tot);
+        u64 v = i < P ? s[i] : 0;
+        __syncthreads();
+        if (f) reinterpret_cast<uint32_t *>(flags)[nu + pos] = (uint32_t)v;  // stage ids in flags
+        nu += tot;
+        __syncthreads();
+    }
+    // move unique ids to the front of s (as u32 in the low half), flags reused below
+    for (int i = threadIdx.x; i < nu; i += blockDim.x) s[i] = reinterpret_cast<uint32_t *>(flags)[i];
+    __syncthreads();
+    // threshold, one warp per unique centroid
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const float *STb = ST + (size_t)b * K * QS;
+    for (int u = w; u < nu; u += nwarps) {
+        const uint32_t c = (uint32_t)s[u];
+        int keep = 1;
+        if (has_thr) {
+            const float *row = STb + (size_t)c * QS;
+            if (!batched) {
+                uint32_t best = 0u;
+                for (int q = lane; q < nq; q += 32) best = max(best, score_key_asc(row[q]));
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) best = max(best, __shfl_xor_sync(PB_FULL, best, m));
+                // Iterator::max_by keeps the last maximum: all non-finite -> the last token's value
+                float mval = best ? key_to_score(best) : (nq > 0 ? row[nq - 1] : -INFINITY);
+                keep = (mval >= thr);
+            } else {
+                // m1 = best finite score among tokens that selected c (they entered their slab heap).
+                // Non-finite scores are not tracked here: with NaN/Inf centroid scores only the
+                // dense variant's threshold is reproduced exactly (DESIGN.md "Limits").
+                uint32_t best = 0u;
+                for (int q = lane; q < nq; q += 32) {
+                    const u64 *sq = sel + ((size_t)b * QS + q) * n;
+                    bool is_sel = false;
+                    for (int i = 0; i < n; ++i)
+                        if (sq[i] != 0ull && (uint32_t)(~(uint32_t)sq[i]) == c) is_sel = true;
+                    if (is_sel) best = max(best, score_key_asc(row[q]));
+                }
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) best = max(best, __shfl_xor_sync(PB_FULL, best, m));
+                float m1 = best ? key_to_score(best) : -INFINITY;
+                keep = (m1 >= thr);
+                if (!keep) {
+                    // another token may have recorded a score >= thr for c while scanning its slab
+                    const long long s0 = (long long)(c / slab) * slab;
+                    for (int q = 0; q < nq && !keep; ++q) {
+                        const float v = row[q];
+                        const uint32_t kv = score_key_asc(v);
+                        if (!(kv != 0u && v >= thr)) continue;  // finite and over the threshold
+                        // entered iff fewer than n earlier slab entries are "not worse" than v
+                        // only the rows of selected centroids are exact in ST here: rank the slab prefix on the 16-bit
+                        // table, and settle the codes within the margin of v's own code by an exact pinned-order dot
+                        const float2 rg = qrange[b];
+                        const int kv16 = (int)fminf(fmaxf(floorf(__fmaf_rn(v, rg.y, rg.x)), 0.0f), 65535.0f);
+                        const unsigned short *col16 = ST16 + (size_t)b * K * QS + q;
+                        const float *qrow = Q + (size_t)(q_off[b] + q) * dim;
+                        int cnt = 0;
+                        for (long long c2 = s0 + lane; c2 < (long long)c; c2 += 32) {
+                            const int cd2 = (int)col16[(size_t)c2 * QS];
+                            if (cd2 > kv16 + code_margin) ++cnt;
+                            else if (cd2 + code_margin >= kv16) {
+                                const float *crow = C + (size_t)c2 * dim;
+                                float s2 = 0.0f;
+                                for (int j = 0; j < dim; ++j) s2 = __fmaf_rn(qrow[j], crow[j], s2);
+                                cnt += (score_key_asc(s2) >= kv) ? 1 : 0;
+                            }
+                        }
+#pragma unroll
+                        for (int m = 16; m >= 1; m >>= 1) cnt += __shfl_xor_sync(PB_FULL, cnt, m);
+                        if (cnt < n) keep = 1;
+                    }
+                }
+            }
+        }
+        if (lane == 0) flags[u] = keep;
+    }
+    __syncthreads();
+    // ordered compaction
+    int outn = 0;
+    for (int base = 0; base < nu; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int f = (i < nu) ? flags[i] : 0;
+        int tot;
+        int pos = block_exclusive_scan(f, scan_tmp, &tot);
+        if (f && outn + pos < cells_cap) cells[(size_t)b * cells_cap + outn + pos] = (uint32_t)s[i];
+        outn += tot;
+    }
+    if (threadIdx.x == 0) n_cells[b] = min(outn, cells_cap);
 }

@@ -18,6 +18,8 @@ VARIANTS = [
     ("FFMA2 in k_exact, filter off", {"PB_FMA2_EXACT": "1", "PB_FAST_EXACT": "0"}),
     ("list-scan probe", {"PB_PROBE16": "0"}),
     ("K1 tensor-core twin (diagnostic)", {"PB_K1_TC_DIAG": "1"}),
+    ("K1 on tensor cores (stage 2)", {"PB_K1_TC": "1"}),
+    ("K1 on tensor cores, margin 6", {"PB_K1_TC": "1", "PB_K1_TC_E": "6"}),
 ]
 
 
