@@ -304,7 +304,7 @@ k_collect16_tc(const unsigned short *__restrict__ ST16, const float *__restrict_
                 if (slot < cap) {  // the exact selection key: pinned-order dot of the query token and the centroid
                     const float *qrow = Q + (size_t)(q_off[b] + q) * dim, *crow = C + (size_t)c * dim;
                     float s = 0.0f;
-                    for (int j = 0; j < dim; ++j) s = __fmaf_rn(qrow[j], crow[j], s);
+                    for (int d = 0; d < dim; ++d) s = __fmaf_rn(qrow[d], crow[d], s);
                     list[((size_t)b * QS + q) * cap + slot] = ((u64)score_key_asc(s) << 32) | (uint32_t)(~(uint32_t)c);
                 }
                 else atomicOr(fallback, 1);
