@@ -208,19 +208,30 @@ extern "C" pb_status pb_index_load(const char *index_dir, int32_t device, pb_ind
     long long ivf_sum = 0;
     for (long long i = 0; i < K; ++i) ivf_sum += ((const int32_t *)ivfl.data)[i];
     if (ivf_sum != ivf.count()) return pb_fail(PB_ERR_IO, "ivf.npy has %lld entries, ivf_lengths sum to %lld", ivf.count(), ivf_sum);
+    const long long packed = (long long)dim * nb / 8;
+    // every chunk file is checked (header, dtype, shape, payload size) before the device is touched: a bad
+    // directory fails here, not after tens of GB have been uploaded
+    auto open_chunk = [&](int c, Npy &codes, Npy &res) -> pb_status {
+        if (pb_status s = codes.open(dir + std::to_string(c) + ".codes.npy")) return s;
+        if (pb_status s = res.open(dir + std::to_string(c) + ".residuals.npy")) return s;
+        if (!codes.is("i8") || codes.count() != chunk_tokens[c])
+            return pb_fail(PB_ERR_IO, "%d.codes.npy must be <i8 [%lld]", c, chunk_tokens[c]);
+        if (!res.is("u1") || res.shape.size() != 2 || res.shape[0] != chunk_tokens[c] || res.shape[1] != packed)
+            return pb_fail(PB_ERR_IO, "%d.residuals.npy must be u1 [%lld, %lld]", c, chunk_tokens[c], packed);
+        return PB_OK;
+    };
+    for (int c = 0; c < (int)num_chunks; ++c) {
+        if (chunk_tokens[c] == 0) continue;
+        Npy codes, res;
+        if (pb_status s = open_chunk(c, codes, res)) return s;
+    }
     pb_index *ix = nullptr;
     if (pb_status s = pb_index_open_begin(&d, &ix)) return s;
-    const long long packed = (long long)dim * nb / 8;
     long long off = 0;
     for (int c = 0; c < (int)num_chunks; ++c) {
         if (chunk_tokens[c] == 0) continue;
         Npy codes, res;
-        pb_status s = codes.open(dir + std::to_string(c) + ".codes.npy");
-        if (!s) s = res.open(dir + std::to_string(c) + ".residuals.npy");
-        if (!s && (!codes.is("i8") || codes.count() != chunk_tokens[c]))
-            s = pb_fail(PB_ERR_IO, "%d.codes.npy must be <i8 [%lld]", c, chunk_tokens[c]);
-        if (!s && (!res.is("u1") || res.shape.size() != 2 || res.shape[0] != chunk_tokens[c] || res.shape[1] != packed))
-            s = pb_fail(PB_ERR_IO, "%d.residuals.npy must be u1 [%lld, %lld]", c, chunk_tokens[c], packed);
+        pb_status s = open_chunk(c, codes, res);
         if (!s) s = pb_index_upload_tokens(ix, off, (const int64_t *)codes.data, res.data, chunk_tokens[c], PB_MEM_HOST);
         if (s) {
             pb_index_close(ix);
