@@ -289,6 +289,14 @@ PB_API pb_status pb_kmeans_fit(int32_t device, const float *samples, int64_t n, 
  */
 PB_API pb_status pb_comm_unique_id(uint8_t *out128);   /* rank 0: 128-byte NCCL unique id */
 PB_API pb_status pb_index_comm_init(pb_index *ix, const uint8_t *id128, int32_t rank, int32_t world);
+/* The same protocol inside ONE process: one handle per shard (same or different devices), one host thread
+ * per handle, all threads call pb_search_batch together.  The exchanges are peer copies behind a host
+ * barrier instead of NCCL; a peer that fails or does not arrive within 60 s breaks the group (PB_ERR_COMM).
+ * The group must outlive every handle that joined it. */
+typedef struct pb_shard_group pb_shard_group;
+PB_API pb_status pb_shard_group_create(int32_t world, pb_shard_group **out);
+PB_API void pb_shard_group_destroy(pb_shard_group *g);
+PB_API pb_status pb_index_group_join(pb_index *ix, pb_shard_group *g, int32_t rank);
 
 /* ---- misc ----------------------------------------------------------------------------- */
 

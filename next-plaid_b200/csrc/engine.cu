@@ -6,7 +6,9 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -49,6 +51,45 @@ struct NcclApi {
     }
 };
 static NcclApi g_nccl;
+
+// ------------------------------------------------------------------------------------------
+// In-process shard group: the same two exchanges without NCCL, for ONE process that drives several shards
+// from several host threads (any mix of devices, including all shards on one GPU -- which is how the merge
+// kernels run under `pytest -m gpu` on a single-GPU box).  An all-gather is a host barrier, one
+// cudaMemcpyPeerAsync per peer into the caller's receive buffer, and a second barrier so nobody reuses a
+// send buffer that is still being read.
+// ------------------------------------------------------------------------------------------
+struct pb_shard_group {
+    int world = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = 0;
+    unsigned long long gen = 0;
+    bool broken = false;
+    int joined = 0;
+    std::vector<const void *> send;
+    std::vector<int> dev;
+    // false = a peer failed or did not arrive within the timeout; the group stays broken
+    bool barrier() {
+        std::unique_lock<std::mutex> g(mu);
+        if (broken) return false;
+        const unsigned long long my = gen;
+        if (++arrived == world) {
+            arrived = 0;
+            ++gen;
+            cv.notify_all();
+            return true;
+        }
+        if (!cv.wait_for(g, std::chrono::seconds(60), [&] { return gen != my || broken; })) broken = true;
+        if (broken) cv.notify_all();
+        return !broken;
+    }
+    void fail() {
+        std::lock_guard<std::mutex> g(mu);
+        broken = true;
+        cv.notify_all();
+    }
+};
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -230,6 +271,7 @@ struct pb_index {
     bool profiling = false;
     size_t st_budget = (size_t)4 << 30;
     ncclComm_t comm = nullptr;  // doc-sharded deployment: one rank per GPU
+    pb_shard_group *group = nullptr;  // or one host thread per shard inside this process (pb_index_group_join)
     int rank = 0, world = 1;
     std::mutex mu;
     std::vector<std::unique_ptr<Workspace>> pool;
@@ -744,6 +786,33 @@ static pb_status launch_centroid_scores_exact(pb_index *ix, Workspace &ws, int B
     return PB_OK;
 }
 
+// all-gather of `count` 64-bit words per rank over whichever transport the handle joined
+static pb_status shard_allgather(pb_index *ix, cudaStream_t stream, const void *send, void *recv, size_t count) {
+    if (ix->comm) {
+        CKN(g_nccl.AllGather(send, recv, count, PB_NCCL_UINT64, ix->comm, stream));
+        return PB_OK;
+    }
+    pb_shard_group *g = ix->group;
+    if (!g) return pb_fail(PB_ERR_COMM, "sharded handle without a transport");
+    cudaError_t e = cudaStreamSynchronize(stream);  // my send buffer is complete
+    if (e != cudaSuccess) {
+        g->fail();
+        return pb_fail(PB_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+    }
+    g->send[ix->rank] = send;
+    if (!g->barrier()) return pb_fail(PB_ERR_COMM, "shard group: a peer failed or timed out");
+    for (int p = 0; p < g->world && e == cudaSuccess; ++p)
+        e = cudaMemcpyPeerAsync(static_cast<char *>(recv) + (size_t)p * count * 8, ix->device, g->send[p], g->dev[p],
+                                count * 8, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // peers may reuse their send buffers after the barrier
+    if (e != cudaSuccess) {
+        g->fail();
+        return pb_fail(PB_ERR_CUDA, "shard group copy failed: %s", cudaGetErrorString(e));
+    }
+    if (!g->barrier()) return pb_fail(PB_ERR_COMM, "shard group: a peer failed or timed out");
+    return PB_OK;
+}
+
 struct KeptView {  // the docs the exact stage scores: the cut's output, or the filter's survivors
     uint32_t *kept;
     int *nkept;
@@ -852,7 +921,7 @@ struct SearchIO {
     pb_trace *trace;
 };
 
-static pb_status search_impl(pb_index *ix, const pb_search_params *p, const SearchIO &io) {
+static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, const SearchIO &io) {
     if (!ix || !p) return pb_fail(PB_ERR_INVALID, "null argument");
     if (io.n_queries < 0) return pb_fail(PB_ERR_INVALID, "n_queries < 0");
     if (io.n_queries > 0 && (!io.queries || !io.q_off)) return pb_fail(PB_ERR_INVALID, "null queries");
@@ -1233,7 +1302,7 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             const int G = ix->world;
             CKS(ws.gkeys.ensure((size_t)G * B * M * 8));
             CKS(ws.krank.ensure((size_t)B * Mcap * 4));
-            CKN(g_nccl.AllGather(ws.lkeys.p, ws.gkeys.p, (size_t)B * M, PB_NCCL_UINT64, ix->comm, ws.stream));
+            CKS(shard_allgather(ix, ws.stream, ws.lkeys.p, ws.gkeys.p, (size_t)B * M));
             int Pg = 1;
             while (Pg < G * M) Pg <<= 1;
             CKS(set_smem(k_merge_cut, (size_t)Pg * 8));
@@ -1306,8 +1375,8 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
             const int G = ix->world;
             CKS(ws.gfkeys.ensure((size_t)G * B * M * 8));
             CKS(ws.gpayload.ensure((size_t)G * B * M * 8));
-            CKN(g_nccl.AllGather(ws.fkeys.p, ws.gfkeys.p, (size_t)B * M, PB_NCCL_UINT64, ix->comm, ws.stream));
-            CKN(g_nccl.AllGather(ws.payload.p, ws.gpayload.p, (size_t)B * M, PB_NCCL_UINT64, ix->comm, ws.stream));
+            CKS(shard_allgather(ix, ws.stream, ws.fkeys.p, ws.gfkeys.p, (size_t)B * M));
+            CKS(shard_allgather(ix, ws.stream, ws.payload.p, ws.gpayload.p, (size_t)B * M));
             int Pg = 1;
             while (Pg < G * M) Pg <<= 1;
             size_t sm = (size_t)Pg * 8 + (size_t)M * 8;
@@ -1421,6 +1490,12 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
     }
     rel.ok = true;
     return PB_OK;
+}
+
+static pb_status search_impl(pb_index *ix, const pb_search_params *p, const SearchIO &io) {
+    const pb_status st = search_impl_inner(ix, p, io);
+    if (st != PB_OK && ix && ix->group) ix->group->fail();  // the peers must not wait for a rank that gave up
+    return st;
 }
 
 extern "C" pb_status pb_search_batch_traced(pb_index *ix, const float *queries, const int64_t *q_tok_offsets,
@@ -1664,6 +1739,30 @@ extern "C" pb_status pb_index_comm_init(pb_index *ix, const uint8_t *id128, int3
     CKN(g_nccl.CommInitRank(&ix->comm, world, id, rank));
     ix->rank = rank;
     ix->world = world;
+    return PB_OK;
+}
+
+// In-process alternative to NCCL: one handle per shard, one host thread per handle (any devices, peer copies)
+extern "C" pb_status pb_shard_group_create(int32_t world, pb_shard_group **out) {
+    if (!out || world < 1 || world > 64) return pb_fail(PB_ERR_INVALID, "shard group: world must be in [1, 64]");
+    pb_shard_group *g = new pb_shard_group();
+    g->world = world;
+    g->send.assign((size_t)world, nullptr);
+    g->dev.assign((size_t)world, 0);
+    *out = g;
+    return PB_OK;
+}
+extern "C" void pb_shard_group_destroy(pb_shard_group *g) { delete g; }
+extern "C" pb_status pb_index_group_join(pb_index *ix, pb_shard_group *g, int32_t rank) {
+    if (!ix || !g) return pb_fail(PB_ERR_INVALID, "null argument");
+    if (rank < 0 || rank >= g->world) return pb_fail(PB_ERR_INVALID, "bad rank %d / world %d", rank, g->world);
+    if (ix->comm || ix->group) return pb_fail(PB_ERR_INVALID, "communicator already initialised");
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->dev[rank] = ix->device;
+    ++g->joined;
+    ix->group = g;
+    ix->rank = rank;
+    ix->world = g->world;
     return PB_OK;
 }
 

@@ -76,7 +76,8 @@ EXPORTS = [
     "pb_search_batch", "pb_search_batch_traced", "pb_centroid_scores", "pb_decompress_documents",
     "pb_maxsim_scores", "pb_exhaustive_scores", "pb_set_profiling", "pb_last_stage_stats",
     "pb_last_work_counters", "pb_search_batch_device", "pb_last_error", "pb_version",
-    "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init", "pb_set_fast_approx", "pb_set_fast_exact",
+    "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init", "pb_shard_group_create", "pb_shard_group_destroy",
+    "pb_index_group_join", "pb_set_fast_approx", "pb_set_fast_exact",
     "pb_codec_open", "pb_codec_close", "pb_codec_compress_into_codes", "pb_codec_compress_and_residuals",
     "pb_codec_encode_chunk", "pb_kmeans_fit", "pb_codec_last_assign_stats", "pb_codec_find_outliers",
 ]
@@ -138,6 +139,10 @@ def load_library():
                                     C.c_void_p]
         L.pb_comm_unique_id.argtypes = [C.c_void_p]
         L.pb_index_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+        L.pb_shard_group_create.argtypes = [C.c_int32, C.c_void_p]
+        L.pb_shard_group_destroy.argtypes = [C.c_void_p]
+        L.pb_shard_group_destroy.restype = None
+        L.pb_index_group_join.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         _lib = L
     return _lib
 
@@ -149,6 +154,48 @@ def _check(status: int):
 
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class ShardGroup:
+    """pb_shard_group: several shard handles of ONE process searched together (one host thread per shard).
+
+    `search_batch` runs the collective from len(shards) threads and returns rank 0's result (every rank's
+    result is identical; `all_results` keeps them for the tests)."""
+
+    def __init__(self, shards: Sequence["MmapIndex"]):
+        self.shards = list(shards)
+        h = C.c_void_p()
+        _check(load_library().pb_shard_group_create(len(self.shards), C.byref(h)))
+        self._g = h
+        for r, s in enumerate(self.shards):
+            _check(load_library().pb_index_group_join(s._h, self._g, r))
+        self.all_results = None
+
+    def search_batch(self, queries, params=None, subset=None):
+        import threading
+        out, err = [None] * len(self.shards), [None] * len(self.shards)
+
+        def run(r):
+            try:
+                out[r] = self.shards[r].search_batch(queries, params, subset=subset)
+            except Exception as e:      # noqa: BLE001 - re-raised below
+                err[r] = e
+        ths = [threading.Thread(target=run, args=(r,)) for r in range(len(self.shards))]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        for e in err:
+            if e is not None:
+                raise e
+        self.all_results = out
+        return out[0]
+
+    def close(self):
+        for s in self.shards:
+            s.close()
+        self.shards = []
+        if self._g:
+            load_library().pb_shard_group_destroy(self._g)
+            self._g = None
 
 
 def comm_unique_id() -> bytes:

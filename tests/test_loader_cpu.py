@@ -41,7 +41,7 @@ def test_well_formed_directory_reaches_the_device(npb, index_dir):
     path, ix = index_dir
     if npb.device_count() > 0:
         gpu = npb.MmapIndex.load(path)
-        assert gpu.num_documents == ix.num_documents and gpu.num_embeddings == ix.num_embeddings
+        assert gpu.num_documents() == ix.num_documents and gpu.num_embeddings() == ix.num_embeddings
         gpu.close()
     else:
         st, msg = _status(npb, path)
