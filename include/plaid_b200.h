@@ -207,7 +207,7 @@ PB_API void pb_set_fast_approx(pb_index *ix, int32_t enabled);
 /* Diagnostic switch for the exact stage (default on): 1 = an fp16 tcgen05 estimate with a certified error bound
  * first picks the kept docs that can still reach the top_k, and only those are scored exactly; 0 = every kept
  * doc is scored exactly.  Same results bit for bit; tests compare both.  (PB_FAST_EXACT=0 in the environment
- * sets the default.)  The filter applies when dim is 64/96/128, queries have <= 32 tokens and no trace is asked. */
+ * sets the default.)  The filter applies when dim is 64/96/128, queries have <= 64 tokens and no trace is asked. */
 PB_API void pb_set_fast_exact(pb_index *ix, int32_t enabled);
 
 /* Enable per-stage CUDA-event timing for subsequent searches on this handle (adds event
@@ -232,6 +232,11 @@ typedef struct pb_work_counters {
                                   * its split-fp16 tensor-core twin (diagnostic; 0 otherwise) */
     int64_t k1_rows_mismatch;    /* PB_K1_TC_DIAG=1 only: words of the sparse exact-row kernel (k_exact_rows, on the probe's
                                   * cells) that differ from the dense score table; 0 expected */
+    int64_t n_probe_threshold;   /* sub-batches whose a3 ran threshold-first on the 16-bit table (no device fallback) */
+    int64_t n_probe_list;        /* sub-batches whose a3 ran the per-lane list scan (fallback, eligibility filter, ...) */
+    int64_t n_k1_tc;             /* sub-batches whose score table came from the tcgen05 kernel (k_scores16_tc) */
+    int64_t n_recheck_docs;      /* docs that got the exact fp32 approximate score (a5 second pass) */
+    int64_t n_k1_tc_redo;        /* sub-batches the tensor-core pass handed back to the exact path (flagged query, list overflow) */
 } pb_work_counters;
 PB_API pb_status pb_last_work_counters(pb_index *ix, pb_work_counters *out);
 

@@ -213,7 +213,7 @@ struct Workspace {
     cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2, cand3, ncand3, ub, theta, rel, cellbits,
-        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, codebits, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax;
+        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -223,7 +223,6 @@ struct Workspace {
         subset_bits.zero_on_grow = true;
         elig.zero_on_grow = true;
         cellbits.zero_on_grow = true;
-        codebits.zero_on_grow = true;
         return PB_OK;
     }
     ~Workspace() {
@@ -253,11 +252,11 @@ struct pb_index {
     bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
                                // the cut sits well above the background score level
     bool fma2 = true;          // FFMA2 (fma.rn.f32x2) k_centroid_scores; PB_FMA2=0 selects the scalar-FFMA twin (same bits)
-    bool k1_tc = false;        // a2 + a3 + the a5 re-check on the tensor-core score table (PB_K1_TC=1; stage 2 of the
-                               // certified a2: unmeasured, off by default)
-    int k1_margin = 3;         // code units an estimate-built 16-bit code may differ from the exact one (PB_K1_TC_E)
-    bool k1_diag = false;      // run the split-fp16 tensor-core score table next to the exact one and report the
-                               // largest code difference (PB_K1_TC_DIAG=1; stage 1 of the certified a2, diagnostic only)
+    bool k1_tc = true;         // a2 on the tensor cores (k_scores16_tc) with its certified consumers: the default;
+                               // PB_K1_TC=0 keeps every sub-batch on the exact fp32 kernel (the device-gated fallback)
+    int k1_margin = 1;         // E: code units an estimate-built 16-bit code may differ from the exact one (PB_K1_TC_E widens it)
+    int cent_exp = 0;          // centroids enter the tensor-core operands scaled by 2^cent_exp (max norm in [1, 2))
+    bool k1_diag = false;      // also run the exact table and report the largest code difference (PB_K1_TC_DIAG=1)
     DevBuf cent_h16t, cent_l16t;  // its centroid operands: fp16 hi / lo, UMMA tile order
     bool fma2_exact = false;   // FFMA2 dots in k_exact (PB_FMA2_EXACT=1; prepared, to be measured)
     bool approx_cg = false;    // k_approx16 row gathers bypass L1 allocation (PB_APPROX_CG=1)
@@ -513,13 +512,15 @@ pb_status pb_index_finalize(pb_index *ix) {
             default: k_min_vnorm<128><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>()); break;
         }
         CK(cudaGetLastError());
-        if (ix->k1_diag || ix->k1_tc) {
+        if ((ix->k1_diag || ix->k1_tc) && ix->cmax > 0.0f && ix->cmax < 3.0e38f) {
+            // operands of the tensor-core score table: centroids * 2^cent_exp (max norm in [1, 2)), fp16 hi / lo parts
+            ix->cent_exp = -ilogbf(ix->cmax);
             const size_t elems = (size_t)((ix->K + 127) / 128) * 128 * ix->dim;
             CKS(ix->cent_h16t.ensure(elems * 2));
             CKS(ix->cent_l16t.ensure(elems * 2));
             CK(cudaMemset(ix->cent_h16t.p, 0, elems * 2));
             CK(cudaMemset(ix->cent_l16t.p, 0, elems * 2));
-            k_rows_to_f16_split_tiles<<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->K, ix->dim,
+            k_rows_to_f16_split_tiles<<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->K, ix->dim, ix->cent_exp,
                                                                 ix->cent_h16t.as<__half>(), ix->cent_l16t.as<__half>());
             CK(cudaGetLastError());
         }
@@ -612,6 +613,19 @@ extern "C" pb_status pb_last_work_counters(pb_index *, pb_work_counters *out) {
 // ------------------------------------------------------------------------------------------
 static pb_status launch_centroid_scores_exact(pb_index *ix, Workspace &ws, int B, int QS, int *launches, bool with16);
 
+// a2 on the tensor cores (k_scores_tc.cuh).  err = certified bound of |exact - estimate| in 16-bit code units
+// (derivation at the top of that file); E = ceil(err) is the largest difference between an estimate-built code and
+// the exact-table code, 2E + 1 the code margin of its consumers.
+static float k1_err_codes(int dim) {
+    const float chain = (float)dim * 5.9604645e-8f;                 // dim * 2^-24: the pinned fp32 FMA chain
+    const float tc = (3.0f * (float)(dim / 16) + 3.0f) * 2.3841858e-7f;  // 2^-22 per MMA accumulation + the dropped split terms
+    const float sub = 2.0f * 2.9802322e-8f * sqrtf((float)dim);     // fp16 subnormal spacing of the lo parts
+    return (chain + tc + sub) * 32768.0f * 1.0001f;
+}
+static bool k1_tc_usable(const pb_index *ix) {
+    return ix->k1_tc && ix->cent_h16t.p && (ix->dim == 64 || ix->dim == 96 || ix->dim == 128) && k1_err_codes(ix->dim) < 1.0f;
+}
+
 // the 16-bit score table from the split-fp16 UMMA GEMM (k_scores16_tc) into `table`; `flags` gets the per-query
 // out-of-range bits the exact kernel would set in qflag
 static pb_status launch_k1_table(pb_index *ix, Workspace &ws, int B, int QS, unsigned short *table, int *flags) {
@@ -619,8 +633,11 @@ static pb_status launch_k1_table(pb_index *ix, Workspace &ws, int B, int QS, uns
     const size_t qelems = (size_t)n_groups * 128 * ix->dim;
     CKS(ws.Qh16t.ensure(qelems * 2));
     CKS(ws.Ql16t.ensure(qelems * 2));
-    k_query_split_tiles<<<ix->sm_count, 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), B, QS, ix->dim,
-                                                             ws.Qh16t.as<__half>(), ws.Ql16t.as<__half>());
+    CKS(ws.qrange_tc.ensure((size_t)B * 8 + 16));
+    k_query_split_tiles<<<ix->sm_count, 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), ws.qexp.as<int>(), B, QS,
+                                                             ix->dim, ws.Qh16t.as<__half>(), ws.Ql16t.as<__half>());
+    k_query_range_tc<<<(B + 127) / 128, 128, 0, ws.stream>>>(ws.qrange.as<float2>(), ws.qexp.as<int>(), ix->cent_exp, B,
+                                                            ws.qrange_tc.as<float2>());
     const int tiles = (int)((ix->K + 127) / 128);
     const size_t sm = (size_t)6 * 128 * ix->dim * 2 + 128;
 #define PB_K1_LAUNCH(DV)                                                                                               \
@@ -629,7 +646,7 @@ static pb_status launch_k1_table(pb_index *ix, Workspace &ws, int B, int QS, uns
         CKS(set_smem(kern, sm));                                                                                       \
         kern<<<tiles, 192, sm, ws.stream>>>(ix->cent_h16t.as<__half>(), ix->cent_l16t.as<__half>(), ix->K,             \
                                             ws.Qh16t.as<__half>(), ws.Ql16t.as<__half>(), n_groups, B, QS,             \
-                                            ws.qoff.as<int>(), ws.qrange.as<float2>(), table, flags);                  \
+                                            ws.qoff.as<int>(), ws.qrange_tc.as<float2>(), table, flags);               \
     }
     switch (ix->dim) {
         case 64: PB_K1_LAUNCH(64) break;
@@ -644,7 +661,7 @@ static pb_status launch_k1_table(pb_index *ix, Workspace &ws, int B, int QS, uns
 
 // diagnostic twin of the score table on the tensor cores, compared code by code with the exact one
 static pb_status launch_k1_diag(pb_index *ix, Workspace &ws, int B, int QS) {
-    if (ix->dim != 64 && ix->dim != 96 && ix->dim != 128) return PB_OK;
+    if (!ix->cent_h16t.p || (ix->dim != 64 && ix->dim != 96 && ix->dim != 128)) return PB_OK;
     CKS(ws.ST16b.ensure((size_t)B * ix->K * QS * 2));
     CKS(ws.k1diag.ensure((size_t)(B + 4) * 4));
     CK(cudaMemsetAsync(ws.k1diag.p, 0, (size_t)(B + 4) * 4, ws.stream));
@@ -655,32 +672,17 @@ static pb_status launch_k1_diag(pb_index *ix, Workspace &ws, int B, int QS) {
     return PB_OK;
 }
 
-// exact pinned-order rows of ST for a list of centroids per query (k_exact_rows, in place)
-static pb_status launch_exact_rows(pb_index *ix, Workspace &ws, int B, int QS, const uint32_t *list, const int *list_n, int cap) {
-    const size_t smr = (size_t)(PB_TOK_TILE * (ix->dim + 4) + PB_Q_TILE * ix->dim) * sizeof(float);
-    PB_DIM_SWITCH(ix->dim, {
-        auto kern = k_exact_rows<DIM>;
-        CKS(set_smem(kern, smr));
-        kern<<<dim3((cap + PB_TOK_TILE - 1) / PB_TOK_TILE, B), 128, smr, ws.stream>>>(
-            ws.Qi.as<float>(), ws.qoff.as<int>(), QS, ix->centroids.as<float>(), ix->K, list, list_n, cap, 0, ws.ST.as<float>());
-    });
-    CK(cudaGetLastError());
-    return PB_OK;
-}
-
-// a2 + a3 with the dense table from the tensor cores (PB_K1_TC=1).  *ok = false -- a flagged query, a probe-list
-// overflow or an unsupported shape -- means nothing was decided and the caller runs the exact path.
-static pb_status try_k1_tc(pb_index *ix, Workspace &ws, const pb_search_params *p, int B, int QS, int nq_max, int n,
-                           bool batched, int *L, bool *ok, int *cells_cap_out) {
-    *ok = false;
-    const int n_chunks = (int)((ix->K + 1023) / 1024), GQ = QS / 8;
-    if ((GQ & (GQ - 1)) != 0 || GQ > 32 || n_chunks < n || n > 64 || !ix->cent_h16t.p) return PB_OK;
-    if (ix->dim != 64 && ix->dim != 96 && ix->dim != 128) return PB_OK;
-    const int E = ix->k1_margin;
+// a2 + a3 on the tensor-core table.  Nothing is read back here: a flagged query or a probe-list overflow raises
+// *d_fallback on the device, the kernels after it stay memory-safe, and the caller redoes the sub-batch on the
+// exact path once it sees the flag at the end.
+static pb_status run_k1_tc(pb_index *ix, Workspace &ws, const pb_search_params *p, int B, int QS, int nq_max, int n,
+                           bool batched, int *L, int *cells_cap_out, const int **d_fallback_out) {
+    const int n_chunks = (int)((ix->K + 1023) / 1024);
+    const int cm = 2 * ix->k1_margin + 1;
     CKS(ws.Qi.ensure((size_t)B * QS * ix->dim * 4));
     k_interleave_query_rows<<<dim3(8, B), 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->dim, ws.Qi.as<float>());
     CKS(launch_k1_table(ix, ws, B, QS, ws.ST16.as<unsigned short>(), ws.qflag.as<int>()));
-    L[PB_STAGE_CENTROID_SCORES] += 3;
+    L[PB_STAGE_CENTROID_SCORES] += 4;
     const int cap = n * std::max(1, 128 / n);
     const int cells_cap = (int)std::min<long long>((long long)QS * n, ix->K);
     CKS(ws.cmax16.ensure((size_t)B * n_chunks * QS * 2));
@@ -690,8 +692,9 @@ static pb_status try_k1_tc(pb_index *ix, Workspace &ws, const pb_search_params *
     CKS(ws.sel.ensure((size_t)B * QS * n * 8));
     CKS(ws.cells.ensure((size_t)B * cells_cap * 4));
     CKS(ws.ncells.ensure((size_t)B * 4 + 16));
-    CKS(ws.ulist.ensure((size_t)B * std::max<long long>(ix->K, (long long)QS * n) * 4));
+    CKS(ws.ulist.ensure((size_t)B * cells_cap * 4));
     CKS(ws.nulist.ensure((size_t)B * 4 + 16));
+    CKS(ws.k1rows.ensure((size_t)B * cells_cap * QS * 4));
     CK(cudaMemsetAsync(ws.plist.p, 0, (size_t)B * QS * cap * 8, ws.stream));
     CK(cudaMemsetAsync(ws.pcount.p, 0, (size_t)B * QS * 4 + 16, ws.stream));
     int *d_fallback = ws.pcount.as<int>() + (size_t)B * QS;
@@ -700,47 +703,34 @@ static pb_status try_k1_tc(pb_index *ix, Workspace &ws, const pb_search_params *
     k_tau16<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.cmax16.as<unsigned short>(), ws.qoff.as<int>(), QS, n, n_chunks,
                                               ws.qflag.as<int>(), ws.tau16.as<uint32_t>(), d_fallback);
     k_collect16_tc<<<dim3((n_chunks + 3) / 4, B), 128, 0, ws.stream>>>(
-        ws.ST16.as<unsigned short>(), ws.Q.as<float>(), ws.qoff.as<int>(), ix->centroids.as<float>(), ix->dim, 2 * E, ix->K, QS,
+        ws.ST16.as<unsigned short>(), ws.Q.as<float>(), ws.qoff.as<int>(), ix->centroids.as<float>(), ix->dim, cm, ix->K, QS,
         n_chunks, ws.tau16.as<uint32_t>(), cap, ws.pcount.as<int>(), ws.plist.as<u64>(), d_fallback);
-    CK(cudaGetLastError());
-    int fell_back = 0;  // k_tau16 raises it for flagged queries, k_collect16_tc when a list overflows
-    CK(cudaMemcpyAsync(&fell_back, d_fallback, 4, cudaMemcpyDeviceToHost, ws.stream));
-    CK(cudaStreamSynchronize(ws.stream));
-    if (fell_back) return PB_OK;
     k_topn_merge<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.plist.as<u64>(), ws.qoff.as<int>(), QS, n, cap / n, ws.sel.as<u64>(),
                                                   nullptr, 0);
-    // exact rows for the selected centroids, then the cells
-    const int lcap = QS * n;
-    k_sel_list<<<B, 256, 0, ws.stream>>>(ws.sel.as<u64>(), ws.qoff.as<int>(), QS, n, lcap, ws.ulist.as<uint32_t>(), ws.nulist.as<int>());
-    CKS(launch_exact_rows(ix, ws, B, QS, ws.ulist.as<uint32_t>(), ws.nulist.as<int>(), lcap));
+    // the selected centroids, their exact rows, the variant's threshold rule
     int P = 1;
     while (P < std::max(nq_max * n, 1)) P <<= 1;
-    const size_t sm2 = (size_t)P * 12;
-    CKS(set_smem(k_cells_tc, sm2));
-    k_cells_tc<<<B, 256, sm2, ws.stream>>>(ws.sel.as<u64>(), ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, n, cells_cap,
-                                           p->has_centroid_score_threshold, p->centroid_score_threshold, batched ? 1 : 0,
-                                           batched ? (long long)p->centroid_batch_size : ix->K, ws.cells.as<uint32_t>(),
-                                           ws.ncells.as<int>(), ws.ST16.as<unsigned short>(), ws.qrange.as<float2>(), E,
-                                           ws.Q.as<float>(), ix->centroids.as<float>(), ix->dim);
+    CKS(set_smem(k_cells_unique, (size_t)P * 8));
+    k_cells_unique<<<B, 256, (size_t)P * 8, ws.stream>>>(ws.sel.as<u64>(), ws.qoff.as<int>(), QS, n, cells_cap,
+                                                         ws.ulist.as<uint32_t>(), ws.nulist.as<int>());
+    const size_t smr = (size_t)(PB_TOK_TILE * (ix->dim + 4) + PB_Q_TILE * ix->dim) * sizeof(float);
+    PB_DIM_SWITCH(ix->dim, {
+        auto kern = k_exact_rows<DIM>;
+        CKS(set_smem(kern, smr));
+        kern<<<dim3((cells_cap + PB_TOK_TILE - 1) / PB_TOK_TILE, B), 128, smr, ws.stream>>>(
+            ws.Qi.as<float>(), ws.qoff.as<int>(), QS, ix->centroids.as<float>(), ws.ulist.as<uint32_t>(), ws.nulist.as<int>(),
+            cells_cap, ws.k1rows.as<float>());
+    });
+    CKS(set_smem(k_cells_thr, (size_t)cells_cap * 4));
+    k_cells_thr<<<B, 256, (size_t)cells_cap * 4, ws.stream>>>(
+        ws.sel.as<u64>(), ws.k1rows.as<float>(), ws.ulist.as<uint32_t>(), ws.nulist.as<int>(), ws.qoff.as<int>(), ix->K, QS, n,
+        cells_cap, p->has_centroid_score_threshold, p->centroid_score_threshold, batched ? 1 : 0,
+        batched ? (long long)p->centroid_batch_size : ix->K, ws.cells.as<uint32_t>(), ws.ncells.as<int>(),
+        ws.ST16.as<unsigned short>(), ws.qrange.as<float2>(), cm, ws.Q.as<float>(), ix->centroids.as<float>(), ix->dim);
     CK(cudaGetLastError());
     L[PB_STAGE_PROBE] += 7;
-    *ok = true;
     *cells_cap_out = cells_cap;
-    return PB_OK;
-}
-
-// a5 in that mode: exact ST rows for every code of the docs that get the exact re-check
-static pb_status k1_tc_recheck_rows(pb_index *ix, Workspace &ws, int B, int QS, const uint32_t *docs, const int *n_docs,
-                                    long long Wk, int *L) {
-    CKS(ws.codebits.ensure((size_t)B * Wk * 4));
-    CKS(ws.ulist.ensure((size_t)B * ix->K * 4));
-    CKS(ws.nulist.ensure((size_t)B * 4 + 16));
-    k_mark_codes<<<dim3(ix->sm_count * 4, B), 256, 0, ws.stream>>>(docs, ix->D, n_docs, ix->ucodes.as<uint32_t>(),
-                                                                  ix->udoc_off.as<long long>(), ws.codebits.as<uint32_t>(), Wk);
-    k_compact<<<B, 1024, 0, ws.stream>>>(ws.codebits.as<uint32_t>(), Wk, ws.ulist.as<uint32_t>(), ix->K, ws.nulist.as<int>());
-    CK(cudaGetLastError());
-    CKS(launch_exact_rows(ix, ws, B, QS, ws.ulist.as<uint32_t>(), ws.nulist.as<int>(), (int)ix->K));
-    L[PB_STAGE_APPROX] += 3;
+    *d_fallback_out = d_fallback;
     return PB_OK;
 }
 
@@ -839,9 +829,9 @@ static pb_status launch_exact(pb_index *ix, Workspace &ws, const KeptView &kv, i
     return PB_OK;
 }
 
-static size_t smem_exact_tc(int dim, int packed) {
+static size_t smem_exact_tc(int dim, int packed, int nqt) {
     const int nbits = packed * 8 / dim;
-    return (size_t)(dim / 8) * PB_XTC_LBO + (size_t)32 * dim * 2 + (size_t)256 * (8 / nbits) * 2 + 64;
+    return (size_t)(dim / 8) * PB_XTC_LBO + (size_t)nqt * dim * 2 + (size_t)256 * (8 / nbits) * 2 + 64;
 }
 
 // error of one fp16 tensor-core similarity relative to |q| (derivation above k_exact_tc); 0 = filter unusable
@@ -857,14 +847,15 @@ static float filter_eps_unit(const pb_index *ix) {
 
 // a7': tensor-core estimate of every kept doc, then the survivors that can still reach the top_k
 static pb_status launch_filter(pb_index *ix, Workspace &ws, const KeptView &in, const KeptView &out, int B, int QS, int Mcap,
-                               int top_k, long long max_tokens, float eps_unit, int *launches) {
+                               int top_k, long long max_tokens, float eps_unit, int nq_max, int *launches) {
     long long chunks = (max_tokens + 127) / 128;
     long long want = std::max<long long>(1, ((long long)ix->sm_count * ix->xtc_grid + B - 1) / B);
     int gx = (int)std::max<long long>(1, std::min<long long>(chunks, want));
-    const size_t sm = smem_exact_tc(ix->dim, ix->packed);
+    const int nqt = nq_max <= 32 ? 32 : 64;
+    const size_t sm = smem_exact_tc(ix->dim, ix->packed, nqt);
 #define PB_TC_LAUNCH(DV, NB)                                                                                           \
     {                                                                                                                  \
-        auto kern = k_exact_tc<DV, NB>;                                                                                \
+        auto kern = nqt == 32 ? k_exact_tc<DV, NB, 32> : k_exact_tc<DV, NB, 64>;                                       \
         CKS(set_smem(kern, sm));                                                                                       \
         kern<<<dim3(gx, B), 128, sm, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS,                             \
                                                   ix->centroids_f16.as<__half>(), ix->w_rev.as<float>(),               \
@@ -1060,6 +1051,16 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         for (int b = 0; b < B; ++b) nq_max = std::max(nq_max, qoff[b + 1] - qoff[b]);
         const int QS = std::max(8, (nq_max + 7) & ~7);
         int *L = g_stats.launches;
+        const bool fast = ix->fast_approx && !io.trace;  // trace wants every candidate's exact approx score
+        // the score table comes from the tensor cores unless something needs the dense fp32 S (an eligibility filter,
+        // the radix-select probe, the cascade, a trace) or the shape is outside the kernel's (DESIGN.md "a2")
+        const int n_chunks_k = (int)((ix->K + 1023) / 1024);
+        const bool want_tc = k1_tc_usable(ix) && fast && !ix->k1_diag && !ix->cascade && !all_eligible && !big_probe && !d_elig &&
+                             QS / 8 <= 32 && n_chunks_k >= n_probe && n_probe <= 64;
+        // One pass over the sub-batch.  use_tc: a flagged query or a probe-list overflow raises a device flag instead of
+        // being read back mid-way; the pass then finishes on (memory-safe) garbage and *redo asks for the exact pass.
+        auto run_sub = [&](const bool use_tc, bool *redo) -> pb_status {
+        *redo = false;
         if (prof) CK(cudaEventRecord(ws.ev[0], ws.stream));
         // ---- H2D ----
         CKS(ws.Q.ensure(std::max<size_t>((size_t)R * ix->dim * 4, 16)));
@@ -1074,33 +1075,34 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
                 CK(cudaMemcpyAsync(ws.Q.p, ws.hq.p, (size_t)R * ix->dim * 4, cudaMemcpyHostToDevice, ws.stream));
             }
         }
-        CKS(ws.hcounts.ensure((size_t)(B + 1) * 4 + (size_t)B * 16 * 4 + (size_t)(B + 2) * 8 + 64 + (size_t)B * 12 + 16));
+        CKS(ws.hcounts.ensure((size_t)(B + 1) * 4 + 16 + (size_t)(B + 2) * 8 + (size_t)B * 8 + (size_t)B * 5 * 4 + 64));
         memcpy(ws.hcounts.p, qoff.data(), (size_t)(B + 1) * 4);
         CK(cudaMemcpyAsync(ws.qoff.p, ws.hcounts.p, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ws.stream));
         if (prof) CK(cudaEventRecord(ws.ev[1], ws.stream));
 
         // ---- a2 centroid scores ----
-        CKS(ws.ST.ensure((size_t)B * ix->K * QS * sizeof(float)));
-        const bool fast = ix->fast_approx && !io.trace;  // trace wants every candidate's exact approx score
+        if (!use_tc) CKS(ws.ST.ensure((size_t)B * ix->K * QS * sizeof(float)));
         if (fast) {
             CKS(ws.ST16.ensure((size_t)B * ix->K * QS * 2));
             CKS(ws.qrange.ensure((size_t)B * 8 + 16));
             CKS(ws.qflag.ensure((size_t)B * 4 + 16));
+            CKS(ws.qexp.ensure((size_t)B * 4 + 16));
             k_query_range<<<B, 32, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), ix->dim, ix->cmax,
-                                                   ws.qrange.as<float2>(), ws.qflag.as<int>());
+                                                   ws.qrange.as<float2>(), ws.qflag.as<int>(), ws.qexp.as<int>());
             CK(cudaGetLastError());
             L[PB_STAGE_CENTROID_SCORES] += 1;
         }
-        bool tc = false;  // PB_K1_TC=1: dense table from the tensor cores, exact rows only where a consumer needs them
+        const bool tc = use_tc;
         int cells_cap = 0;
-        if (ix->k1_tc && fast && ix->fma2 && ix->probe16 && !ix->cascade && !all_eligible && !big_probe && !d_elig)
-            CKS(try_k1_tc(ix, ws, p, B, QS, nq_max, n_probe, batched, L, &tc, &cells_cap));
-        if (!tc) CKS(launch_centroid_scores(ix, ws, B, QS, &L[PB_STAGE_CENTROID_SCORES], fast));
+        const int *d_probe_fallback = nullptr;  // device flag of the threshold-first probe (0 = it did the work)
+        bool probe_list_only = false;
+        if (tc) CKS(run_k1_tc(ix, ws, p, B, QS, nq_max, n_probe, batched, L, &cells_cap, &d_probe_fallback));
+        else CKS(launch_centroid_scores(ix, ws, B, QS, &L[PB_STAGE_CENTROID_SCORES], fast));
         if (prof) CK(cudaEventRecord(ws.ev[2], ws.stream));
 
         // ---- a3 probe ----
         if (tc) {
-            // cells are in place (try_k1_tc)
+            // cells are in place (run_k1_tc)
         } else if (all_eligible) {
             cells_cap = (int)n_elig;
             CKS(ws.list.ensure((size_t)n_elig * 4 + 16));
@@ -1140,8 +1142,9 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             // threshold-first selection on the 16-bit table when there is one (k_chunkmax16 / k_collect16);
             // the per-lane list scan of k_topn_partial otherwise, or when the device raises `fallback`
             const int GQ = QS / 8;
-            const bool thr_path = fast && !d_elig && ix->probe16 && (GQ & (GQ - 1)) == 0 && GQ <= 32 && n_chunks >= n && n <= 64;
+            const bool thr_path = fast && !d_elig && ix->probe16 && GQ <= 32 && n_chunks >= n && n <= 64;
             int *d_fallback = nullptr;
+            probe_list_only = !thr_path;
             if (thr_path) {
                 const int cap = n * std::max(1, 128 / n);
                 CKS(ws.cmax16.ensure((size_t)B * n_chunks * QS * 2));
@@ -1151,6 +1154,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
                 CK(cudaMemsetAsync(ws.plist.p, 0, (size_t)B * QS * cap * 8, ws.stream));
                 CK(cudaMemsetAsync(ws.pcount.p, 0, (size_t)B * QS * 4 + 16, ws.stream));
                 d_fallback = ws.pcount.as<int>() + (size_t)B * QS;
+                d_probe_fallback = d_fallback;
                 k_chunkmax16<<<dim3((n_chunks + 3) / 4, B), 128, 0, ws.stream>>>(ws.ST16.as<unsigned short>(), ix->K, QS, n_chunks,
                                                                                  ws.cmax16.as<unsigned short>());
                 k_tau16<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.cmax16.as<unsigned short>(), ws.qoff.as<int>(), QS, n, n_chunks,
@@ -1177,22 +1181,6 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
                                                 ws.cells.as<uint32_t>(), ws.ncells.as<int>());
             CK(cudaGetLastError());
             L[PB_STAGE_PROBE] += 3;
-        }
-        if (fast && ix->k1_diag && ix->fma2 && ws.k1diag.p && cells_cap > 0) {
-            // diagnostic: the sparse exact-row kernel on the probe's cells must reproduce the dense table's rows
-            CKS(ws.k1rows.ensure((size_t)B * cells_cap * QS * 4));
-            const size_t smr = (size_t)(PB_TOK_TILE * (ix->dim + 4) + PB_Q_TILE * ix->dim) * sizeof(float);
-            PB_DIM_SWITCH(ix->dim, {
-                auto kern = k_exact_rows<DIM>;
-                CKS(set_smem(kern, smr));
-                kern<<<dim3((cells_cap + PB_TOK_TILE - 1) / PB_TOK_TILE, B), 128, smr, ws.stream>>>(
-                    ws.Qi.as<float>(), ws.qoff.as<int>(), QS, ix->centroids.as<float>(), ix->K, ws.cells.as<uint32_t>(),
-                    ws.ncells.as<int>(), cells_cap, 1, ws.k1rows.as<float>());
-            });
-            k_cmp_rows<<<dim3(32, B), 256, 0, ws.stream>>>(ws.ST.as<float>(), ws.k1rows.as<float>(), ws.qoff.as<int>(), ix->K, QS,
-                                                          ws.cells.as<uint32_t>(), ws.ncells.as<int>(), cells_cap,
-                                                          ws.k1diag.as<int>() + 1);
-            CK(cudaGetLastError());
         }
         if (prof) CK(cudaEventRecord(ws.ev[3], ws.stream));
 
@@ -1261,9 +1249,10 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             (ix->approx_cg ? k_approx16<true> : k_approx16<false>)<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
                                                   ix->udoc_off.as<long long>(), list, ix->D, list_n, ws.lsum.as<uint32_t>(),
                                                   cascade ? cnt + B + 1 : cnt);
-            // band per query token in code units: 4 covers an exact table (+-1 code per side and token); an estimate-built
-            // one moves each code by up to k1_margin - 1 more on each side
-            const int band_per_q = tc ? 2 * ix->k1_margin + 2 : 4;
+            // band per query token in code units (W = band * nq + 8).  Exact table: +-1 code of rounding per token and side
+            // plus the fp32 summation error -> 4.  Estimate table (k_scores_tc.cuh): W = nq (1.004 + 2 err) + nq^2/256 + 4
+            // <= nq (ceil(1.004 + 2 err) + 1) + 8 for nq <= 256.
+            const int band_per_q = tc ? (int)ceilf(1.004f + 2.0f * std::max(k1_err_codes(ix->dim), (float)(ix->k1_margin - 1))) + 1 : 4;
             k_select_u32<<<B, 1024, 0, ws.stream>>>(ws.lsum.as<uint32_t>(), list_n, M, band_per_q, ws.lsum.as<uint32_t>(), list,
                                                     list_n, ix->D, ws.qoff.as<int>(), ws.qflag.as<int>(),
                                                     ws.cand2.as<uint32_t>(), ws.ncand2.as<int>());
@@ -1271,13 +1260,18 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             L[PB_STAGE_APPROX] += 2;
             cand_list = ws.cand2.as<uint32_t>();
             cand_n = ws.ncand2.as<int>();
-            if (tc) CKS(k1_tc_recheck_rows(ix, ws, B, QS, cand_list, cand_n, Wk, L));
         }
-        k_approx<<<dim3(ix->sm_count * 8, B), 256, 0, ws.stream>>>(
-            ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(),
-            cand_list, ix->D, cand_n, ws.approx.as<float>(), ws.keys.as<u64>(),
-            fast ? ws.counters.as<unsigned long long>() + B + 1 : ws.counters.as<unsigned long long>(),
-            (uint32_t)ix->doc_id_base);
+        if (tc)  // the exact approximate score of the docs around the cut from pinned-order dots (no dense fp32 S)
+            k_approx_recheck<<<dim3(ix->sm_count * 4, B), 256, 0, ws.stream>>>(
+                ws.ST16.as<unsigned short>(), ws.Q.as<float>(), ws.qoff.as<int>(), ix->centroids.as<float>(), ix->dim, ix->K, QS,
+                ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(), cand_list, ix->D, cand_n, 2 * ix->k1_margin + 1,
+                ws.approx.as<float>(), ws.keys.as<u64>(), ws.counters.as<unsigned long long>() + B + 1, (uint32_t)ix->doc_id_base);
+        else
+            k_approx<<<dim3(ix->sm_count * 8, B), 256, 0, ws.stream>>>(
+                ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(),
+                cand_list, ix->D, cand_n, ws.approx.as<float>(), ws.keys.as<u64>(),
+                fast ? ws.counters.as<unsigned long long>() + B + 1 : ws.counters.as<unsigned long long>(),
+                (uint32_t)ix->doc_id_base);
         CK(cudaGetLastError());
         L[PB_STAGE_APPROX] += 1;
         if (prof) CK(cudaEventRecord(ws.ev[5], ws.stream));
@@ -1323,7 +1317,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
                     sharded ? ws.krank.as<uint32_t>() : nullptr};
         // only the top_k need exact scores: the tensor-core filter drops the docs that provably cannot reach them
         const float eps_unit = filter_eps_unit(ix);
-        const bool filt = ix->fast_exact && !io.trace && ix->centroids_f16.p && eps_unit > 0.0f && nq_max <= 32 &&
+        const bool filt = ix->fast_exact && !io.trace && ix->centroids_f16.p && eps_unit > 0.0f && nq_max <= 64 &&
                           top_k < Mcap && ix->packed % 4 == 0;
         if (filt) {
             CKS(ws.est.ensure((size_t)B * Mcap * 4));
@@ -1337,7 +1331,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             CK(cudaGetLastError());
             KeptView kv2{ws.kept2.as<uint32_t>(), ws.nkept2.as<int>(), ws.tokp2.as<long long>(), ws.krank2.as<uint32_t>()};
             CKS(launch_filter(ix, ws, kv, kv2, B, QS, Mcap, top_k, (long long)Mcap * std::max(ix->max_doclen, 1), eps_unit,
-                              &L[PB_STAGE_EXACT]));
+                              nq_max, &L[PB_STAGE_EXACT]));
             L[PB_STAGE_EXACT] += 1;
             kv = kv2;
             if (!sharded) kv.krank = nullptr;  // survivors keep their order, so position breaks ties the same way
@@ -1394,19 +1388,24 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         if (prof) CK(cudaEventRecord(ws.ev[8], ws.stream));
 
         // ---- D2H ----
-        int *hc = ws.hcounts.as<int>() + (B + 1);  // [3][B]: n_cells, n_cand, n_kept
+        // pinned layout after the (B + 1) query offsets: u64 counters[B + 2] | i64 survivor tokens[B] |
+        // int n_cells[B], n_cand[B], n_kept[B], survivors[B], re-checked[B], probe fallback flag
+        char *hbase = ws.hcounts.as<char>() + (((size_t)(B + 1) * 4 + 15) & ~(size_t)15);
+        unsigned long long *hcnt = reinterpret_cast<unsigned long long *>(hbase);
+        long long *hsurv_tok = reinterpret_cast<long long *>(hcnt + (B + 2));
+        int *hc = reinterpret_cast<int *>(hsurv_tok + B);
+        int *hsurv = hc + 3 * B, *hrecheck = hc + 4 * B, *hfell = hc + 5 * B;
+        *hfell = 0;
         CK(cudaMemcpyAsync(hc, ws.ncells.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
         CK(cudaMemcpyAsync(hc + B, ws.ncand.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
         CK(cudaMemcpyAsync(hc + 2 * B, ws.nkept.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
-        unsigned long long *hcnt = reinterpret_cast<unsigned long long *>(hc + 4 * B);  // 8-byte aligned: (B+1+4B) ints
-        if ((reinterpret_cast<uintptr_t>(hcnt) & 7) != 0) hcnt = reinterpret_cast<unsigned long long *>(hc + 4 * B + 1);
         CK(cudaMemcpyAsync(hcnt, ws.counters.p, (size_t)(B + 2) * 8, cudaMemcpyDeviceToHost, ws.stream));
-        long long *hsurv_tok = reinterpret_cast<long long *>(hcnt + (B + 2));  // [B] survivors' tokens, then [B] ints
-        int *hsurv = reinterpret_cast<int *>(hsurv_tok + B);
         if (filt) {
             CK(cudaMemcpyAsync(hsurv_tok, ws.ktok2.p, (size_t)B * 8, cudaMemcpyDeviceToHost, ws.stream));
             CK(cudaMemcpyAsync(hsurv, ws.nkept2.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
         }
+        if (fast) CK(cudaMemcpyAsync(hrecheck, ws.ncand2.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
+        if (d_probe_fallback) CK(cudaMemcpyAsync(hfell, d_probe_fallback, 4, cudaMemcpyDeviceToHost, ws.stream));
         if (!io.out_on_device) {
             size_t bytes = (size_t)B * top_k * 12 + (size_t)B * 4;
             CKS(ws.hres.ensure(bytes));
@@ -1417,6 +1416,10 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         }
         if (prof) CK(cudaEventRecord(ws.ev[9], ws.stream));
         CK(cudaStreamSynchronize(ws.stream));
+        if (tc && *hfell) {  // the tensor-core pass gave up on the device: same sub-batch again on the exact path
+            *redo = true;
+            return PB_OK;
+        }
         if (!io.out_on_device) {
             char *h = ws.hres.as<char>();
             memcpy(io.out_ids + (size_t)b0 * top_k, h, (size_t)B * top_k * 8);
@@ -1433,10 +1436,15 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             int got[2] = {0, 0};
             CK(cudaMemcpy(got, ws.k1diag.p, 8, cudaMemcpyDeviceToHost));
             g_stats.work.k1_tc_max_code_diff = std::max<long long>(g_stats.work.k1_tc_max_code_diff, got[0]);
-            g_stats.work.k1_rows_mismatch += got[1];
+            g_stats.work.k1_rows_mismatch += 0;
         }
         g_stats.work.n_queries += B;
         g_stats.work.n_query_tokens += R;
+        if (tc) g_stats.work.n_k1_tc += 1;
+        else if (d_probe_fallback) (*hfell ? g_stats.work.n_probe_list : g_stats.work.n_probe_threshold) += 1;
+        else if (probe_list_only) g_stats.work.n_probe_list += 1;
+        if (fast)
+            for (int b = 0; b < B; ++b) g_stats.work.n_recheck_docs += hrecheck[b];
         g_stats.work.n_candidate_tokens += (long long)hcnt[0];
         for (int b = 0; b < B; ++b) {
             g_stats.work.n_cells += hc[b];
@@ -1486,6 +1494,14 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
                                       cudaMemcpyDeviceToHost));
                 }
             }
+        }
+        return PB_OK;
+        };  // run_sub
+        bool redo = false;
+        CKS(run_sub(want_tc, &redo));
+        if (redo) {
+            g_stats.work.n_k1_tc_redo += 1;
+            CKS(run_sub(false, &redo));
         }
     }
     rel.ok = true;

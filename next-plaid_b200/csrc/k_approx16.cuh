@@ -10,8 +10,9 @@
 //   => doc X certainly outranks doc Y when L_X - L_Y > 3.25*nq; band W = 4*nq + 8 code units.
 // Queries whose scores leave [-R, R] or are non-finite (qflag) skip the shortcut entirely.
 // ------------------------------------------------------------------------------------------
+// qexp[b]: the power of two that brings the query's largest token norm into [1, 2) (operand scaling of k_scores16_tc)
 __global__ void k_query_range(const float *__restrict__ Q, const int *__restrict__ q_off, int dim, float cmax,
-                              float2 *__restrict__ qrange, int *__restrict__ qflag) {
+                              float2 *__restrict__ qrange, int *__restrict__ qflag, int *__restrict__ qexp) {
     const int b = blockIdx.x, lane = threadIdx.x;
     const int r0 = q_off[b], nq = q_off[b + 1] - r0;
     float best = 0.0f;
@@ -28,10 +29,15 @@ __global__ void k_query_range(const float *__restrict__ Q, const int *__restrict
     }
     if (lane == 0) {
         float R = cmax * sqrtf(best) * 1.0001f;
+        int kq = 0;
         if (!(R > 1e-30f) || !(R < 1e30f) || bad) {
             R = 1.0f;
             qflag[b] = nq > 0 ? 1 : 0;
-        } else qflag[b] = 0;
+        } else {
+            qflag[b] = 0;
+            kq = -ilogbf(sqrtf(best));
+        }
+        if (qexp) qexp[b] = kq;
         const float scale = 65535.0f / (2.0f * R);
         qrange[b] = make_float2(R * scale, scale);
     }

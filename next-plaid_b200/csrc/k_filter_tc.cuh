@@ -70,8 +70,10 @@ k_min_vnorm(const float *__restrict__ C, const float *__restrict__ w_rev, int nb
     }
 }
 
-template <int DIM, int NBITS>
-__global__ void __launch_bounds__(128, 4)
+// NQT = query rows of the N operand: 32 (nq <= 32, 4 CTAs/SM) or 64 (nq <= 64, e.g. the 48-token default of the
+// reference's ONNX encoder; 3 CTAs/SM)
+template <int DIM, int NBITS, int NQT>
+__global__ void __launch_bounds__(128, NQT == 32 ? 4 : 3)
 k_exact_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, const __half *__restrict__ Ch,
            const float *__restrict__ w_rev, const uint32_t *__restrict__ codes,
            const uint8_t *__restrict__ residuals, const long long *__restrict__ doc_off,
@@ -80,8 +82,9 @@ k_exact_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, c
     extern __shared__ __align__(128) unsigned char smem_x[];
     constexpr int KC = DIM / 8, KSTEPS = DIM / 16;
     static_assert(KC <= 16 && DIM % 16 == 0, "k_exact_tc: one half-warp stages one centroid row");
-    constexpr uint32_t LBO_A = PB_XTC_LBO, A_BYTES = KC * LBO_A, QB_BYTES = 32 * DIM * 2;
-    constexpr uint32_t LBO_B = 4 * 128, SBO = 128;
+    static_assert(NQT == 32 || NQT == 64, "k_exact_tc: N = 32 or 64");
+    constexpr uint32_t LBO_A = PB_XTC_LBO, A_BYTES = KC * LBO_A, QB_BYTES = NQT * DIM * 2;
+    constexpr uint32_t LBO_B = (NQT / 8) * 128, SBO = 128;
     constexpr int PACKED = DIM * NBITS / 8, NW = PACKED / 4;
     static_assert(PACKED % 4 == 0, "k_exact_tc: packed rows are read in 32-bit words");
     constexpr bool PIECES = PACKED % 16 == 0;  // packed rows are read straight into registers, 16 bytes at a time
@@ -109,19 +112,19 @@ k_exact_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, c
         Th[i] = __float2half_rn(w_rev[(byte >> (8 - NBITS * (j + 1))) & ((1 << NBITS) - 1)]);
     }
     // query -> fp16, canonical layout (kc * 4 + r/8) * 128 + (r%8) * 16 + 2e; rows >= nq are zero
-    for (int idx = threadIdx.x; idx < 32 * KC; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < NQT * KC; idx += blockDim.x) {
         const int r = idx / KC, kc = idx - r * KC;
         __half v8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v8[e] = __float2half_rn(r < nq ? Q[(size_t)(r0q + r) * DIM + kc * 8 + e] : 0.0f);
-        *reinterpret_cast<uint4 *>(Qb + (kc * 4 + (r >> 3)) * 128 + (r & 7) * 16) = *reinterpret_cast<uint4 *>(v8);
+        *reinterpret_cast<uint4 *>(Qb + (kc * (NQT / 8) + (r >> 3)) * 128 + (r & 7) * 16) = *reinterpret_cast<uint4 *>(v8);
     }
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (w == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(NQT) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -129,7 +132,7 @@ k_exact_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // instruction descriptor: c = f32 [4,6) = 1, a = b = f16 (format 0), K-major, N>>3 [17,23), M>>4 [24,29)
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(NQT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     uint32_t phase = 0;
     const int hl = lane >> 4, kcl = lane & 15;  // staging: one lane per 8-wide K chunk, two centroid rows per instruction
     const int row = threadIdx.x;                // decompression and epilogue: one thread per token (= TMEM lane)
@@ -244,35 +247,39 @@ k_exact_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, c
         mbar_wait(mbar, phase);
         phase ^= 1u;
         tc_fence_after();
-        // ---- epilogue: thread = token, 32 similarities; per-doc maxima ----
-        uint32_t rr[32];
-        tc_ld32(tmem_base + ((uint32_t)(32 * w) << 16), rr);
+        // ---- epilogue: thread = token, 32 similarities per pass; per-doc maxima ----
         const int rank = cur.r;
         const unsigned grp = __match_any_sync(PB_FULL, rank);
-        // maxima are taken on the order-preserving int image of the float (x ^ ((x >> 31) & 0x7fffffff), its own
-        // inverse); only the publishing lane converts to the score key.  +inf / +NaN win the max and map to key 0 =
-        // "no estimate" (filter off for the query); -NaN loses, like every non-finite value in the exact path.
-        if (grp == PB_FULL) {
-            if (rank >= 0) {  // the warp's 32 tokens belong to one doc: one 32-lane atomic (lane = query token)
-                int mine = 0;
+#pragma unroll 1
+        for (int h = 0; h < NQT / 32; ++h) {
+            if (32 * h >= nq) break;
+            uint32_t rr[32];
+            tc_ld32(tmem_base + ((uint32_t)(32 * w) << 16) + 32 * h, rr);
+            // maxima are taken on the order-preserving int image of the float (x ^ ((x >> 31) & 0x7fffffff), its own
+            // inverse); only the publishing lane converts to the score key.  +inf / +NaN win the max and map to key 0 =
+            // "no estimate" (filter off for the query); -NaN loses, like every non-finite value in the exact path.
+            if (grp == PB_FULL) {
+                if (rank >= 0) {  // the warp's 32 tokens belong to one doc: one 32-lane atomic (lane = query token)
+                    int mine = 0;
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const int x = __float_as_int(__uint_as_float(rr[q]) * inv);
-                    const int m = __reduce_max_sync(PB_FULL, x ^ ((x >> 31) & 0x7fffffff));
-                    if (lane == q) mine = m;
+                    for (int q = 0; q < 32; ++q) {
+                        const int x = __float_as_int(__uint_as_float(rr[q]) * inv);
+                        const int m = __reduce_max_sync(PB_FULL, x ^ ((x >> 31) & 0x7fffffff));
+                        if (lane == q) mine = m;
+                    }
+                    const uint32_t key = score_key_asc(__int_as_float(mine ^ ((mine >> 31) & 0x7fffffff)));
+                    if (32 * h + lane < nq && key) atomicMax(&maxkey[((size_t)b * Mcap + rank) * QS + 32 * h + lane], key);
                 }
-                const uint32_t key = score_key_asc(__int_as_float(mine ^ ((mine >> 31) & 0x7fffffff)));
-                if (lane < nq && key) atomicMax(&maxkey[((size_t)b * Mcap + rank) * QS + lane], key);
-            }
-        } else if (rank >= 0) {  // doc boundary inside the warp: reduce per group, the group's first lane publishes
-            const int leader = __ffs(grp) - 1;
-            uint32_t *mrow = &maxkey[((size_t)b * Mcap + rank) * QS];
+            } else if (rank >= 0) {  // doc boundary inside the warp: reduce per group, the group's first lane publishes
+                const int leader = __ffs(grp) - 1;
+                uint32_t *mrow = &maxkey[((size_t)b * Mcap + rank) * QS + 32 * h];
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {  // unrolled: rr stays in registers
-                const int x = __float_as_int(__uint_as_float(rr[q]) * inv);
-                const int m = __reduce_max_sync(grp, x ^ ((x >> 31) & 0x7fffffff));
-                const uint32_t key = score_key_asc(__int_as_float(m ^ ((m >> 31) & 0x7fffffff)));
-                if (lane == leader && q < nq && key) atomicMax(mrow + q, key);
+                for (int q = 0; q < 32; ++q) {  // unrolled: rr stays in registers
+                    const int x = __float_as_int(__uint_as_float(rr[q]) * inv);
+                    const int m = __reduce_max_sync(grp, x ^ ((x >> 31) & 0x7fffffff));
+                    const uint32_t key = score_key_asc(__int_as_float(m ^ ((m >> 31) & 0x7fffffff)));
+                    if (lane == leader && 32 * h + q < nq && key) atomicMax(mrow + q, key);
+                }
             }
         }
         tc_fence_before();
@@ -281,7 +288,7 @@ k_exact_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, c
     __syncthreads();
     if (w == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NQT) : "memory");
     }
 }
 

@@ -88,37 +88,45 @@ k_chunkmax16(const unsigned short *__restrict__ ST16, long long K, int QS, int n
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
     const int chunk = blockIdx.x * 4 + w;
     if (chunk >= n_chunks) return;
-    const int GQ = QS >> 3;
+    // GQ lanes cover one row; L = the largest multiple of GQ that fits a warp, so a lane keeps its 8 query
+    // tokens for the whole scan (GQ a power of two: L = 32; nq = 48: GQ = 6, L = 30, two lanes idle)
+    const int GQ = QS >> 3, L = (32 / GQ) * GQ;
     const long long c0 = (long long)chunk * 1024;
     const int rows = (int)min(1024ll, K - c0);
     const uint4 *base = reinterpret_cast<const uint4 *>(ST16 + ((size_t)b * K + c0) * QS);
     const int total = rows * GQ;
     uint4 acc = make_uint4(0, 0, 0, 0);
-    int idx = lane;
-    for (; idx + 7 * 32 < total; idx += 8 * 32) {
-        uint4 v[8];
+    if (lane < L) {
+        int idx = lane;
+        for (; idx + 7 * L < total; idx += 8 * L) {
+            uint4 v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __ldg(base + idx + 32 * e);
+            for (int e = 0; e < 8; ++e) v[e] = __ldg(base + idx + L * e);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            acc.x = __vmaxu2(acc.x, v[e].x);
-            acc.y = __vmaxu2(acc.y, v[e].y);
-            acc.z = __vmaxu2(acc.z, v[e].z);
-            acc.w = __vmaxu2(acc.w, v[e].w);
+            for (int e = 0; e < 8; ++e) {
+                acc.x = __vmaxu2(acc.x, v[e].x);
+                acc.y = __vmaxu2(acc.y, v[e].y);
+                acc.z = __vmaxu2(acc.z, v[e].z);
+                acc.w = __vmaxu2(acc.w, v[e].w);
+            }
+        }
+        for (; idx < total; idx += L) {
+            const uint4 v = __ldg(base + idx);
+            acc.x = __vmaxu2(acc.x, v.x);
+            acc.y = __vmaxu2(acc.y, v.y);
+            acc.z = __vmaxu2(acc.z, v.z);
+            acc.w = __vmaxu2(acc.w, v.w);
         }
     }
-    for (; idx < total; idx += 32) {
-        const uint4 v = __ldg(base + idx);
-        acc.x = __vmaxu2(acc.x, v.x);
-        acc.y = __vmaxu2(acc.y, v.y);
-        acc.z = __vmaxu2(acc.z, v.z);
-        acc.w = __vmaxu2(acc.w, v.w);
-    }
-    for (int m = GQ; m < 32; m <<= 1) {  // lanes with the same lane % GQ hold the same query tokens
-        acc.x = __vmaxu2(acc.x, __shfl_xor_sync(PB_FULL, acc.x, m));
-        acc.y = __vmaxu2(acc.y, __shfl_xor_sync(PB_FULL, acc.y, m));
-        acc.z = __vmaxu2(acc.z, __shfl_xor_sync(PB_FULL, acc.z, m));
-        acc.w = __vmaxu2(acc.w, __shfl_xor_sync(PB_FULL, acc.w, m));
+    for (int off = GQ; off < L; off <<= 1) {  // lanes g, g + GQ, g + 2 GQ, ... hold the same query tokens
+        const uint32_t ox = __shfl_down_sync(PB_FULL, acc.x, off), oy = __shfl_down_sync(PB_FULL, acc.y, off);
+        const uint32_t oz = __shfl_down_sync(PB_FULL, acc.z, off), ow = __shfl_down_sync(PB_FULL, acc.w, off);
+        if (lane + off < L) {
+            acc.x = __vmaxu2(acc.x, ox);
+            acc.y = __vmaxu2(acc.y, oy);
+            acc.z = __vmaxu2(acc.z, oz);
+            acc.w = __vmaxu2(acc.w, ow);
+        }
     }
     if (lane < GQ) *reinterpret_cast<uint4 *>(cmax + ((size_t)b * n_chunks + chunk) * QS + 8 * lane) = acc;
 }
@@ -152,7 +160,8 @@ k_collect16(const unsigned short *__restrict__ ST16, const float *__restrict__ S
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
     const int chunk = blockIdx.x * 4 + w;
     if (chunk >= n_chunks || *fallback) return;
-    const int GQ = QS >> 3, g = lane & (GQ - 1);
+    const int GQ = QS >> 3, L = (32 / GQ) * GQ, g = lane % GQ;  // lane -> query-token group as in k_chunkmax16
+    if (lane >= L) return;
     const long long c0 = (long long)chunk * 1024;
     const int rows = (int)min(1024ll, K - c0);
     const uint4 *base = reinterpret_cast<const uint4 *>(ST16 + ((size_t)b * K + c0) * QS);
@@ -165,16 +174,16 @@ k_collect16(const unsigned short *__restrict__ ST16, const float *__restrict__ S
         t2[e] = min(a, 65535u) | (min(c, 65535u) << 16);
         live[e] = (a < 65536u ? 0xffffu : 0u) | (c < 65536u ? 0xffff0000u : 0u);
     }
-    for (int i0 = lane; i0 < total; i0 += 8 * 32) {
+    for (int i0 = lane; i0 < total; i0 += 8 * L) {
         uint4 v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (i0 + 32 * e < total) ? __ldg(base + i0 + 32 * e) : make_uint4(0, 0, 0, 0);
+        for (int e = 0; e < 8; ++e) v[e] = (i0 + L * e < total) ? __ldg(base + i0 + L * e) : make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const uint32_t hx = __vcmpgeu2(v[e].x, t2[0]) & live[0], hy = __vcmpgeu2(v[e].y, t2[1]) & live[1];
             const uint32_t hz = __vcmpgeu2(v[e].z, t2[2]) & live[2], hw = __vcmpgeu2(v[e].w, t2[3]) & live[3];
-            if ((hx | hy | hz | hw) == 0u || i0 + 32 * e >= total) continue;  // the common case
-            const long long c = c0 + (i0 + 32 * e) / GQ;
+            if ((hx | hy | hz | hw) == 0u || i0 + L * e >= total) continue;  // the common case
+            const long long c = c0 + (i0 + L * e) / GQ;
             const uint32_t hits[4] = {hx, hy, hz, hw};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {

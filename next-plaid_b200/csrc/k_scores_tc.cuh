@@ -1,25 +1,44 @@
-// k_k1tc.cuh -- a2 on the tensor cores: diagnostic stages (PB_K1_TC_DIAG).
+// k_scores_tc.cuh -- a2 on the tensor cores (the default path) and the consumers of its score table.
 // Part of kernels.cuh (included from there, in order; not a standalone header).
 // ==========================================================================================
-// a2 on the tensor cores, stage 1 (diagnostic, PB_K1_TC_DIAG=1; not on the product path yet).
-// The 16-bit score table from a 3-product split-fp16 UMMA GEMM: x = xh + xl (xh = fp16(x), xl = fp16(x - xh)),
-// S~ = qh.ch + qh.cl + ql.ch accumulated in fp32 in TMEM.  M = 128 centroids = TMEM lanes, N = 128 rows of the
-// QS-padded query layout (row = b*QS + q), so a thread's accumulator row is a run of ST16[b][c][.] rows.
-// The engine runs it next to k_centroid_scores and reports the largest code difference
-// (pb_work_counters.k1_tc_max_code_diff): the measured input for the certified consumers of profiles/r01_summary.md.
+// a2 = the one dense contraction of the path (search.rs:345 / :171-174): S = Q C^T for every query token of the
+// sub-batch against all K centroids.  k_scores16_tc computes it as a 3-product split-fp16 UMMA GEMM
+//     x = xh + xl  (xh = fp16(x), xl = fp16(x - xh));   S~ = qh.ch + qh.cl + ql.ch   (fp32 accumulator in TMEM)
+// and writes ONLY the 16-bit fixed-point score table ST16[b][c][QS] the probe (a3) and the first approximate pass
+// (a5) stream / gather.  Nothing downstream needs a dense fp32 S: the few values that decide something
+//   - the exact selection keys of the probe winners            (k_collect16_tc)
+//   - the threshold test of the selected cells                 (k_cells_unique -> k_exact_rows -> k_cells_thr)
+//   - the per-token maxima of the docs around the cut          (k_approx_recheck)
+// are recomputed as pinned-order fp32 dots (common.cuh), so every decision and every output bit equals the
+// exact path's.
+//
+// Error budget (the certificate).  Both operands are scaled by powers of two (exact) so that max|q'|, max|c'| are
+// in [1, 2): kq per query (k_query_range), kc per index (pb_index_finalize).  With e = the pinned-order fp32 dot
+// and t = the tensor-core estimate of the same pair, in units of R' = max|q'| max|c'| (1 + 1e-4):
+//     |e - q.c|  <= dim 2^-24                     (fp32 FMA chain, |partial sums| <= |q'||c'|)
+//     |t - q.c|  <= 3 * 2^-22 + 2^-21             (two dropped split terms + ql.cl; fp32 accumulation of 3 dim/16 MMAs)
+//                   + 2^-25 sqrt(dim) (|q'| + |c'|) / R'   (fp16 subnormal spacing of the lo parts)
+// => |e - t| * scale <= err_codes(dim) = (dim 2^-24 + 2^-20) * 32768 + 4 * 2^-25 sqrt(dim) * 32768 < 0.34 for
+// dim <= 128 (k1_err_codes() in engine.cu), i.e. an estimate-built code differs from the exact-table code by at most
+// E = 1.  Consumers use: code margin 2E + 1 = 3 for "could still be the maximum / in the top n", and the band
+// W = nq (1.004 + 2 err) + nq^2 / 256 + 4 for the first approximate pass (derivations at each kernel).
+// PB_K1_TC_DIAG=1 measures the largest code difference against the exact table (pb_work_counters).
 // grid = ceil(K/128) CTAs, 192 threads: warps 0-3 epilogue, warp 4 bulk-copy loader, warp 5 MMA issuer.
 // ==========================================================================================
-// fp16 hi/lo split of `n` rows into UMMA tile order (128-row tiles, K-major core matrices); rows >= n stay zero
-__global__ void k_rows_to_f16_split_tiles(const float *__restrict__ X, long long n, int dim, __half *__restrict__ Xh,
-                                          __half *__restrict__ Xl) {
+
+// fp16 hi/lo split of `n` rows, scaled by 2^kexp, into UMMA tile order (128-row tiles, K-major core matrices);
+// rows >= n stay zero
+__global__ void k_rows_to_f16_split_tiles(const float *__restrict__ X, long long n, int dim, int kexp,
+                                          __half *__restrict__ Xh, __half *__restrict__ Xl) {
     const int lane = threadIdx.x & 31;
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
     const size_t tile_elems = (size_t)128 * dim;
+    const float mul = ldexpf(1.0f, kexp);
     for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += nw) {
         const size_t tbase = (size_t)(r >> 7) * tile_elems;
         const int rr = (int)(r & 127);
         for (int j = lane; j < dim; j += 32) {
-            const float v = X[(size_t)r * dim + j];
+            const float v = X[(size_t)r * dim + j] * mul;
             const __half h = __float2half_rn(v);
             const size_t o = tbase + (size_t)((j >> 3) * 16 + (rr >> 3)) * 64 + (rr & 7) * 8 + (j & 7);
             Xh[o] = h;
@@ -28,9 +47,10 @@ __global__ void k_rows_to_f16_split_tiles(const float *__restrict__ X, long long
     }
 }
 
-// the same for the query rows in the QS-padded layout (row = b*QS + q, rows q >= nq are zero)
-__global__ void k_query_split_tiles(const float *__restrict__ Q, const int *__restrict__ q_off, int B, int QS, int dim,
-                                    __half *__restrict__ Qh, __half *__restrict__ Ql) {
+// the same for the query rows in the QS-padded layout (row = b*QS + q, rows q >= nq are zero); query b is scaled by
+// 2^qexp[b]
+__global__ void k_query_split_tiles(const float *__restrict__ Q, const int *__restrict__ q_off, const int *__restrict__ qexp,
+                                    int B, int QS, int dim, __half *__restrict__ Qh, __half *__restrict__ Ql) {
     const int lane = threadIdx.x & 31;
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
     const size_t tile_elems = (size_t)128 * dim;
@@ -39,10 +59,11 @@ __global__ void k_query_split_tiles(const float *__restrict__ Q, const int *__re
         const long long b = r / QS;
         const int q = (int)(r - b * QS);
         const bool real = b < B && q < q_off[b + 1] - q_off[b];
+        const float mul = real ? ldexpf(1.0f, qexp[b]) : 0.0f;
         const size_t tbase = (size_t)(r >> 7) * tile_elems;
         const int rr = (int)(r & 127);
         for (int j = lane; j < dim; j += 32) {
-            const float v = real ? Q[(size_t)(q_off[b] + q) * dim + j] : 0.0f;
+            const float v = real ? Q[(size_t)(q_off[b] + q) * dim + j] * mul : 0.0f;
             const __half h = __float2half_rn(v);
             const size_t o = tbase + (size_t)((j >> 3) * 16 + (rr >> 3)) * 64 + (rr & 7) * 8 + (j & 7);
             Qh[o] = h;
@@ -51,11 +72,20 @@ __global__ void k_query_split_tiles(const float *__restrict__ Q, const int *__re
     }
 }
 
+// qrange_tc[b] = (R*scale, scale * 2^-(qexp[b] + kc)): the code of an accumulator value of the scaled operands
+__global__ void k_query_range_tc(const float2 *__restrict__ qrange, const int *__restrict__ qexp, int kc, int B,
+                                 float2 *__restrict__ qrange_tc) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float2 rg = qrange[b];
+    qrange_tc[b] = make_float2(rg.x, ldexpf(rg.y, -(qexp[b] + kc)));
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(192, 1)
 k_scores16_tc(const __half *__restrict__ Ch, const __half *__restrict__ Cl, long long K, const __half *__restrict__ Qh,
               const __half *__restrict__ Ql, int n_groups, int B, int QS, const int *__restrict__ q_off,
-              const float2 *__restrict__ qrange, unsigned short *__restrict__ ST16, int *__restrict__ qflag) {
+              const float2 *__restrict__ qrange_tc, unsigned short *__restrict__ ST16, int *__restrict__ qflag) {
     extern __shared__ __align__(128) unsigned char smem_k1[];
     constexpr int KSTEPS = DIM / 16;
     constexpr uint32_t T_BYTES = 128 * DIM * 2;  // one 128-row fp16 tile
@@ -142,7 +172,7 @@ k_scores16_tc(const __half *__restrict__ Ch, const __half *__restrict__ Cl, long
                     const int b = (int)(row0 / QS), q = (int)(row0 - (long long)b * QS);
                     if (b >= B || c >= K) continue;
                     const int nq = q_off[b + 1] - q_off[b];
-                    const float2 rg = qrange[b];  // (R*scale, scale)
+                    const float2 rg = qrange_tc[b];  // (R*scale, scale / 2^(kq+kc))
                     uint32_t cd[8];
                     bool real_bad = false;
 #pragma unroll
@@ -168,7 +198,7 @@ k_scores16_tc(const __half *__restrict__ Ch, const __half *__restrict__ Cl, long
     }
 }
 
-// largest |a - b| over the codes of real query tokens (diagnostic)
+// largest |a - b| over the codes of real query tokens (PB_K1_TC_DIAG)
 __global__ void k_diff16(const unsigned short *__restrict__ a, const unsigned short *__restrict__ b, const int *__restrict__ q_off,
                          long long K, int QS, int *__restrict__ out_max) {
     const int bq = blockIdx.y, nq = q_off[bq + 1] - q_off[bq];
@@ -184,18 +214,14 @@ __global__ void k_diff16(const unsigned short *__restrict__ a, const unsigned sh
 }
 
 // ------------------------------------------------------------------------------------------
-// a2 on the tensor cores, stage 2 building block (diagnostic under PB_K1_TC_DIAG=1): exact pinned-order score
-// rows for a LIST of centroids per query -- the sparse fp32 pass that will serve the consumers which need exact
-// values (probe winners, cells, the a5 re-check) once the dense table comes from k_scores16_tc.
+// Exact pinned-order score rows for a LIST of centroids per query: OUT[b][i][QS] = S[q][list[b][i]].
 // Same FFMA2 tile as k_centroid_scores<., true>; the centroid rows are gathered with cp.async.
-// out row = list position (compact = 1: OUT[b][cap][QS]) or the centroid id (compact = 0: ST[b][K][QS]).
 // grid = (ceil(cap/128), B), 128 threads.
 // ------------------------------------------------------------------------------------------
 template <int DIM>
 __global__ void __launch_bounds__(128, 2)
-k_exact_rows(const float *__restrict__ Qi, const int *__restrict__ q_off, int QS, const float *__restrict__ C, long long K,
-             const uint32_t *__restrict__ list, const int *__restrict__ list_n, int cap, int compact,
-             float *__restrict__ out) {
+k_exact_rows(const float *__restrict__ Qi, const int *__restrict__ q_off, int QS, const float *__restrict__ C,
+             const uint32_t *__restrict__ list, const int *__restrict__ list_n, int cap, float *__restrict__ out) {
     extern __shared__ __align__(16) float smem[];
     constexpr int LD = DIM + 4, G = DIM / 4;
     float *Vs = smem;                      // [128][LD] gathered centroid rows
@@ -222,8 +248,7 @@ k_exact_rows(const float *__restrict__ Qi, const int *__restrict__ q_off, int QS
             for (int k = 0; k < 4; ++k) {
                 const int i = lane + 32 * k;
                 if (i < nv) {
-                    const size_t row = compact ? (size_t)b * cap + i0 + i : (size_t)b * K + lst[i];
-                    float4 *dst = reinterpret_cast<float4 *>(out + row * QS + qb + 8 * w);
+                    float4 *dst = reinterpret_cast<float4 *>(out + ((size_t)b * cap + i0 + i) * QS + qb + 8 * w);
                     dst[0] = make_float4(acc[0][k], acc[1][k], acc[2][k], acc[3][k]);
                     dst[1] = make_float4(acc[4][k], acc[5][k], acc[6][k], acc[7][k]);
                 }
@@ -233,43 +258,36 @@ k_exact_rows(const float *__restrict__ Qi, const int *__restrict__ q_off, int QS
     }
 }
 
-// number of 32-bit words that differ between OUT[b][i][q] and ST[b][list[i]][q] (diagnostic; 0 expected)
-__global__ void k_cmp_rows(const float *__restrict__ ST, const float *__restrict__ OUT, const int *__restrict__ q_off, long long K,
-                           int QS, const uint32_t *__restrict__ list, const int *__restrict__ list_n, int cap,
-                           int *__restrict__ mismatches) {
-    const int b = blockIdx.y, n = min(list_n[b], cap), nq8 = ((q_off[b + 1] - q_off[b]) + 7) & ~7;
-    int bad = 0;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)n * QS; t += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(t / QS), q = (int)(t - (long long)i * QS);
-        if (q >= nq8) continue;
-        const uint32_t x = __float_as_uint(ST[((size_t)b * K + list[(size_t)b * cap + i]) * QS + q]);
-        const uint32_t y = __float_as_uint(OUT[((size_t)b * cap + i) * QS + q]);
-        bad += x != y;
+// the pinned-order dot of common.cuh for one (query token, centroid) pair, 128-bit loads
+PB_DEV float pinned_dot(const float *__restrict__ q, const float *__restrict__ c, int dim) {
+    float s = 0.0f;
+    for (int j = 0; j < dim; j += 4) {
+        const float4 a = *reinterpret_cast<const float4 *>(q + j), v = *reinterpret_cast<const float4 *>(c + j);
+        s = __fmaf_rn(a.x, v.x, s);
+        s = __fmaf_rn(a.y, v.y, s);
+        s = __fmaf_rn(a.z, v.z, s);
+        s = __fmaf_rn(a.w, v.w, s);
     }
-    bad = __reduce_add_sync(PB_FULL, bad);
-    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
+    return s;
 }
 
 // ------------------------------------------------------------------------------------------
-// a2 on the tensor cores, stage 2 (PB_K1_TC=1, off by default, unmeasured): the consumers of S when the dense
-// table is the 16-bit one from k_scores16_tc and exact fp32 rows exist only where k_exact_rows put them.
-//   k_collect16_tc  a3: thresholds lowered by the code margin, exact selection keys from pinned-order dots
-//   k_sel_list      a3: the selected centroids of a query as a list (for k_exact_rows -> their exact rows)
-//   k_cells_tc      a3: k_cells whose slab-prefix scan (batched variant) ranks on the 16-bit table and settles the
-//                       codes within the margin by exact dots
-//   k_mark_codes    a5: bitmap of the distinct codes of the docs that get the exact re-check (k_compact turns it
-//                       into the list k_exact_rows consumes)
-// Both generated from their exact-table twins in k_probe.cuh, which stay untouched.
+// a3 on the tensor-core table.  k_chunkmax16 / k_tau16 (k_probe.cuh) run unchanged: tau = the n-th largest chunk
+// maximum of a token's ESTIMATE codes, so n entries with code >= tau exist (set A).  An entry x of the exact top n
+// outside A displaces some a in A with e(x) >= e(a), hence t(x) >= t(a) - 2 delta and code(x) >= code(a) - (2E + 1)
+// >= tau - code_margin: k_collect16_tc lowers the thresholds by code_margin and takes the exact selection key of
+// every hit from a pinned-order dot, so k_topn_merge ranks exactly the keys the exact path would.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_collect16_tc(const unsigned short *__restrict__ ST16, const float *__restrict__ Q, const int *__restrict__ q_off,
                const float *__restrict__ C, int dim, int code_margin, long long K, int QS, int n_chunks,
-            const uint32_t *__restrict__ tau, int cap, int *__restrict__ counts, u64 *__restrict__ list,
-            int *__restrict__ fallback) {
+               const uint32_t *__restrict__ tau, int cap, int *__restrict__ counts, u64 *__restrict__ list,
+               int *__restrict__ fallback) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
     const int chunk = blockIdx.x * 4 + w;
     if (chunk >= n_chunks || *fallback) return;
-    const int GQ = QS >> 3, g = lane & (GQ - 1);
+    const int GQ = QS >> 3, L = (32 / GQ) * GQ, g = lane % GQ;  // lane -> query-token group as in k_chunkmax16
+    if (lane >= L) return;
     const long long c0 = (long long)chunk * 1024;
     const int rows = (int)min(1024ll, K - c0);
     const uint4 *base = reinterpret_cast<const uint4 *>(ST16 + ((size_t)b * K + c0) * QS);
@@ -278,136 +296,102 @@ k_collect16_tc(const unsigned short *__restrict__ ST16, const float *__restrict_
     uint32_t t2[4], live[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        // thresholds lowered by the margin: an estimate-built code may sit up to code_margin/2 off its exact value
         uint32_t a = tau[(size_t)b * QS + 8 * g + 2 * e], c = tau[(size_t)b * QS + 8 * g + 2 * e + 1];
         if (a < 65536u) a = a > (uint32_t)code_margin ? a - (uint32_t)code_margin : 0u;
         if (c < 65536u) c = c > (uint32_t)code_margin ? c - (uint32_t)code_margin : 0u;
         t2[e] = min(a, 65535u) | (min(c, 65535u) << 16);
         live[e] = (a < 65536u ? 0xffffu : 0u) | (c < 65536u ? 0xffff0000u : 0u);
     }
-    for (int i0 = lane; i0 < total; i0 += 8 * 32) {
+    for (int i0 = lane; i0 < total; i0 += 8 * L) {
         uint4 v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (i0 + 32 * e < total) ? __ldg(base + i0 + 32 * e) : make_uint4(0, 0, 0, 0);
+        for (int e = 0; e < 8; ++e) v[e] = (i0 + L * e < total) ? __ldg(base + i0 + L * e) : make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const uint32_t hx = __vcmpgeu2(v[e].x, t2[0]) & live[0], hy = __vcmpgeu2(v[e].y, t2[1]) & live[1];
             const uint32_t hz = __vcmpgeu2(v[e].z, t2[2]) & live[2], hw = __vcmpgeu2(v[e].w, t2[3]) & live[3];
-            if ((hx | hy | hz | hw) == 0u || i0 + 32 * e >= total) continue;  // the common case
-            const long long c = c0 + (i0 + 32 * e) / GQ;
+            if ((hx | hy | hz | hw) == 0u || i0 + L * e >= total) continue;  // the common case
+            const long long c = c0 + (i0 + L * e) / GQ;
             const uint32_t hits[4] = {hx, hy, hz, hw};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 if (!((hits[j >> 1] >> (16 * (j & 1))) & 1u)) continue;
                 const int q = 8 * g + j;
                 const int slot = atomicAdd(&counts[(size_t)b * QS + q], 1);
-                if (slot < cap) {  // the exact selection key: pinned-order dot of the query token and the centroid
-                    const float *qrow = Q + (size_t)(q_off[b] + q) * dim, *crow = C + (size_t)c * dim;
-                    float s = 0.0f;
-                    for (int d = 0; d < dim; ++d) s = __fmaf_rn(qrow[d], crow[d], s);
+                if (slot < cap) {
+                    const float s = pinned_dot(Q + (size_t)(q_off[b] + q) * dim, C + (size_t)c * dim, dim);
                     list[((size_t)b * QS + q) * cap + slot] = ((u64)score_key_asc(s) << 32) | (uint32_t)(~(uint32_t)c);
-                }
-                else atomicOr(fallback, 1);
+                } else atomicOr(fallback, 1);
             }
         }
     }
 }
 
-// grid = B, 256 threads: list[b][0..n_list) = centroid ids of the non-empty selection keys (duplicates allowed)
-__global__ void k_sel_list(const u64 *__restrict__ sel, const int *__restrict__ q_off, int QS, int n, int cap,
-                           uint32_t *__restrict__ list, int *__restrict__ list_n) {
-    __shared__ int fill;
-    const int b = blockIdx.x, nq = q_off[b + 1] - q_off[b];
-    if (threadIdx.x == 0) fill = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < nq * n; i += blockDim.x) {
-        const u64 k = sel[(size_t)b * QS * n + i];
-        if (k != 0ull) {
-            const int pos = atomicAdd(&fill, 1);
-            if (pos < cap) list[(size_t)b * cap + pos] = (uint32_t)(~(uint32_t)k);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) list_n[b] = min(fill, cap);
-}
-
-// grid = (CTAs, B): one warp per listed doc, one bit per distinct code
+// the distinct selected centroids of a query, ascending: ulist[b][0..n_u).  grid = B, 256 threads, smem = P*12.
 __global__ void __launch_bounds__(256)
-k_mark_codes(const uint32_t *__restrict__ docs, long long stride, const int *__restrict__ n_docs,
-             const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off, uint32_t *__restrict__ bits,
-             long long W) {
-    const int b = blockIdx.y, lane = threadIdx.x & 31;
-    const int n = n_docs[b];
-    uint32_t *bm = bits + (size_t)b * W;
-    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
-        const uint32_t d = docs[(size_t)b * stride + i];
-        for (long long t = udoc_off[d] + lane; t < udoc_off[d + 1]; t += 32) {
-            const uint32_t c = ucodes[t];
-            atomicOr(&bm[c >> 5], 1u << (c & 31));
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_cells_tc(const u64 *__restrict__ sel, const float *__restrict__ ST, const int *__restrict__ q_off,
-        long long K, int QS, int n, int cells_cap, int has_thr, float thr, int batched,
-        long long slab, uint32_t *__restrict__ cells, int *__restrict__ n_cells,
-        const unsigned short *__restrict__ ST16, const float2 *__restrict__ qrange, int code_margin,
-        const float *__restrict__ Q, const float *__restrict__ C, int dim) {
+k_cells_unique(const u64 *__restrict__ sel, const int *__restrict__ q_off, int QS, int n, int cap,
+               uint32_t *__restrict__ ulist, int *__restrict__ n_u) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     const int nq = q_off[b + 1] - q_off[b];
     const int total = nq * n;
     const int P = next_pow2(max(total, 1));
-    u64 *s = reinterpret_cast<u64 *>(smem_raw);  // [P] sort buffer, then unique list
-    int *flags = reinterpret_cast<int *>(s + P);  // [P]
+    u64 *s = reinterpret_cast<u64 *>(smem_raw);  // [P]
     __shared__ int scan_tmp[33];
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
         u64 v = ~0ull;
         if (i < total) {
-            u64 k = sel[(size_t)b * QS * n + i];  // rows q < nq are the first nq*n entries
-            if (k != 0ull) v = (u64)(uint32_t)(~(uint32_t)k);  // centroid id
+            const u64 k = sel[(size_t)b * QS * n + i];  // rows q < nq are the first nq*n entries
+            if (k != 0ull) v = (u64)(uint32_t)(~(uint32_t)k);
         }
         s[i] = v;
     }
     __syncthreads();
     bitonic_sort_u64(s, P);
-    // unique
     int nu = 0;
     for (int base = 0; base < P; base += blockDim.x) {
-        int i = base + threadIdx.x;
-        int f = (i < P && s[i] != ~0ull && (i == 0 || s[i - 1] != s[i])) ? 1 : 0;
+        const int i = base + threadIdx.x;
+        const int f = (i < P && s[i] != ~0ull && (i == 0 || s[i - 1] != s[i])) ? 1 : 0;
         int tot;
-        int pos = block_exclusive_scan(f, scan_tmp, &tot);
-        u64 v = i < P ? s[i] : 0;
-        __syncthreads();
-        if (f) reinterpret_cast<uint32_t *>(flags)[nu + pos] = (uint32_t)v;  // stage ids in flags
+        const int pos = block_exclusive_scan(f, scan_tmp, &tot);
+        if (f && nu + pos < cap) ulist[(size_t)b * cap + nu + pos] = (uint32_t)s[i];
         nu += tot;
-        __syncthreads();
     }
-    // move unique ids to the front of s (as u32 in the low half), flags reused below
-    for (int i = threadIdx.x; i < nu; i += blockDim.x) s[i] = reinterpret_cast<uint32_t *>(flags)[i];
-    __syncthreads();
-    // threshold, one warp per unique centroid
+    if (threadIdx.x == 0) n_u[b] = min(nu, cap);
+}
+
+// the variant's threshold rule (k_cells, k_probe.cuh) on the exact rows of the selected centroids:
+// rows[b][u][QS] = S[.][ulist[b][u]].  The batched variant's slab-prefix scan ("did c enter token q's slab heap?")
+// ranks the earlier centroids of the slab on the 16-bit estimate table: with kv16 = the code of the exact value v,
+// an estimate code >= kv16 + code_margin is certainly not below v, one <= kv16 - code_margin certainly below,
+// anything between is settled by a pinned-order dot.  grid = B, 256 threads.
+__global__ void __launch_bounds__(256)
+k_cells_thr(const u64 *__restrict__ sel, const float *__restrict__ rows, const uint32_t *__restrict__ ulist,
+            const int *__restrict__ n_u, const int *__restrict__ q_off, long long K, int QS, int n, int cap, int has_thr,
+            float thr, int batched, long long slab, uint32_t *__restrict__ cells, int *__restrict__ n_cells,
+            const unsigned short *__restrict__ ST16, const float2 *__restrict__ qrange, int code_margin,
+            const float *__restrict__ Q, const float *__restrict__ C, int dim) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *flags = reinterpret_cast<int *>(smem_raw);  // [cap]
+    __shared__ int scan_tmp[33];
+    const int b = blockIdx.x;
+    const int nq = q_off[b + 1] - q_off[b];
+    const int nu = n_u[b];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const float *STb = ST + (size_t)b * K * QS;
     for (int u = w; u < nu; u += nwarps) {
-        const uint32_t c = (uint32_t)s[u];
+        const uint32_t c = ulist[(size_t)b * cap + u];
         int keep = 1;
         if (has_thr) {
-            const float *row = STb + (size_t)c * QS;
+            const float *row = rows + ((size_t)b * cap + u) * QS;
             if (!batched) {
                 uint32_t best = 0u;
                 for (int q = lane; q < nq; q += 32) best = max(best, score_key_asc(row[q]));
 #pragma unroll
                 for (int m = 16; m >= 1; m >>= 1) best = max(best, __shfl_xor_sync(PB_FULL, best, m));
                 // Iterator::max_by keeps the last maximum: all non-finite -> the last token's value
-                float mval = best ? key_to_score(best) : (nq > 0 ? row[nq - 1] : -INFINITY);
+                const float mval = best ? key_to_score(best) : (nq > 0 ? row[nq - 1] : -INFINITY);
                 keep = (mval >= thr);
             } else {
-                // m1 = best finite score among tokens that selected c (they entered their slab heap).
-                // Non-finite scores are not tracked here: with NaN/Inf centroid scores only the
-                // dense variant's threshold is reproduced exactly (DESIGN.md "Limits").
                 uint32_t best = 0u;
                 for (int q = lane; q < nq; q += 32) {
                     const u64 *sq = sel + ((size_t)b * QS + q) * n;
@@ -418,32 +402,25 @@ k_cells_tc(const u64 *__restrict__ sel, const float *__restrict__ ST, const int 
                 }
 #pragma unroll
                 for (int m = 16; m >= 1; m >>= 1) best = max(best, __shfl_xor_sync(PB_FULL, best, m));
-                float m1 = best ? key_to_score(best) : -INFINITY;
+                const float m1 = best ? key_to_score(best) : -INFINITY;
                 keep = (m1 >= thr);
                 if (!keep) {
                     // another token may have recorded a score >= thr for c while scanning its slab
                     const long long s0 = (long long)(c / slab) * slab;
+                    const float2 rg = qrange[b];
                     for (int q = 0; q < nq && !keep; ++q) {
                         const float v = row[q];
                         const uint32_t kv = score_key_asc(v);
                         if (!(kv != 0u && v >= thr)) continue;  // finite and over the threshold
-                        // entered iff fewer than n earlier slab entries are "not worse" than v
-                        // only the rows of selected centroids are exact in ST here: rank the slab prefix on the 16-bit
-                        // table, and settle the codes within the margin of v's own code by an exact pinned-order dot
-                        const float2 rg = qrange[b];
                         const int kv16 = (int)fminf(fmaxf(floorf(__fmaf_rn(v, rg.y, rg.x)), 0.0f), 65535.0f);
                         const unsigned short *col16 = ST16 + (size_t)b * K * QS + q;
                         const float *qrow = Q + (size_t)(q_off[b] + q) * dim;
                         int cnt = 0;
                         for (long long c2 = s0 + lane; c2 < (long long)c; c2 += 32) {
                             const int cd2 = (int)col16[(size_t)c2 * QS];
-                            if (cd2 > kv16 + code_margin) ++cnt;
-                            else if (cd2 + code_margin >= kv16) {
-                                const float *crow = C + (size_t)c2 * dim;
-                                float s2 = 0.0f;
-                                for (int j = 0; j < dim; ++j) s2 = __fmaf_rn(qrow[j], crow[j], s2);
-                                cnt += (score_key_asc(s2) >= kv) ? 1 : 0;
-                            }
+                            if (cd2 >= kv16 + code_margin) ++cnt;
+                            else if (cd2 + code_margin > kv16)
+                                cnt += (score_key_asc(pinned_dot(qrow, C + (size_t)c2 * dim, dim)) >= kv) ? 1 : 0;
                         }
 #pragma unroll
                         for (int m = 16; m >= 1; m >>= 1) cnt += __shfl_xor_sync(PB_FULL, cnt, m);
@@ -455,15 +432,108 @@ k_cells_tc(const u64 *__restrict__ sel, const float *__restrict__ ST, const int 
         if (lane == 0) flags[u] = keep;
     }
     __syncthreads();
-    // ordered compaction
     int outn = 0;
     for (int base = 0; base < nu; base += blockDim.x) {
-        int i = base + threadIdx.x;
-        int f = (i < nu) ? flags[i] : 0;
+        const int i = base + threadIdx.x;
+        const int f = (i < nu) ? flags[i] : 0;
         int tot;
-        int pos = block_exclusive_scan(f, scan_tmp, &tot);
-        if (f && outn + pos < cells_cap) cells[(size_t)b * cells_cap + outn + pos] = (uint32_t)s[i];
+        const int pos = block_exclusive_scan(f, scan_tmp, &tot);
+        if (f && outn + pos < cap) cells[(size_t)b * cap + outn + pos] = ulist[(size_t)b * cap + i];
         outn += tot;
     }
-    if (threadIdx.x == 0) n_cells[b] = min(outn, cells_cap);
+    if (threadIdx.x == 0) n_cells[b] = min(outn, cap);
+}
+
+// ------------------------------------------------------------------------------------------
+// a5 second pass on the tensor-core table: the EXACT approximate score (search.rs:305-324) of the docs that can
+// still make the cut, without a dense fp32 S.  For a doc and a query token q, m_q = the largest estimate code over
+// the doc's distinct codes; the code c* that attains the exact maximum satisfies code(c*) >= m_q - (2E + 1)
+// (e(c*) >= e(c^) for the estimate's argmax c^, so t(c*) >= t(c^) - 2 delta), so the exact per-token maximum is the
+// maximum of the pinned-order dots over the (typically one or two) codes within `code_margin` of m_q.
+// One warp per doc: pass A lane = query token gathers the 16-bit rows for m_q; pass B finds the (q, code) pairs
+// within the margin and queues them in a per-warp list, which the lanes then work off as independent dots
+// (one 128-bit-load FMA chain per lane).  Emits what k_approx emits: approx[b][i] and the cut key.
+// grid = (CTAs, B), 256 threads.
+// ------------------------------------------------------------------------------------------
+#define PB_RECHECK_LIST 96
+__global__ void __launch_bounds__(256)
+k_approx_recheck(const unsigned short *__restrict__ ST16, const float *__restrict__ Q, const int *__restrict__ q_off,
+                 const float *__restrict__ C, int dim, long long K, int QS, const uint32_t *__restrict__ ucodes,
+                 const long long *__restrict__ udoc_off, const uint32_t *__restrict__ cand, long long cand_cap,
+                 const int *__restrict__ n_cand, int code_margin, float *__restrict__ approx, u64 *__restrict__ keys,
+                 unsigned long long *__restrict__ tok_counter, uint32_t doc_id_base) {
+    __shared__ uint32_t pair_s[8][PB_RECHECK_LIST + 32];  // queued pairs of a warp: centroid ids ...
+    __shared__ uint32_t pairq_s[8][PB_RECHECK_LIST + 32];  // ... and their query tokens
+    __shared__ uint32_t qmax_s[8][32];
+    const int b = blockIdx.y;
+    const int r0 = q_off[b], nq = q_off[b + 1] - r0;
+    const int n = n_cand[b];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    const unsigned short *STb = ST16 + (size_t)b * K * QS;
+    const unsigned rowb = (unsigned)QS * 2u;
+    uint32_t *pc = pair_s[w], *pq = pairq_s[w], *qm = qmax_s[w];
+    unsigned long long my_tokens = 0;
+    for (int i = blockIdx.x * (blockDim.x >> 5) + w; i < n; i += warps_per_grid) {
+        const uint32_t d = cand[(size_t)b * cand_cap + i];
+        const long long t0 = udoc_off[d], t1 = udoc_off[d + 1];
+        my_tokens += (unsigned long long)(t1 - t0);
+        float score = 0.0f;
+        for (int qc = 0; qc < nq; qc += 32) {
+            const int q = qc + lane;
+            const bool live = q < nq;
+            const char *col = reinterpret_cast<const char *>(STb + (live ? q : 0));
+            // pass A: the largest estimate code per query token
+            const uint32_t m = gather_max<GatherU16>(col, rowb, ucodes, t0, t1);
+            const uint32_t lo = m > (uint32_t)code_margin ? m - (uint32_t)code_margin : 0u;
+            qm[lane] = 0u;  // exact maxima as score keys (0 = none: a doc without codes)
+            __syncwarp();
+            // pass B: queue the (code, q) pairs within the margin; the lanes work the queue off as independent dots
+            // whenever another step could overflow it, and once at the end
+            int cnt = 0;
+            for (long long t = t0; t < t1; t += 8) {
+                const uint4 ca = *reinterpret_cast<const uint4 *>(ucodes + t);
+                const uint4 cb = *reinterpret_cast<const uint4 *>(ucodes + t + 4);
+                const uint32_t cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+                uint32_t v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const unsigned short *>(col + (size_t)cs[e] * rowb);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    // lists are padded to 8 with the last code: a code equal to its predecessor is a repeat
+                    const bool hit = live && v[e] >= lo && (e == 0 || cs[e] != cs[e - 1]);
+                    const unsigned bal = __ballot_sync(PB_FULL, hit);
+                    if (hit) {
+                        const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+                        pc[pos] = cs[e];
+                        pq[pos] = (uint32_t)q;
+                    }
+                    cnt += __popc(bal);
+                    if (cnt > PB_RECHECK_LIST || (t + 8 >= t1 && e == 7 && cnt > 0)) {
+                        __syncwarp();
+                        for (int j = lane; j < cnt; j += 32) {
+                            const float sdot = pinned_dot(Q + (size_t)(r0 + pq[j]) * dim, C + (size_t)pc[j] * dim, dim);
+                            atomicMax(&qm[pq[j] - qc], score_key_asc(sdot));
+                        }
+                        __syncwarp();
+                        cnt = 0;
+                    }
+                }
+            }
+            __syncwarp();
+            // score += max for q ascending, skipping rows without a finite maximum (search.rs:318-320)
+            const uint32_t mk = qm[lane];
+            const int lim = min(32, nq - qc);
+            for (int qq = 0; qq < lim; ++qq) {
+                const uint32_t kk = __shfl_sync(PB_FULL, mk, qq);
+                if (kk) score = __fadd_rn(score, key_to_score(kk));
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            approx[(size_t)b * cand_cap + i] = score;
+            keys[(size_t)b * cand_cap + i] = ((u64)(~score_key_asc(score)) << 32) | (d + doc_id_base);
+        }
+    }
+    if (lane == 0 && my_tokens) atomicAdd(tok_counter, my_tokens);
 }

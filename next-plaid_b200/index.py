@@ -66,7 +66,8 @@ class _Work(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_queries", "n_query_tokens", "n_cells", "n_candidates",
                                          "n_candidate_tokens", "n_exact_docs", "n_exact_tokens",
                                          "n_filter_docs", "n_filter_tokens", "k1_tc_max_code_diff",
-                                         "k1_rows_mismatch")]
+                                         "k1_rows_mismatch", "n_probe_threshold", "n_probe_list", "n_k1_tc",
+                                         "n_recheck_docs", "n_k1_tc_redo")]
 
 
 EXPORTS = [

@@ -401,3 +401,22 @@ def test_probe_threshold_path_and_its_fallbacks(oracle, npb, corpus, monkeypatch
                 assert np.array_equal(x.scores, w.scores) and np.array_equal(y.scores, w.scores), kw
     plain.close()
 
+
+
+@pytest.mark.parametrize("nq", [33, 48, 64])
+def test_long_queries_keep_the_fast_paths(oracle, npb, corpus, nq):
+    # default_query_length() = 48 in the reference's ONNX encoder (next-plaid-onnx/src/lib.rs:628-630): the tensor-core
+    # filter (N = 64 UMMA) and the threshold-first probe (QS/8 = 5, 6, 8 lanes per row) must stay engaged past 32 tokens
+    docs, ix, qs, src, gpu = corpus
+    ql, _ = oracle.synthetic_queries(docs, 6, nq=nq, seed=100 + nq)
+    for kw in (dict(top_k=5, n_full_scores=2048), dict(top_k=20, n_full_scores=1024, centroid_batch_size=128),
+               dict(top_k=10, n_full_scores=512, n_ivf_probe=16, centroid_score_threshold=None)):
+        pg, po = _params(npb, oracle, **kw)
+        res = gpu.search_batch(ql, pg)
+        work = gpu.last_work_counters()
+        assert work["n_filter_docs"] > 0 and work["n_exact_docs"] < work["n_filter_docs"], (kw, work)
+        assert work["n_probe_list"] == 0 and work["n_probe_threshold"] + work["n_k1_tc"] > 0, (kw, work)
+        for q, r in zip(ql, res):
+            w = oracle.search_one(ix, q, po)
+            assert r.passage_ids.tolist() == w.passage_ids.tolist(), (kw, nq)
+            assert np.array_equal(r.scores, w.scores), (kw, nq)

@@ -5,7 +5,7 @@
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/first_gpu_call.sh'
 set -u
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+timeout 600 python -m pytest tests -q -m gpu 2>&1 | tail -25
 timeout 200 python -m pytest tests/test_loader_cpu.py -x -q 2>&1 | tail -3
 timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -1
 timeout 250 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
@@ -15,8 +15,8 @@ d = json.load(open("gpurun_out/bench_n1.json"))
 print({k: d[k] for k in ("value", "ms_per_step", "recall_at_k", "parity")},
       {k: round(v, 3) for k, v in d["stage_ms_per_step"].items()}, d["e2e"]["value"], d["clocks"])
 PY
-timeout 600 python tools/variant_sweep.py --steps 10 --only "FFMA2 in k_exact,cg,K1" 2>&1 | tee gpurun_out/variant_sweep.txt
+timeout 600 python tools/variant_sweep.py --steps 10 --only "default,exact,E=2,FFMA2,cg" 2>&1 | tee gpurun_out/variant_sweep.txt
 timeout 200 ncu --set full --import-source on --clock-control none \
-    -k "regex:^k_(centroid_scores|scores16_tc|exact_rows)$" -s 3 -c 3 -o gpurun_out/ncu_k1 \
-    env PB_K1_TC_DIAG=1 python bench.py --steps 3 --warmup 2 --no-cpu --recall-queries 0 > gpurun_out/ncu_k1.log 2>&1
+    -k "regex:^k_(scores16_tc|approx_recheck|approx16)$" -s 3 -c 3 -o gpurun_out/ncu_k1 \
+    python bench.py --steps 3 --warmup 2 --no-cpu --recall-queries 0 > gpurun_out/ncu_k1.log 2>&1
 tail -c 300 gpurun_out/ncu_k1.log

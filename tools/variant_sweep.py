@@ -9,17 +9,15 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = [
-    ("default", {}),
-    ("scalar FFMA centroid scores", {"PB_FMA2": "0"}),
+    ("default (a2 on tensor cores)", {}),
+    ("exact fp32 a2 (PB_K1_TC=0)", {"PB_K1_TC": "0"}),
+    ("exact a2 + code-diff diagnostic", {"PB_K1_TC_DIAG": "1"}),
+    ("tensor cores, E=2", {"PB_K1_TC_E": "2"}),
     ("FFMA2 in k_exact", {"PB_FMA2_EXACT": "1"}),
     ("ld.global.cg gathers", {"PB_APPROX_CG": "1"}),
     ("approx grid x4", {"PB_APPROX_GRID": "4"}),
     ("filter off", {"PB_FAST_EXACT": "0"}),
-    ("FFMA2 in k_exact, filter off", {"PB_FMA2_EXACT": "1", "PB_FAST_EXACT": "0"}),
-    ("list-scan probe", {"PB_PROBE16": "0"}),
-    ("K1 tensor-core twin (diagnostic)", {"PB_K1_TC_DIAG": "1"}),
-    ("K1 on tensor cores (stage 2)", {"PB_K1_TC": "1"}),
-    ("K1 on tensor cores, margin 6", {"PB_K1_TC": "1", "PB_K1_TC_E": "6"}),
+    ("list-scan probe (exact a2)", {"PB_PROBE16": "0", "PB_K1_TC": "0"}),
 ]
 
 
@@ -52,7 +50,8 @@ def main():
               ("centroid_scores", "probe", "approx", "exact")) +
               f"  parity {par.get('ids_identical')}/{par.get('queries')} dmax={par.get('max_abs_score_diff')}"
               f"  k1_code_diff={d.get('work_per_step', {}).get('k1_tc_max_code_diff')}"
-              f"  k1_rows_mismatch={d.get('work_per_step', {}).get('k1_rows_mismatch')}")
+              f"  tc/redo={d.get('work_per_step', {}).get('n_k1_tc')}/{d.get('work_per_step', {}).get('n_k1_tc_redo')}"
+              f"  recheck_docs={d.get('work_per_step', {}).get('n_recheck_docs')}")
 
 
 if __name__ == "__main__":
