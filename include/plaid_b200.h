@@ -73,7 +73,14 @@ typedef struct pb_index_desc {
     int32_t device;                /* CUDA ordinal */
     int32_t memory_space;          /* PB_MEM_HOST | PB_MEM_DEVICE */
     int64_t doc_id_base;           /* global id of local doc 0 (doc-sharded deployment), else 0 */
+    int32_t flags;                 /* PB_OPEN_* below, 0 = none */
 } pb_index_desc;
+/* pb_index_desc.flags.
+ * ADOPT_RESIDUALS: memory_space must be PB_MEM_DEVICE; the packed residuals (the largest array: 19 GB per million
+ *   300-token docs at 4 bits) are used in place instead of copied -- the caller keeps them alive until pb_index_close.
+ * ivf == NULL && ivf_lengths == NULL (no flag needed): the inverted file is built on the device from the codes,
+ *   exactly as index.rs:850-873 does (per centroid the ascending unique doc ids); pb_index_export_ivf returns it. */
+enum { PB_OPEN_ADOPT_RESIDUALS = 1 };
 
 /* search.rs:27-69 SearchParameters.  batch_size is accepted and ignored, as in the reference
  * (it is never read there). */
@@ -102,6 +109,11 @@ PB_API pb_status pb_index_open(const pb_index_desc *desc, pb_index **out);
 
 /* Drop for the handle. */
 PB_API void pb_index_close(pb_index *ix);
+
+/* The inverted file of the handle in the reference's dtypes (ivf.npy <i8, ivf_lengths.npy <i4; index.rs:501-508):
+ * what create_index writes after building it (index.rs:850-873).  out_ivf may be NULL to query the total length
+ * (returned in *out_total); out_lengths [K] may be NULL. */
+PB_API pb_status pb_index_export_ivf(pb_index *ix, int64_t *out_ivf, int32_t *out_lengths, int64_t *out_total);
 
 /* accessors, index.rs:1290-1312 */
 PB_API int64_t pb_index_num_documents(const pb_index *ix);
@@ -216,6 +228,19 @@ PB_API void pb_set_profiling(pb_index *ix, int32_t enabled);
 /* Milliseconds and kernel launches per stage, summed over the sub-batches of the calling thread's
  * last pb_search_batch.  out_ms / out_launches: [PB_STAGE_COUNT]. */
 PB_API pb_status pb_last_stage_stats(pb_index *ix, float *out_ms, int32_t *out_launches);
+/* Device time of the calling thread's last search call, one CUDA-event pair on the library's stream around the whole
+ * call (all sub-batches, their exchanges and the gaps between them); needs pb_set_profiling(ix, 1). */
+PB_API pb_status pb_last_call_ms(pb_index *ix, float *out_ms);
+/* Device time of the main kernel of each stage alone (CUDA events around that one launch, summed over sub-batches):
+ * the `achieved` side of bench.py's roofline blocks. */
+enum {
+    PB_KERNEL_SCORES = 0,   /* k_scores16_tc (or k_centroid_scores on the exact path) */
+    PB_KERNEL_APPROX16 = 1, /* k_approx16, the first approximate pass */
+    PB_KERNEL_FILTER = 2,   /* k_exact_tc, the tcgen05 MaxSim estimate of every kept doc */
+    PB_KERNEL_EXACT = 3,    /* k_exact, fused decompress + MaxSim of the survivors */
+    PB_KERNEL_COUNT = 4
+};
+PB_API pb_status pb_last_kernel_ms(pb_index *ix, float *out_ms /* [PB_KERNEL_COUNT] */);
 /* Work counters of the calling thread's last search: candidates scored, doc tokens gathered by the
  * approximate stage, docs / tokens exact-scored. */
 typedef struct pb_work_counters {

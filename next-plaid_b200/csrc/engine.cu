@@ -5,6 +5,9 @@
 #include "engine_internal.h"
 #include "kernels.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -124,6 +127,19 @@ pb_status pb_fail(pb_status s, const char *fmt, ...) {
         if (s_ != PB_OK) return s_;                                                                \
     } while (0)
 
+// CUDA-event pair around the main kernel of a stage (profiling mode only); read after the sub-batch's synchronize
+#define KEV_BEGIN(k)                                                                               \
+    do {                                                                                           \
+        if (ix->profiling) CK(cudaEventRecord(ws.kev[2 * (k)], ws.stream));                        \
+    } while (0)
+#define KEV_END(k)                                                                                 \
+    do {                                                                                           \
+        if (ix->profiling) {                                                                       \
+            CK(cudaEventRecord(ws.kev[2 * (k) + 1], ws.stream));                                   \
+            g_stats.kernel_seen[k] = true;                                                         \
+        }                                                                                          \
+    } while (0)
+
 extern "C" const char *pb_last_error(void) { return g_err.c_str(); }
 extern "C" const char *pb_version(void) { return "plaid_b200 0.1 (sm_100a)"; }
 
@@ -161,9 +177,17 @@ struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
     bool zero_on_grow = false;
+    bool owned = true;
+    void adopt(void *ptr, size_t bytes) {  // caller-owned device memory, used in place
+        if (p && owned) cudaFree(p);
+        p = ptr;
+        cap = bytes;
+        owned = false;
+    }
     pb_status ensure(size_t bytes) {
         if (bytes <= cap) return PB_OK;
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
+        owned = true;
         p = nullptr;
         cap = 0;
         size_t want = bytes + (bytes >> 3) + 256;
@@ -181,7 +205,7 @@ struct DevBuf {
     }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
     ~DevBuf() {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
     }
 };
 
@@ -211,6 +235,8 @@ struct HostBuf {  // pinned
 struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[PB_STAGE_COUNT + 1] = {};
+    cudaEvent_t kev[2 * PB_KERNEL_COUNT] = {};  // begin / end around the main kernel of a stage
+    cudaEvent_t call_ev[2] = {};                // around a whole search call
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2, cand3, ncand3, ub, theta, rel, cellbits,
         gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc;
@@ -218,6 +244,8 @@ struct Workspace {
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (auto &e : ev) CK(cudaEventCreate(&e));
+        for (auto &e : kev) CK(cudaEventCreate(&e));
+        for (auto &e : call_ev) CK(cudaEventCreate(&e));
         bitmap.zero_on_grow = true;
         maxkey.zero_on_grow = true;
         subset_bits.zero_on_grow = true;
@@ -228,12 +256,19 @@ struct Workspace {
     ~Workspace() {
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto &e : kev)
+            if (e) cudaEventDestroy(e);
+        for (auto &e : call_ev)
+            if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 };
 
 struct Stats {
     float ms[PB_STAGE_COUNT] = {};
+    float kernel_ms[PB_KERNEL_COUNT] = {};
+    bool kernel_seen[PB_KERNEL_COUNT] = {};
+    float call_ms = 0.f;
     int launches[PB_STAGE_COUNT] = {};
     pb_work_counters work = {};
 };
@@ -247,11 +282,11 @@ struct pb_index {
     int sm_count = 148;
     DevBuf centroids, w_rev, codes, residuals, doc_off, ivf, ivf_off, ucodes, udoc_off;
     long long n_ucodes = 0;
+    bool build_ivf = false;    // no inverted file was given: built from the codes at finalize (index.rs:850-873)
     float cmax = 1.0f;         // largest centroid L2 norm (range of the 16-bit score table)
     bool fast_approx = true;   // two-pass approximate stage (exact cut either way)
     bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
                                // the cut sits well above the background score level
-    bool fma2 = true;          // FFMA2 (fma.rn.f32x2) k_centroid_scores; PB_FMA2=0 selects the scalar-FFMA twin (same bits)
     bool k1_tc = true;         // a2 on the tensor cores (k_scores16_tc) with its certified consumers: the default;
                                // PB_K1_TC=0 keeps every sub-batch on the exact fp32 kernel (the device-gated fallback)
     int k1_margin = 1;         // E: code units an estimate-built 16-bit code may differ from the exact one (PB_K1_TC_E widens it)
@@ -268,7 +303,7 @@ struct pb_index {
     float wmax = 0.0f;         // largest residual norm |w| over the index (same)
     DevBuf centroids_f16;      // [K][dim] fp16 copy for the filter
     bool profiling = false;
-    size_t st_budget = (size_t)4 << 30;
+    size_t st_budget = (size_t)8 << 30;  // workspace budget of one search call (PB_WS_BUDGET_MB)
     ncclComm_t comm = nullptr;  // doc-sharded deployment: one rank per GPU
     pb_shard_group *group = nullptr;  // or one host thread per shard inside this process (pb_index_group_join)
     int rank = 0, world = 1;
@@ -378,8 +413,12 @@ pb_status pb_index_upload_tokens(pb_index *ix, long long tok_off, const int64_t 
     if (n == 0) return PB_OK;
     if (tok_off < 0 || tok_off + n > ix->N) return pb_fail(PB_ERR_INVALID, "token range [%lld,+%lld) outside the index", tok_off, n);
     CK(cudaSetDevice(ix->device));
-    CK(cudaMemcpy(ix->residuals.as<uint8_t>() + (size_t)tok_off * ix->packed, residuals, (size_t)n * ix->packed,
-                  space == PB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    if (!ix->residuals.owned) {  // PB_OPEN_ADOPT_RESIDUALS: the caller's array is the index
+        if (tok_off != 0 || n != ix->N || residuals != ix->residuals.as<uint8_t>())
+            return pb_fail(PB_ERR_INVALID, "adopted residuals cover the whole index");
+    } else
+        CK(cudaMemcpy(ix->residuals.as<uint8_t>() + (size_t)tok_off * ix->packed, residuals, (size_t)n * ix->packed,
+                      space == PB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
     return upload_narrow(ix->codes, tok_off, codes, n, ix->K, space, "codes");
 }
 
@@ -398,8 +437,10 @@ pb_status pb_index_open_begin(const pb_index_desc *d, pb_index **out) {
         return pb_fail(PB_ERR_UNSUPPORTED, "K and D must be below 2^32-1 per shard");
     if (d->doc_id_base < 0 || d->doc_id_base + d->num_documents >= (1ll << 32) - 1)
         return pb_fail(PB_ERR_UNSUPPORTED, "global doc ids must stay below 2^32-1");
-    if (!d->centroids || !d->bucket_weights || (!d->doc_lengths && d->num_documents) || !d->ivf_lengths)
+    if (!d->centroids || !d->bucket_weights || (!d->doc_lengths && d->num_documents) || (!d->ivf_lengths && d->ivf))
         return pb_fail(PB_ERR_INVALID, "null index array");
+    if ((d->flags & PB_OPEN_ADOPT_RESIDUALS) && (d->memory_space != PB_MEM_DEVICE || !d->residuals))
+        return pb_fail(PB_ERR_INVALID, "PB_OPEN_ADOPT_RESIDUALS needs device-resident residuals");
     CKS(check_device(d->device));
     std::unique_ptr<pb_index> ix(new pb_index());
     ix->device = d->device;
@@ -413,10 +454,11 @@ pb_status pb_index_open_begin(const pb_index_desc *d, pb_index **out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, d->device));
     ix->sm_count = prop.multiProcessorCount;
-    if (const char *e = getenv("PB_ST_BUDGET_MB")) {
-        long v = atol(e);
-        if (v > 0) ix->st_budget = (size_t)v << 20;
-    }
+    for (const char *name : {"PB_ST_BUDGET_MB", "PB_WS_BUDGET_MB"})
+        if (const char *e = getenv(name)) {
+            long v = atol(e);
+            if (v > 0) ix->st_budget = (size_t)v << 20;
+        }
     const int sp = d->memory_space;
     // doc offsets (index.rs:1107-1110)
     std::vector<int64_t> dl;
@@ -432,17 +474,20 @@ pb_status pb_index_open_begin(const pb_index_desc *d, pb_index **out) {
         return pb_fail(PB_ERR_INVALID, "sum(doc_lengths)=%lld != num_embeddings=%lld", doff[ix->D], ix->N);
     ix->max_doclen = maxlen;
     CKS(upload(ix->doc_off, doff.data(), doff.size() * 8, PB_MEM_HOST));
-    // ivf offsets (index.rs:1089-1094)
-    std::vector<int32_t> il;
-    CKS(fetch_host(il, d->ivf_lengths, (size_t)ix->K, sp));
-    std::vector<long long> ioff((size_t)ix->K + 1, 0);
-    for (long long i = 0; i < ix->K; ++i) {
-        if (il[i] < 0) return pb_fail(PB_ERR_INVALID, "ivf_lengths[%lld] < 0", i);
-        ioff[i + 1] = ioff[i] + il[i];
+    // ivf offsets (index.rs:1089-1094); without an inverted file it is built from the codes in pb_index_finalize
+    ix->build_ivf = d->ivf_lengths == nullptr;
+    if (!ix->build_ivf) {
+        std::vector<int32_t> il;
+        CKS(fetch_host(il, d->ivf_lengths, (size_t)ix->K, sp));
+        std::vector<long long> ioff((size_t)ix->K + 1, 0);
+        for (long long i = 0; i < ix->K; ++i) {
+            if (il[i] < 0) return pb_fail(PB_ERR_INVALID, "ivf_lengths[%lld] < 0", i);
+            ioff[i + 1] = ioff[i] + il[i];
+        }
+        ix->ivf_len = ioff[ix->K];
+        if (ix->ivf_len && !d->ivf) return pb_fail(PB_ERR_INVALID, "null ivf");
+        CKS(upload(ix->ivf_off, ioff.data(), ioff.size() * 8, PB_MEM_HOST));
     }
-    ix->ivf_len = ioff[ix->K];
-    if (ix->ivf_len && !d->ivf) return pb_fail(PB_ERR_INVALID, "null ivf");
-    CKS(upload(ix->ivf_off, ioff.data(), ioff.size() * 8, PB_MEM_HOST));
     // bucket weights with the packer's bit reversal folded in (codec.rs:168-214, :389-395)
     std::vector<float> w;
     CKS(fetch_host(w, d->bucket_weights, (size_t)1 << ix->nbits, sp));
@@ -450,11 +495,52 @@ pb_status pb_index_open_begin(const pb_index_desc *d, pb_index **out) {
     for (unsigned f = 0; f < (1u << ix->nbits); ++f) wrev[f] = w[bitrev_n(f, ix->nbits)];
     CKS(upload(ix->w_rev, wrev.data(), 256 * sizeof(float), PB_MEM_HOST));
     CKS(upload(ix->centroids, d->centroids, (size_t)ix->K * ix->dim * sizeof(float), sp));
-    CKS(ix->residuals.ensure(std::max<size_t>((size_t)ix->N * ix->packed, 16)));
+    if (d->flags & PB_OPEN_ADOPT_RESIDUALS)
+        ix->residuals.adopt(const_cast<uint8_t *>(d->residuals), (size_t)ix->N * ix->packed);
+    else CKS(ix->residuals.ensure(std::max<size_t>((size_t)ix->N * ix->packed, 16)));
     CKS(ix->codes.ensure(std::max<size_t>((size_t)ix->N * 4, 16)));
-    CKS(ix->ivf.ensure(std::max<size_t>((size_t)ix->ivf_len * 4, 16)));
-    CKS(upload_narrow(ix->ivf, 0, d->ivf, ix->ivf_len, std::max<long long>(ix->D, 1), sp, "ivf"));
+    if (!ix->build_ivf) {
+        CKS(ix->ivf.ensure(std::max<size_t>((size_t)ix->ivf_len * 4, 16)));
+        CKS(upload_narrow(ix->ivf, 0, d->ivf, ix->ivf_len, std::max<long long>(ix->D, 1), sp, "ivf"));
+    }
     *out = ix.release();
+    return PB_OK;
+}
+
+// The inverted file of an index opened without one (index.rs:850-873), from the per-doc distinct code lists.
+static pb_status build_ivf_on_device(pb_index *ix) {
+    CKS(ix->ivf_off.ensure((size_t)(ix->K + 1) * 8));
+    const long long cap = std::max<long long>(ix->n_ucodes, 1);
+    DevBuf ka, kb, cnt, tmp;
+    CKS(ka.ensure((size_t)cap * 8));
+    CKS(kb.ensure((size_t)cap * 8));
+    CKS(cnt.ensure(16));
+    CK(cudaMemset(cnt.p, 0, 16));
+    if (ix->D > 0) {
+        k_ivf_pairs<<<ix->sm_count * 8, 256>>>(ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(), ix->D, ka.as<u64>(),
+                                               cnt.as<unsigned long long>());
+        CK(cudaGetLastError());
+    }
+    unsigned long long m = 0;
+    CK(cudaMemcpy(&m, cnt.p, 8, cudaMemcpyDeviceToHost));
+    if (m > (1ull << 31) - 2) return pb_fail(PB_ERR_UNSUPPORTED, "more than 2^31 (centroid, doc) pairs per shard");
+    int kbits = 1;
+    while ((1ll << kbits) < ix->K) ++kbits;
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, ka.as<u64>(), kb.as<u64>(), (int)m, 0, 32 + kbits));
+    size_t tb2 = 0;
+    CK(cub::DeviceSelect::Unique(nullptr, tb2, kb.as<u64>(), ka.as<u64>(), cnt.as<int>() + 2, (int)m));
+    CKS(tmp.ensure(std::max(tb, tb2) + 16));
+    CK(cub::DeviceRadixSort::SortKeys(tmp.p, tb, ka.as<u64>(), kb.as<u64>(), (int)m, 0, 32 + kbits));
+    CK(cub::DeviceSelect::Unique(tmp.p, tb2, kb.as<u64>(), ka.as<u64>(), cnt.as<int>() + 2, (int)m));
+    int m2 = 0;
+    CK(cudaMemcpy(&m2, cnt.as<int>() + 2, 4, cudaMemcpyDeviceToHost));
+    ix->ivf_len = m2;
+    CKS(ix->ivf.ensure(std::max<size_t>((size_t)m2 * 4, 16)));
+    k_ivf_from_keys<<<ix->sm_count * 8, 256>>>(ka.as<u64>(), m2, ix->ivf.as<uint32_t>());
+    k_ivf_offsets<<<(unsigned)((ix->K + 256) / 256), 256>>>(ka.as<u64>(), m2, ix->K, ix->ivf_off.as<long long>());
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
     return PB_OK;
 }
 
@@ -487,7 +573,6 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_CASCADE")) ix->cascade = atoi(e) != 0;
         if (const char *e = getenv("PB_FAST_EXACT")) ix->fast_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
-        if (const char *e = getenv("PB_FMA2")) ix->fma2 = atoi(e) != 0;
         if (const char *e = getenv("PB_FMA2_EXACT")) ix->fma2_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC_DIAG")) ix->k1_diag = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC")) ix->k1_tc = atoi(e) != 0;
@@ -539,6 +624,24 @@ pb_status pb_index_finalize(pb_index *ix) {
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
     }
+    if (ix->build_ivf) CKS(build_ivf_on_device(ix));
+    return PB_OK;
+}
+
+extern "C" pb_status pb_index_export_ivf(pb_index *ix, int64_t *out_ivf, int32_t *out_lengths, int64_t *out_total) {
+    if (!ix) return pb_fail(PB_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(ix->device));
+    if (out_total) *out_total = ix->ivf_len;
+    if (!out_ivf && !out_lengths) return PB_OK;
+    DevBuf di, dl;
+    if (out_ivf) CKS(di.ensure(std::max<size_t>((size_t)ix->ivf_len * 8, 16)));
+    if (out_lengths) CKS(dl.ensure(std::max<size_t>((size_t)ix->K * 4, 16)));
+    k_ivf_export<<<ix->sm_count * 8, 256>>>(ix->ivf.as<uint32_t>(), ix->ivf_off.as<long long>(), ix->ivf_len, ix->K,
+                                           ix->doc_id_base, out_ivf ? di.as<long long>() : nullptr,
+                                           out_lengths ? dl.as<int>() : nullptr);
+    CK(cudaGetLastError());
+    if (out_ivf && ix->ivf_len) CK(cudaMemcpy(out_ivf, di.p, (size_t)ix->ivf_len * 8, cudaMemcpyDeviceToHost));
+    if (out_lengths) CK(cudaMemcpy(out_lengths, dl.p, (size_t)ix->K * 4, cudaMemcpyDeviceToHost));
     return PB_OK;
 }
 
@@ -602,6 +705,16 @@ extern "C" pb_status pb_last_stage_stats(pb_index *, float *out_ms, int32_t *out
     }
     return PB_OK;
 }
+extern "C" pb_status pb_last_call_ms(pb_index *, float *out_ms) {
+    if (!out_ms) return pb_fail(PB_ERR_INVALID, "null argument");
+    *out_ms = g_stats.call_ms;
+    return PB_OK;
+}
+extern "C" pb_status pb_last_kernel_ms(pb_index *, float *out_ms) {
+    if (!out_ms) return pb_fail(PB_ERR_INVALID, "null argument");
+    for (int i = 0; i < PB_KERNEL_COUNT; ++i) out_ms[i] = g_stats.kernel_ms[i];
+    return PB_OK;
+}
 extern "C" pb_status pb_last_work_counters(pb_index *, pb_work_counters *out) {
     if (!out) return pb_fail(PB_ERR_INVALID, "null argument");
     *out = g_stats.work;
@@ -644,9 +757,11 @@ static pb_status launch_k1_table(pb_index *ix, Workspace &ws, int B, int QS, uns
     {                                                                                                                  \
         auto kern = k_scores16_tc<DV>;                                                                                 \
         CKS(set_smem(kern, sm));                                                                                       \
+        KEV_BEGIN(PB_KERNEL_SCORES);                                                                                   \
         kern<<<tiles, 192, sm, ws.stream>>>(ix->cent_h16t.as<__half>(), ix->cent_l16t.as<__half>(), ix->K,             \
                                             ws.Qh16t.as<__half>(), ws.Ql16t.as<__half>(), n_groups, B, QS,             \
                                             ws.qoff.as<int>(), ws.qrange_tc.as<float2>(), table, flags);               \
+        KEV_END(PB_KERNEL_SCORES);                                                                                     \
     }
     switch (ix->dim) {
         case 64: PB_K1_LAUNCH(64) break;
@@ -744,35 +859,23 @@ static pb_status launch_centroid_scores_exact(pb_index *ix, Workspace &ws, int B
     const int tiles = (int)((ix->K + PB_TOK_TILE - 1) / PB_TOK_TILE);
     // enough CTAs to fill the machine twice over; each CTA keeps its centroid tile in smem and walks queries
     int groups = std::max(1, std::min(B, (4 * ix->sm_count + tiles - 1) / tiles));
-    if (ix->fma2) {
-        // FFMA2 variant (default): query rows interleaved pairwise, one packed FMA per two dots
-        CKS(ws.Qi.ensure((size_t)B * QS * ix->dim * 4));
-        k_interleave_query_rows<<<dim3(8, B), 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->dim,
-                                                                   ws.Qi.as<float>());
-        PB_DIM_SWITCH(ix->dim, {
-            auto kern = k_centroid_scores<DIM, true>;
-            CKS(set_smem(kern, smem_scores(DIM)));
-            kern<<<dim3(tiles, groups), 128, smem_scores(DIM), ws.stream>>>(ws.Qi.as<float>(), ws.qoff.as<int>(), B, QS,
-                                                                            ix->centroids.as<float>(), ix->K,
-                                                                            ws.ST.as<float>(),
-                                                                            with16 ? ws.ST16.as<unsigned short>() : nullptr,
-                                                                            ws.qrange.as<float2>(), ws.qflag.as<int>());
-        });
-        CK(cudaGetLastError());
-        if (launches) *launches += 2;
-        return PB_OK;
-    }
+    // packed fp32 FMA (FFMA2): query rows interleaved pairwise, one instruction advances two dots
+    CKS(ws.Qi.ensure((size_t)B * QS * ix->dim * 4));
+    k_interleave_query_rows<<<dim3(8, B), 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->dim,
+                                                               ws.Qi.as<float>());
     PB_DIM_SWITCH(ix->dim, {
-        auto kern = k_centroid_scores<DIM, false>;
+        auto kern = k_centroid_scores<DIM, true>;
         CKS(set_smem(kern, smem_scores(DIM)));
-        kern<<<dim3(tiles, groups), 128, smem_scores(DIM), ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), B, QS,
+        KEV_BEGIN(PB_KERNEL_SCORES);
+        kern<<<dim3(tiles, groups), 128, smem_scores(DIM), ws.stream>>>(ws.Qi.as<float>(), ws.qoff.as<int>(), B, QS,
                                                                         ix->centroids.as<float>(), ix->K,
                                                                         ws.ST.as<float>(),
                                                                         with16 ? ws.ST16.as<unsigned short>() : nullptr,
                                                                         ws.qrange.as<float2>(), ws.qflag.as<int>());
+        KEV_END(PB_KERNEL_SCORES);
     });
     CK(cudaGetLastError());
-    if (launches) ++*launches;
+    if (launches) *launches += 2;
     return PB_OK;
 }
 
@@ -819,10 +922,12 @@ static pb_status launch_exact(pb_index *ix, Workspace &ws, const KeptView &kv, i
     PB_DIM_SWITCH(ix->dim, {
         auto kern = ix->fma2_exact ? k_exact<DIM, false, true> : k_exact<DIM, false, false>;
         CKS(set_smem(kern, smem_exact(DIM, ix->packed)));
+        KEV_BEGIN(PB_KERNEL_EXACT);
         kern<<<dim3(gx, B), 128, smem_exact(DIM, ix->packed), ws.stream>>>(
             ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits,
             ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->doc_off.as<long long>(), nullptr,
             kv.kept, kv.nkept, kv.tokp, Mcap, kept_shared, ws.maxkey.as<uint32_t>());
+        KEV_END(PB_KERNEL_EXACT);
     });
     CK(cudaGetLastError());
     if (launches) ++*launches;
@@ -857,11 +962,13 @@ static pb_status launch_filter(pb_index *ix, Workspace &ws, const KeptView &in, 
     {                                                                                                                  \
         auto kern = nqt == 32 ? k_exact_tc<DV, NB, 32> : k_exact_tc<DV, NB, 64>;                                       \
         CKS(set_smem(kern, sm));                                                                                       \
+        KEV_BEGIN(PB_KERNEL_FILTER);                                                                                   \
         kern<<<dim3(gx, B), 128, sm, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS,                             \
                                                   ix->centroids_f16.as<__half>(), ix->w_rev.as<float>(),               \
                                                   ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(),               \
                                                   ix->doc_off.as<long long>(), in.kept, in.nkept, in.tokp, Mcap,       \
                                                   ws.maxkey.as<uint32_t>());                                           \
+        KEV_END(PB_KERNEL_FILTER);                                                                                     \
     }
 #define PB_TC_NBITS(DV)                                                                                                \
     switch (ix->nbits) {                                                                                               \
@@ -1036,11 +1143,15 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
     size_t per_q = (size_t)ix->K * QS_all * sizeof(float);
     if (per_q >= ((size_t)1 << 32))
         return pb_fail(PB_ERR_UNSUPPORTED, "num_centroids x query tokens x 4 = %zu bytes per query exceeds 2^32", per_q);
-    int QB = (int)std::max<size_t>(1, std::min<size_t>((size_t)Bt, ix->st_budget / std::max<size_t>(per_q, 1)));
+    // sub-batch size: the score tables (16-bit always, fp32 only on the exact path) and the per-(query, doc) scratch
+    // (candidate lists, code sums, approximate scores, cut keys, bitmap: 24.2 bytes per document) share one budget
+    const size_t per_q_all = (size_t)ix->K * QS_all * (k1_tc_usable(ix) ? 2 : 6) + (size_t)ix->D * 24 + (size_t)ix->D / 8 + 4096;
+    int QB = (int)std::max<size_t>(1, std::min<size_t>((size_t)Bt, ix->st_budget / per_q_all));
     QB = std::min(QB, 256);
+    QB = (int)((Bt + (Bt + QB - 1) / QB - 1) / ((Bt + QB - 1) / QB));  // equal sub-batches
 
     const bool prof = ix->profiling;
-    std::vector<int> h_counts;
+    if (prof) CK(cudaEventRecord(ws.call_ev[0], ws.stream));
     for (int64_t b0 = 0; b0 < Bt; b0 += QB) {
         const int B = (int)std::min<int64_t>(QB, Bt - b0);
         const int64_t r0 = io.q_off[b0];
@@ -1246,9 +1357,11 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
                 list = ws.cand3.as<uint32_t>();
                 list_n = ws.ncand3.as<int>();
             }
+            KEV_BEGIN(PB_KERNEL_APPROX16);
             (ix->approx_cg ? k_approx16<true> : k_approx16<false>)<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
                                                   ix->udoc_off.as<long long>(), list, ix->D, list_n, ws.lsum.as<uint32_t>(),
                                                   cascade ? cnt + B + 1 : cnt);
+            KEV_END(PB_KERNEL_APPROX16);
             // band per query token in code units (W = band * nq + 8).  Exact table: +-1 code of rounding per token and side
             // plus the fp32 summation error -> 4.  Estimate table (k_scores_tc.cuh): W = nq (1.004 + 2 err) + nq^2/256 + 4
             // <= nq (ceil(1.004 + 2 err) + 1) + 8 for nq <= 256.
@@ -1426,12 +1539,20 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             memcpy(io.out_scores + (size_t)b0 * top_k, h + (size_t)B * top_k * 8, (size_t)B * top_k * 4);
             memcpy(io.out_counts + b0, h + (size_t)B * top_k * 12, (size_t)B * 4);
         }
-        if (prof)
+        if (prof) {
             for (int s = 0; s < PB_STAGE_COUNT; ++s) {
                 float ms = 0.f;
                 CK(cudaEventElapsedTime(&ms, ws.ev[s], ws.ev[s + 1]));
                 g_stats.ms[s] += ms;
             }
+            for (int k = 0; k < PB_KERNEL_COUNT; ++k)
+                if (g_stats.kernel_seen[k]) {
+                    float ms = 0.f;
+                    CK(cudaEventElapsedTime(&ms, ws.kev[2 * k], ws.kev[2 * k + 1]));
+                    g_stats.kernel_ms[k] += ms;
+                    g_stats.kernel_seen[k] = false;
+                }
+        }
         if (fast && ix->k1_diag && ws.k1diag.p) {
             int got[2] = {0, 0};
             CK(cudaMemcpy(got, ws.k1diag.p, 8, cudaMemcpyDeviceToHost));
@@ -1503,6 +1624,11 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             g_stats.work.n_k1_tc_redo += 1;
             CKS(run_sub(false, &redo));
         }
+    }
+    if (prof) {
+        CK(cudaEventRecord(ws.call_ev[1], ws.stream));
+        CK(cudaEventSynchronize(ws.call_ev[1]));
+        CK(cudaEventElapsedTime(&g_stats.call_ms, ws.call_ev[0], ws.call_ev[1]));
     }
     rel.ok = true;
     return PB_OK;

@@ -474,3 +474,56 @@ __global__ void k_scatter_codes(const long long *__restrict__ src, const long lo
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x)
         dst[idx[i]] = src[i];
 }
+
+// ------------------------------------------------------------------------------------------
+// Inverted file from the codes (index.rs:850-873: code -> sorted unique doc ids).  The per-doc distinct code lists
+// (ucodes, built by k_unique_codes for a5) already hold the (doc, code) relation; k_ivf_pairs emits one 64-bit key
+// (code << 32 | doc) per distinct pair -- entries equal to their predecessor are the padding -- a radix sort on
+// the keys orders them by centroid, then doc id; duplicates (docs longer than PB_UCODE_MAX keep a raw code list) are
+// dropped by a unique pass.  Offsets = one lower_bound per centroid.
+// ------------------------------------------------------------------------------------------
+__global__ void k_ivf_pairs(const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off, long long D,
+                            u64 *__restrict__ keys, unsigned long long *__restrict__ n_keys) {
+    const int lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long d = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); d < D; d += nw) {
+        const long long t0 = udoc_off[d], t1 = udoc_off[d + 1];
+        for (long long t = t0; t < t1; t += 32) {
+            const long long i = t + lane;
+            const bool real = i < t1 && (i == t0 || ucodes[i] != ucodes[i - 1]);
+            const unsigned bal = __ballot_sync(PB_FULL, real);
+            unsigned long long base = 0;
+            if (lane == 0 && bal) base = atomicAdd(n_keys, (unsigned long long)__popc(bal));
+            base = shfl_u64(base, 0);
+            if (real) keys[base + __popc(bal & ((1u << lane) - 1u))] = ((u64)ucodes[i] << 32) | (uint32_t)d;
+        }
+    }
+}
+
+__global__ void k_ivf_from_keys(const u64 *__restrict__ keys, long long n, uint32_t *__restrict__ ivf) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        ivf[i] = (uint32_t)keys[i];
+}
+
+// ivf_off[c] = first position whose key has centroid >= c (c = 0..K)
+__global__ void k_ivf_offsets(const u64 *__restrict__ keys, long long n, long long K, long long *__restrict__ ivf_off) {
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c <= K; c += (long long)gridDim.x * blockDim.x) {
+        const u64 want = (u64)c << 32;
+        long long lo = 0, hi = n;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (keys[mid] < want) lo = mid + 1; else hi = mid;
+        }
+        ivf_off[c] = lo;
+    }
+}
+
+// export in the reference's dtypes: ivf.npy <i8 (global doc ids), ivf_lengths.npy <i4
+__global__ void k_ivf_export(const uint32_t *__restrict__ ivf, const long long *__restrict__ ivf_off, long long n, long long K,
+                             long long doc_id_base, long long *__restrict__ out_ivf, int *__restrict__ out_len) {
+    const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (out_ivf)
+        for (long long i = i0; i < n; i += stride) out_ivf[i] = (long long)ivf[i] + doc_id_base;
+    if (out_len)
+        for (long long c = i0; c < K; c += stride) out_len[c] = (int)(ivf_off[c + 1] - ivf_off[c]);
+}

@@ -40,7 +40,7 @@ class _Desc(C.Structure):
         ("centroids", C.c_void_p), ("bucket_weights", C.c_void_p), ("codes", C.c_void_p),
         ("residuals", C.c_void_p), ("doc_lengths", C.c_void_p), ("ivf", C.c_void_p),
         ("ivf_lengths", C.c_void_p), ("device", C.c_int32), ("memory_space", C.c_int32),
-        ("doc_id_base", C.c_int64),
+        ("doc_id_base", C.c_int64), ("flags", C.c_int32),
     ]
 
 
@@ -78,7 +78,7 @@ EXPORTS = [
     "pb_maxsim_scores", "pb_exhaustive_scores", "pb_set_profiling", "pb_last_stage_stats",
     "pb_last_work_counters", "pb_search_batch_device", "pb_last_error", "pb_version",
     "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init", "pb_shard_group_create", "pb_shard_group_destroy",
-    "pb_index_group_join", "pb_set_fast_approx", "pb_set_fast_exact",
+    "pb_index_group_join", "pb_index_export_ivf", "pb_last_call_ms", "pb_last_kernel_ms", "pb_set_fast_approx", "pb_set_fast_exact",
     "pb_codec_open", "pb_codec_close", "pb_codec_compress_into_codes", "pb_codec_compress_and_residuals",
     "pb_codec_encode_chunk", "pb_kmeans_fit", "pb_codec_last_assign_stats", "pb_codec_find_outliers",
 ]
@@ -127,6 +127,9 @@ def load_library():
         L.pb_exhaustive_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.pb_last_stage_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pb_last_work_counters.argtypes = [C.c_void_p, C.POINTER(_Work)]
+        L.pb_last_call_ms.argtypes = [C.c_void_p, C.c_void_p]
+        L.pb_last_kernel_ms.argtypes = [C.c_void_p, C.c_void_p]
+        L.pb_index_export_ivf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pb_codec_open.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                     C.POINTER(C.c_void_p)]
         L.pb_codec_close.argtypes = [C.c_void_p]
@@ -282,21 +285,25 @@ class MmapIndex:
         cd = np.ascontiguousarray(codes, np.int64)
         rs = np.ascontiguousarray(residuals, np.uint8)
         dl = np.ascontiguousarray(doc_lengths, np.int64)
-        iv = np.ascontiguousarray(ivf, np.int64)
-        il = np.ascontiguousarray(ivf_lengths, np.int32)
+        # ivf = ivf_lengths = None: the inverted file is built on the device from the codes (index.rs:850-873)
+        iv = None if ivf is None else np.ascontiguousarray(ivf, np.int64)
+        il = None if ivf_lengths is None else np.ascontiguousarray(ivf_lengths, np.int32)
         d = _Desc(cen.shape[1], nbits, cen.shape[0], len(dl), len(cd), _ptr(cen), _ptr(w), _ptr(cd),
-                  _ptr(rs), _ptr(dl), _ptr(iv), _ptr(il), device, 0, doc_id_base)
+                  _ptr(rs), _ptr(dl), _ptr(iv), _ptr(il), device, 0, doc_id_base, 0)
         h = C.c_void_p()
         _check(L.pb_index_open(C.byref(d), C.byref(h)))
         return cls(h.value)
 
     @classmethod
     def from_device_pointers(cls, dim, nbits, K, D, N, centroids, bucket_weights, codes, residuals,
-                             doc_lengths, ivf, ivf_lengths, device: int = 0, doc_id_base: int = 0):
-        """pb_index_open with PB_MEM_DEVICE pointers (integers), e.g. torch tensors' data_ptr()."""
+                             doc_lengths, ivf, ivf_lengths, device: int = 0, doc_id_base: int = 0,
+                             adopt_residuals: bool = False):
+        """pb_index_open with PB_MEM_DEVICE pointers (integers), e.g. torch tensors' data_ptr().  ivf = ivf_lengths
+        = None: the inverted file is built on the device (index.rs:850-873).  adopt_residuals: the packed residuals
+        are used in place (keep the array alive until close())."""
         L = load_library()
         d = _Desc(dim, nbits, K, D, N, centroids, bucket_weights, codes, residuals, doc_lengths, ivf,
-                  ivf_lengths, device, 1, doc_id_base)
+                  ivf_lengths, device, 1, doc_id_base, 1 if adopt_residuals else 0)
         h = C.c_void_p()
         _check(L.pb_index_open(C.byref(d), C.byref(h)))
         return cls(h.value)
@@ -434,6 +441,27 @@ class MmapIndex:
         ln = np.zeros(len(STAGES), np.int32)
         _check(load_library().pb_last_stage_stats(self._h, _ptr(ms), _ptr(ln)))
         return dict(zip(STAGES, ms.tolist())), dict(zip(STAGES, ln.tolist()))
+
+    def export_ivf(self):
+        """pb_index_export_ivf: (ivf <i8 global doc ids, ivf_lengths <i4), what create_index writes to ivf.npy /
+        ivf_lengths.npy (index.rs:501-508)."""
+        L = load_library()
+        tot = C.c_int64()
+        _check(L.pb_index_export_ivf(self._h, None, None, C.byref(tot)))
+        ivf = np.zeros(max(tot.value, 1), np.int64)
+        lens = np.zeros(self.num_partitions(), np.int32)
+        _check(L.pb_index_export_ivf(self._h, _ptr(ivf), _ptr(lens), C.byref(tot)))
+        return ivf[:tot.value], lens
+
+    def last_call_ms(self) -> float:
+        v = np.zeros(1, np.float32)
+        _check(load_library().pb_last_call_ms(self._h, _ptr(v)))
+        return float(v[0])
+
+    def last_kernel_ms(self) -> dict:
+        v = np.zeros(4, np.float32)
+        _check(load_library().pb_last_kernel_ms(self._h, _ptr(v)))
+        return dict(zip(("scores", "approx16", "filter", "exact"), v.tolist()))
 
     def last_work_counters(self) -> dict:
         w = _Work()

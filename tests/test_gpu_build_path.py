@@ -165,3 +165,46 @@ def test_find_outliers_reference_kat(npb):
     c = np.zeros((2, 32), np.float32); c[1, :2] = 1.0
     e = np.zeros((3, 32), np.float32); e[0, :2] = 0.1; e[1, :2] = 0.9; e[2, :2] = 5.0
     assert npb.ResidualCodec(4, c).find_outliers(e, 1.0).tolist() == [2]
+
+
+def test_inverted_file_is_built_on_the_device_when_none_is_given(oracle, npb):
+    # index.rs:850-873: code -> sorted unique doc ids.  A handle opened without ivf builds it from the codes; the
+    # export is what create_index writes to ivf.npy / ivf_lengths.npy, and searches on it equal the oracle's.
+    docs = oracle.synthetic_corpus(1200, 36, dim=64, seed=77, ragged=True)
+    docs[5] = docs[5][:0]                                           # a doc without tokens
+    ix = oracle.create_index(docs, nbits=2, seed=9, num_partitions=300)
+    gpu = npb.MmapIndex.from_arrays(ix.centroids, ix.bucket_weights, ix.codes, ix.residuals, ix.doc_lengths,
+                                    None, None, ix.nbits, doc_id_base=0)
+    try:
+        ivf, lens = gpu.export_ivf()
+        assert lens.dtype == np.int32 and ivf.dtype == np.int64
+        assert np.array_equal(lens, ix.ivf_lengths) and np.array_equal(ivf, ix.ivf)
+        qs, _ = oracle.synthetic_queries(docs, 6, nq=16, seed=4)
+        kw = dict(top_k=10, n_ivf_probe=4, n_full_scores=128)
+        for q, r in zip(qs, gpu.search_batch(qs, npb.SearchParameters(**kw))):
+            w = oracle.search_one(ix, q, oracle.SearchParameters(**kw))
+            assert r.passage_ids.tolist() == w.passage_ids.tolist() and np.array_equal(r.scores, w.scores)
+    finally:
+        gpu.close()
+
+
+def test_adopted_device_residuals_are_used_in_place(oracle, npb):
+    import torch
+    docs = oracle.synthetic_corpus(600, 30, dim=128, seed=78)
+    ix = oracle.create_index(docs, nbits=4, seed=9, num_partitions=128)
+    dev = torch.device("cuda", 0)
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in dict(
+        cen=ix.centroids, w=ix.bucket_weights, codes=ix.codes.astype(np.int64), res=ix.residuals,
+        dl=ix.doc_lengths.astype(np.int64)).items()}
+    gpu = npb.MmapIndex.from_device_pointers(128, 4, ix.num_centroids, ix.num_documents, ix.num_embeddings,
+                                             t["cen"].data_ptr(), t["w"].data_ptr(), t["codes"].data_ptr(),
+                                             t["res"].data_ptr(), t["dl"].data_ptr(), None, None, device=0,
+                                             adopt_residuals=True)
+    try:
+        qs, _ = oracle.synthetic_queries(docs, 4, nq=32, seed=5)
+        kw = dict(top_k=5, n_ivf_probe=8, n_full_scores=64)
+        for q, r in zip(qs, gpu.search_batch(qs, npb.SearchParameters(**kw))):
+            w = oracle.search_one(ix, q, oracle.SearchParameters(**kw))
+            assert r.passage_ids.tolist() == w.passage_ids.tolist() and np.array_equal(r.scores, w.scores)
+    finally:
+        gpu.close()
