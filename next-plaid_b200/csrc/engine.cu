@@ -692,6 +692,9 @@ extern "C" void pb_set_fast_approx(pb_index *ix, int32_t enabled) {
     ix->fast_approx = enabled != 0;  // 0 = single exact pass, 1 = two-pass, 2 = two-pass behind the pruning cascade
     ix->cascade = enabled == 2;
 }
+extern "C" void pb_set_scores_tc(pb_index *ix, int32_t enabled) {
+    if (ix) ix->k1_tc = enabled != 0;  // effective when the tensor-core operands were built at open (k1_tc_usable)
+}
 extern "C" void pb_set_fast_exact(pb_index *ix, int32_t enabled) {
     if (ix) ix->fast_exact = enabled != 0;
 }

@@ -78,7 +78,7 @@ EXPORTS = [
     "pb_maxsim_scores", "pb_exhaustive_scores", "pb_set_profiling", "pb_last_stage_stats",
     "pb_last_work_counters", "pb_search_batch_device", "pb_last_error", "pb_version",
     "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init", "pb_shard_group_create", "pb_shard_group_destroy",
-    "pb_index_group_join", "pb_index_export_ivf", "pb_last_call_ms", "pb_last_kernel_ms", "pb_set_fast_approx", "pb_set_fast_exact",
+    "pb_index_group_join", "pb_index_export_ivf", "pb_last_call_ms", "pb_last_kernel_ms", "pb_set_fast_approx", "pb_set_fast_exact", "pb_set_scores_tc",
     "pb_codec_open", "pb_codec_close", "pb_codec_compress_into_codes", "pb_codec_compress_and_residuals",
     "pb_codec_encode_chunk", "pb_kmeans_fit", "pb_codec_last_assign_stats", "pb_codec_find_outliers",
 ]
@@ -112,6 +112,8 @@ def load_library():
         L.pb_set_fast_approx.restype = None
         L.pb_set_fast_exact.argtypes = [C.c_void_p, C.c_int32]
         L.pb_set_fast_exact.restype = None
+        L.pb_set_scores_tc.argtypes = [C.c_void_p, C.c_int32]
+        L.pb_set_scores_tc.restype = None
         L.pb_index_load.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
         L.pb_index_open.argtypes = [C.POINTER(_Desc), C.POINTER(C.c_void_p)]
         L.pb_search_batch_traced.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
@@ -428,6 +430,10 @@ class MmapIndex:
     def set_fast_approx(self, mode):
         """0/False = single exact pass, 1/True = two-pass (default), 2 = two-pass + pruning cascade."""
         load_library().pb_set_fast_approx(self._h, int(mode))
+
+    def set_scores_tc(self, on: bool):
+        """a2 on the tensor cores (default on) vs the dense fp32 kernel; same results either way."""
+        load_library().pb_set_scores_tc(self._h, 1 if on else 0)
 
     def set_fast_exact(self, on: bool):
         """tcgen05 certified filter in front of the exact stage (default on); same results either way."""
