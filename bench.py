@@ -158,7 +158,8 @@ def build_shard(args, G, rank, world, device):
         residuals[c * chunk * T:(c + 1) * chunk * T] = rr
         del cc, rr
     doc_lengths = torch.full((per_rank,), T, dtype=torch.int64, device=device)
-    torch.cuda.synchronize(device)
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
     return dict(codes=codes, residuals=residuals, doc_lengths=doc_lengths, D=per_rank, N=N)
 
 
