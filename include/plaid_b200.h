@@ -311,9 +311,46 @@ PB_API pb_status pb_codec_encode_chunk(pb_codec *c, const float *embeddings, int
  * borderline rows.  out_indices must hold n entries. */
 PB_API pb_status pb_codec_find_outliers(pb_codec *c, const float *embeddings, int64_t n, float threshold_sq,
                                         int64_t *out_indices, int64_t *out_count);
+/* prepare_codec_artifacts' arithmetic (index.rs:228-287) on held-out embeddings the caller sampled (index.rs:195-226
+ * is a seeded shuffle on the host): nearest-centroid residuals, then
+ *   out_cutoffs [2^nbits - 1]  quantiles i / 2^nbits of the flattened residuals        (index.rs:260-266)
+ *   out_weights [2^nbits]      quantiles (i + 1/2) / 2^nbits                             (index.rs:267-270)
+ *   out_avg_residual [dim]     mean |residual| per dimension (may be NULL)               (index.rs:255-258)
+ *   out_cluster_threshold      quantile 0.75 of the residual L2 norms (may be NULL)      (index.rs:249-253)
+ * with utils.rs:125-149's quantile (sort, position q (n - 1) in f64, lo (1 - w) + hi w, w as f32).  The codec keeps
+ * the cutoffs, so pb_codec_encode_chunk works afterwards.  n * dim < 2^31. */
+PB_API pb_status pb_codec_train(pb_codec *c, const float *heldout_embeddings, int64_t n, float *out_cutoffs,
+                                float *out_weights, float *out_avg_residual, float *out_cluster_threshold);
+/* the sizing rules around it: compute_kmeans (kmeans.rs:273-312) and prepare_codec_artifacts (index.rs:195-212) */
+PB_API int64_t pb_kmeans_num_sample_docs(int64_t num_documents);
+PB_API int64_t pb_kmeans_num_partitions(int64_t num_documents, double avg_sample_doclen, int64_t num_sample_tokens);
+PB_API int64_t pb_codec_num_sample_docs(int64_t num_documents);
+PB_API int64_t pb_codec_heldout_tokens(int64_t num_embeddings);
 /* compute_kmeans' inner fit + L2 normalisation (kmeans.rs:319-419): out_centroids [K][dim] */
 PB_API pb_status pb_kmeans_fit(int32_t device, const float *samples, int64_t n, int32_t dim, int64_t num_centroids,
                                int32_t niters, uint64_t seed, float *out_centroids);
+
+/* MmapIndex::create_with_kmeans (index.rs:1392 -> kmeans.rs:261-422 -> index.rs:551-911): from document embeddings to
+ * the reference's index directory (file set of index.rs:394-525), every numeric step on the device -- k-means
+ * (pb_kmeans_fit), codec training (pb_codec_train), per-chunk encode (pb_codec_encode_chunk), inverted file
+ * (index.rs:850-873) -- and the host doing only sampling and file writing.  The directory loads with the reference's
+ * MmapIndex::load and with pb_index_load.  Sample membership and the k-means iteration are parity-unpinned (the
+ * reference delegates them to rand_chacha / fastkmeans-rs, neither in its tree); everything downstream of the
+ * centroids and the held-out sample is bit-identical to the reference's CPU arithmetic.
+ *   embeddings   [sum doc_lengths][dim] f32 host, documents concatenated; doc_lengths [n_docs]
+ *   out_index    optional: the freshly built index, already open on params->device */
+typedef struct pb_create_params {  /* IndexConfig, index.rs:73-102 */
+    int32_t nbits;                   /* 4 */
+    int32_t kmeans_niters;           /* 4 */
+    int32_t max_points_per_centroid; /* 256 */
+    int32_t device;
+    int64_t num_partitions;          /* 0 = the heuristic of kmeans.rs:304-309 */
+    int64_t batch_size;              /* docs per chunk file, 50 000 */
+    uint64_t seed;                   /* 42 */
+} pb_create_params;
+PB_API void pb_create_params_default(pb_create_params *p);
+PB_API pb_status pb_create_index(const float *embeddings, const int64_t *doc_lengths, int64_t n_docs, int32_t dim,
+                                 const pb_create_params *params, const char *index_dir, pb_index **out_index);
 
 /* ---- doc-sharded deployment (no reference analogue: the reference is single-process) ----
  *

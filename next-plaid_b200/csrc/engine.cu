@@ -2115,6 +2115,113 @@ extern "C" pb_status pb_codec_compress_and_residuals(pb_codec *c, const float *e
     return codec_run(c, embeddings, n, out_codes, nullptr, out_residuals);
 }
 
+// prepare_codec_artifacts' arithmetic (index.rs:228-287) for held-out embeddings the caller selected: residuals of
+// the nearest centroid, cluster_threshold = quantile 0.75 of their L2 norms, avg_residual = per-dimension mean of
+// |residual|, bucket cutoffs / weights = quantiles of the flattened residuals at i/2^b and (i+1/2)/2^b
+// (utils.rs:125-149: sort, position q (n-1) in f64, lo (1-w) + hi w with w cast to f32).  The codec keeps the cutoffs.
+static float quantile_pick(const std::vector<float> &sorted_at, const std::vector<long long> &pos, long long n, double q) {
+    // sorted_at[i] = sorted[pos[i]]; pos holds floor/ceil positions of every requested quantile in order
+    const double idx = q * (double)(n - 1);
+    const long long lo = (long long)floor(idx), hi = (long long)ceil(idx);
+    float vlo = 0.f, vhi = 0.f;
+    for (size_t i = 0; i < pos.size(); ++i) {
+        if (pos[i] == lo) vlo = sorted_at[i];
+        if (pos[i] == hi) vhi = sorted_at[i];
+    }
+    if (lo == hi) return vlo;
+    const float w = (float)(idx - (double)lo);
+    return vlo * (1.0f - w) + vhi * w;
+}
+
+static pb_status device_quantiles(DevBuf &vals, long long n, const std::vector<double> &qs, std::vector<float> &out) {
+    out.assign(qs.size(), 0.0f);
+    if (n == 0) return PB_OK;
+    DevBuf sorted, tmp;
+    CKS(sorted.ensure((size_t)n * 4));
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, vals.as<float>(), sorted.as<float>(), (int)n));
+    CKS(tmp.ensure(tb + 16));
+    CK(cub::DeviceRadixSort::SortKeys(tmp.p, tb, vals.as<float>(), sorted.as<float>(), (int)n));
+    std::vector<long long> pos;
+    for (double q : qs) {
+        const double idx = q * (double)(n - 1);
+        pos.push_back((long long)floor(idx));
+        pos.push_back((long long)ceil(idx));
+    }
+    std::vector<float> at(pos.size());
+    for (size_t i = 0; i < pos.size(); ++i)
+        CK(cudaMemcpy(&at[i], sorted.as<float>() + pos[i], 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < qs.size(); ++i) out[i] = quantile_pick(at, pos, n, qs[i]);
+    return PB_OK;
+}
+
+extern "C" pb_status pb_codec_train(pb_codec *c, const float *heldout, int64_t n, float *out_cutoffs, float *out_weights,
+                                    float *out_avg_residual, float *out_cluster_threshold) {
+    if (!c || (!heldout && n) || n < 0 || !out_cutoffs || !out_weights) return pb_fail(PB_ERR_INVALID, "null argument");
+    if ((long long)n * c->dim >= (1ll << 31)) return pb_fail(PB_ERR_UNSUPPORTED, "held-out sample too large");
+    CK(cudaSetDevice(c->device));
+    const int nopt = 1 << c->nbits;
+    DevBuf dX, dcodes, dres, dnorm, davg;
+    CKS(dX.ensure(std::max<size_t>((size_t)n * c->dim * 4, 16)));
+    CKS(dcodes.ensure(std::max<size_t>((size_t)n * 8, 16)));
+    CKS(dres.ensure(std::max<size_t>((size_t)n * c->dim * 4, 16)));
+    CKS(dnorm.ensure(std::max<size_t>((size_t)n * 4, 16)));
+    CKS(davg.ensure((size_t)c->dim * 4));
+    if (n > 0) {
+        CK(cudaMemcpy(dX.p, heldout, (size_t)n * c->dim * 4, cudaMemcpyHostToDevice));
+        CKS(assign_codes(c, dX.as<float>(), n, dcodes.as<long long>()));
+        if (!c->has_cutoffs) {  // the residual kernel takes a cutoff pointer it does not read without a packed output
+            float zero[255] = {0};
+            CKS(upload(c->cutoffs, zero, sizeof zero, PB_MEM_HOST));
+        }
+        PB_DIM_SWITCH(c->dim, {
+            k_quantize_pack<DIM><<<c->sm_count * 8, 256>>>(dX.as<float>(), n, c->centroids.as<float>(), dcodes.as<long long>(),
+                                                            c->cutoffs.as<float>(), c->nbits, nullptr, dres.as<float>());
+        });
+        k_residual_stats<<<c->sm_count * 4, 256>>>(dres.as<float>(), n, c->dim, dnorm.as<float>());
+        k_column_abs_mean<<<(c->dim + 31) / 32, 32>>>(dres.as<float>(), n, c->dim, davg.as<float>());
+        CK(cudaGetLastError());
+    }
+    std::vector<double> q75{0.75}, qc, qw;
+    for (int i = 1; i < nopt; ++i) qc.push_back((double)i / (double)nopt);
+    for (int i = 0; i < nopt; ++i) qw.push_back(((double)i + 0.5) / (double)nopt);
+    std::vector<float> r75, rc, rw;
+    CKS(device_quantiles(dnorm, n, q75, r75));
+    CKS(device_quantiles(dres, (long long)n * c->dim, qc, rc));
+    CKS(device_quantiles(dres, (long long)n * c->dim, qw, rw));
+    for (int i = 0; i < nopt - 1; ++i) out_cutoffs[i] = rc[i];
+    for (int i = 0; i < nopt; ++i) out_weights[i] = rw[i];
+    if (out_cluster_threshold) *out_cluster_threshold = n ? r75[0] : 0.0f;
+    if (out_avg_residual) {
+        if (n) CK(cudaMemcpy(out_avg_residual, davg.p, (size_t)c->dim * 4, cudaMemcpyDeviceToHost));
+        else memset(out_avg_residual, 0, (size_t)c->dim * 4);
+    }
+    float cut[255] = {0};
+    for (int i = 0; i < nopt - 1; ++i) cut[i] = rc[i];
+    CKS(upload(c->cutoffs, cut, sizeof cut, PB_MEM_HOST));
+    c->has_cutoffs = true;
+    return PB_OK;
+}
+
+// compute_kmeans' sizing rules (kmeans.rs:273-312) and prepare_codec_artifacts' (index.rs:195-212), as the host
+// side needs them to pick its samples
+extern "C" int64_t pb_kmeans_num_sample_docs(int64_t num_documents) {  // min(floor(1 + 16 sqrt(120 D)), D)
+    const double v = 1.0 + 16.0 * sqrt(120.0 * (double)num_documents);
+    return std::min<int64_t>((int64_t)v, num_documents);
+}
+extern "C" int64_t pb_kmeans_num_partitions(int64_t num_documents, double avg_sample_doclen, int64_t num_sample_tokens) {
+    const double est = avg_sample_doclen * (double)num_documents;  // K = 2^floor(log2(16 sqrt(avg_doclen * D)))
+    const double k = pow(2.0, floor(log2(16.0 * sqrt(est))));
+    return std::max<int64_t>(1, std::min<int64_t>((int64_t)k, num_sample_tokens));
+}
+extern "C" int64_t pb_codec_num_sample_docs(int64_t num_documents) {  // clamp(floor(16 sqrt(120 D)), 1, D)
+    const int64_t v = (int64_t)(16.0 * sqrt(120.0 * (double)num_documents));
+    return std::max<int64_t>(1, std::min<int64_t>(v, num_documents));
+}
+extern "C" int64_t pb_codec_heldout_tokens(int64_t num_embeddings) {  // min(0.05 N, 50 000)
+    return (int64_t)std::min(0.05 * (double)num_embeddings, 50000.0);
+}
+
 extern "C" pb_status pb_kmeans_fit(int32_t device, const float *samples, int64_t n, int32_t dim, int64_t K, int32_t niters,
                                    uint64_t seed, float *out_centroids) {
     if (!samples || !out_centroids) return pb_fail(PB_ERR_INVALID, "null argument");

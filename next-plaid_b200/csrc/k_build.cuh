@@ -527,3 +527,25 @@ __global__ void k_ivf_export(const uint32_t *__restrict__ ivf, const long long *
     if (out_len)
         for (long long c = i0; c < K; c += stride) out_len[c] = (int)(ivf_off[c + 1] - ivf_off[c]);
 }
+
+// codec training (index.rs:240-258): L2 norm of every residual row; per-dimension mean of |residual|
+__global__ void k_residual_stats(const float *__restrict__ R, long long n, int dim, float *__restrict__ norms) {
+    const int lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += nw) {
+        float p = 0.0f;
+        for (int j = lane; j < dim; j += 32) {
+            const float v = R[(size_t)r * dim + j];
+            p = fmaf(v, v, p);
+        }
+        for (int m = 16; m >= 1; m >>= 1) p += __shfl_xor_sync(PB_FULL, p, m);
+        if (lane == 0) norms[r] = sqrtf(p);
+    }
+}
+__global__ void k_column_abs_mean(const float *__restrict__ R, long long n, int dim, float *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= dim) return;
+    double acc = 0.0;  // one thread per dimension, rows in order: deterministic
+    for (long long r = 0; r < n; ++r) acc += (double)fabsf(R[(size_t)r * dim + j]);
+    out[j] = n > 0 ? (float)(acc / (double)n) : 0.0f;
+}

@@ -80,7 +80,9 @@ EXPORTS = [
     "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init", "pb_shard_group_create", "pb_shard_group_destroy",
     "pb_index_group_join", "pb_index_export_ivf", "pb_last_call_ms", "pb_last_kernel_ms", "pb_set_fast_approx", "pb_set_fast_exact", "pb_set_scores_tc",
     "pb_codec_open", "pb_codec_close", "pb_codec_compress_into_codes", "pb_codec_compress_and_residuals",
-    "pb_codec_encode_chunk", "pb_kmeans_fit", "pb_codec_last_assign_stats", "pb_codec_find_outliers",
+    "pb_codec_encode_chunk", "pb_kmeans_fit", "pb_codec_train", "pb_kmeans_num_sample_docs",
+    "pb_kmeans_num_partitions", "pb_codec_num_sample_docs", "pb_codec_heldout_tokens", "pb_create_index",
+    "pb_create_params_default", "pb_codec_last_assign_stats", "pb_codec_find_outliers",
 ]
 
 _lib = None
@@ -143,6 +145,15 @@ def load_library():
         L.pb_codec_encode_chunk.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.pb_kmeans_fit.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_uint64,
                                     C.c_void_p]
+        L.pb_codec_train.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        for f in ("pb_kmeans_num_sample_docs", "pb_codec_num_sample_docs", "pb_codec_heldout_tokens"):
+            getattr(L, f).restype = C.c_int64
+            getattr(L, f).argtypes = [C.c_int64]
+        L.pb_kmeans_num_partitions.restype = C.c_int64
+        L.pb_kmeans_num_partitions.argtypes = [C.c_int64, C.c_double, C.c_int64]
+        L.pb_create_index.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_char_p, C.c_void_p]
+        L.pb_create_params_default.argtypes = [C.c_void_p]
+        L.pb_create_params_default.restype = None
         L.pb_comm_unique_id.argtypes = [C.c_void_p]
         L.pb_index_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.pb_shard_group_create.argtypes = [C.c_int32, C.c_void_p]
@@ -498,6 +509,34 @@ def maxsim_scores(query: np.ndarray, docs: Sequence[np.ndarray], device: int = 0
     return out
 
 
+class _CreateParams(C.Structure):
+    _fields_ = [("nbits", C.c_int32), ("kmeans_niters", C.c_int32), ("max_points_per_centroid", C.c_int32),
+                ("device", C.c_int32), ("num_partitions", C.c_int64), ("batch_size", C.c_int64), ("seed", C.c_uint64)]
+
+
+def create_index(embeddings: Sequence[np.ndarray], index_dir: str, nbits: int = 4, kmeans_niters: int = 4,
+                 num_partitions: int = 0, batch_size: int = 50_000, seed: int = 42, device: int = 0,
+                 max_points_per_centroid: int = 256) -> "MmapIndex":
+    """MmapIndex::create_with_kmeans (index.rs:1392): builds the reference's index directory from document embeddings
+    on the GPU (pb_create_index) and returns the open index."""
+    L = load_library()
+    dl = np.array([e.shape[0] for e in embeddings], np.int64)
+    flat = np.ascontiguousarray(np.concatenate(embeddings, 0), np.float32)
+    p = _CreateParams(nbits, kmeans_niters, max_points_per_centroid, device, num_partitions, batch_size, seed)
+    h = C.c_void_p()
+    _check(L.pb_create_index(_ptr(flat), _ptr(dl), len(dl), flat.shape[1], C.byref(p), index_dir.encode(), C.byref(h)))
+    return MmapIndex(h.value)
+
+
+def kmeans_sizing(num_documents: int, avg_sample_doclen: float, num_sample_tokens: int, num_embeddings: int) -> dict:
+    """The sizing rules of compute_kmeans (kmeans.rs:273-312) and prepare_codec_artifacts (index.rs:195-212)."""
+    L = load_library()
+    return {"kmeans_sample_docs": int(L.pb_kmeans_num_sample_docs(num_documents)),
+            "num_partitions": int(L.pb_kmeans_num_partitions(num_documents, float(avg_sample_doclen), num_sample_tokens)),
+            "codec_sample_docs": int(L.pb_codec_num_sample_docs(num_documents)),
+            "heldout_tokens": int(L.pb_codec_heldout_tokens(num_embeddings))}
+
+
 class ResidualCodec:
     """Device-resident next_plaid::ResidualCodec (codec.rs:107-123) for the index-build path."""
 
@@ -549,6 +588,16 @@ class ResidualCodec:
         _check(load_library().pb_codec_find_outliers(self._h, _ptr(e), e.shape[0], float(threshold_sq), _ptr(out),
                                                      C.byref(cnt)))
         return out[:cnt.value].copy()
+
+    def train(self, heldout: np.ndarray):
+        """pb_codec_train (prepare_codec_artifacts, index.rs:228-287, on held-out rows the caller sampled):
+        (bucket_cutoffs, bucket_weights, avg_residual, cluster_threshold); the codec keeps the cutoffs."""
+        e = np.ascontiguousarray(heldout, np.float32).reshape(-1, self.dim)
+        nopt = 1 << self.nbits
+        cut, wts, avg = np.zeros(max(nopt - 1, 1), np.float32), np.zeros(nopt, np.float32), np.zeros(self.dim, np.float32)
+        thr = C.c_float()
+        _check(load_library().pb_codec_train(self._h, _ptr(e), e.shape[0], _ptr(cut), _ptr(wts), _ptr(avg), C.byref(thr)))
+        return cut[:nopt - 1], wts, avg, float(thr.value)
 
     def encode_chunk(self, embeddings: np.ndarray):
         """encode_index_chunk (index.rs:289): (codes i64 [n], packed residuals u8 [n, dim*nbits/8])."""

@@ -85,3 +85,17 @@ def test_product_does_not_import_oracle():
                 # comments may cite the oracle's pinned order; code may not import, include or dlopen it
                 assert not re.search(r"^\s*(import|from)\s+oracle", txt, re.M), f
                 assert "libplaid_oracle" not in txt and not re.search(r"#include\s+.*oracle", txt), f
+
+
+def test_build_sizing_rules_match_the_reference_formulas(npb=None):
+    # kmeans.rs:273-312 and index.rs:195-212 are pure arithmetic: no device needed
+    import next_plaid_b200 as m
+    from oracle import oracle
+    for D, avg in ((10_000, 64.0), (1_000_000, 300.0), (123, 17.5), (1, 5.0)):
+        n_docs = min(int(1.0 + 16.0 * np.sqrt(120.0 * D)), D)
+        s = m.kmeans_sizing(D, avg, 10 ** 12, int(D * avg))
+        assert s["kmeans_sample_docs"] == n_docs
+        assert s["num_partitions"] == oracle.num_partitions_heuristic(D, [avg] * 4)
+        assert s["codec_sample_docs"] == max(min(int(16.0 * np.sqrt(120.0 * D)), D), 1)
+        assert s["heldout_tokens"] == int(min(0.05 * int(D * avg), 50000.0))
+    assert m.kmeans_sizing(10_000, 64.0, 100, 640_000)["num_partitions"] == 100      # capped at the sampled tokens
