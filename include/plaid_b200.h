@@ -289,6 +289,7 @@ PB_API pb_status pb_search_batch_device(pb_index *ix, const float *d_queries,
  * tie rule -- the reference's own CUDA kernel picks the FIRST maximum (cuda.rs:202).
  * k-means: fastkmeans-rs is not in the reference tree, so pb_kmeans_fit is parity-unpinned. */
 typedef struct pb_codec pb_codec;
+typedef struct pb_shard_group pb_shard_group;   /* in-process rank group, see "doc-sharded deployment" below */
 PB_API pb_status pb_codec_open(int32_t device, const float *centroids, int64_t num_centroids, int32_t dim,
                                int32_t nbits, const float *bucket_cutoffs /* may be NULL */, pb_codec **out);
 PB_API void pb_codec_close(pb_codec *c);
@@ -330,6 +331,18 @@ PB_API int64_t pb_codec_heldout_tokens(int64_t num_embeddings);
 PB_API pb_status pb_kmeans_fit(int32_t device, const float *samples, int64_t n, int32_t dim, int64_t num_centroids,
                                int32_t niters, uint64_t seed, float *out_centroids);
 
+/* Data-parallel k-means for the multi-GPU build (SURVEY 8e "Build path"): one rank per GPU, each with its shard of
+ * the sample points; per iteration one all-reduce of the [K][dim] sums + [K] counts.  A pb_build_comm is an NCCL
+ * communicator (one process per GPU; ship pb_comm_unique_id's 128 bytes as for search) or a member of an in-process
+ * pb_shard_group (one host thread per rank).  Every rank receives the same L2-normalised centroids.  The encode
+ * that follows needs no communication: each rank runs pb_codec_encode_chunk on its own documents. */
+typedef struct pb_build_comm pb_build_comm;
+PB_API pb_status pb_build_comm_init(const uint8_t *id128, int32_t rank, int32_t world, int32_t device, pb_build_comm **out);
+PB_API pb_status pb_build_comm_group(pb_shard_group *g, int32_t rank, int32_t device, pb_build_comm **out);
+PB_API void pb_build_comm_destroy(pb_build_comm *c);
+PB_API pb_status pb_kmeans_fit_dp(pb_build_comm *c, const float *samples_local, int64_t n_local, int32_t dim,
+                                  int64_t num_centroids, int32_t niters, uint64_t seed, float *out_centroids);
+
 /* MmapIndex::create_with_kmeans (index.rs:1392 -> kmeans.rs:261-422 -> index.rs:551-911): from document embeddings to
  * the reference's index directory (file set of index.rs:394-525), every numeric step on the device -- k-means
  * (pb_kmeans_fit), codec training (pb_codec_train), per-chunk encode (pb_codec_encode_chunk), inverted file
@@ -367,7 +380,6 @@ PB_API pb_status pb_index_comm_init(pb_index *ix, const uint8_t *id128, int32_t 
  * per handle, all threads call pb_search_batch together.  The exchanges are peer copies behind a host
  * barrier instead of NCCL; a peer that fails or does not arrive within 60 s breaks the group (PB_ERR_COMM).
  * The group must outlive every handle that joined it. */
-typedef struct pb_shard_group pb_shard_group;
 PB_API pb_status pb_shard_group_create(int32_t world, pb_shard_group **out);
 PB_API void pb_shard_group_destroy(pb_shard_group *g);
 PB_API pb_status pb_index_group_join(pb_index *ix, pb_shard_group *g, int32_t rank);

@@ -29,13 +29,14 @@
 // ------------------------------------------------------------------------------------------
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
-enum { PB_NCCL_UINT64 = 5 };
+enum { PB_NCCL_UINT64 = 5, PB_NCCL_FLOAT32 = 7, PB_NCCL_SUM = 0 };
 struct NcclApi {
     void *h = nullptr;
     int (*GetUniqueId)(ncclUniqueId *) = nullptr;
     int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     bool load() {
         if (h) return true;
@@ -49,8 +50,9 @@ struct NcclApi {
         CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
         CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
         AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+        AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
         GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
-        return GetUniqueId && CommInitRank && CommDestroy && AllGather && GetErrorString;
+        return GetUniqueId && CommInitRank && CommDestroy && AllGather && AllReduce && GetErrorString;
     }
 };
 static NcclApi g_nccl;
@@ -2262,6 +2264,145 @@ extern "C" pb_status pb_kmeans_fit(int32_t device, const float *samples, int64_t
     k_normalize_rows<<<sms * 4, 256>>>(dC.as<float>(), K, dim);  // kmeans.rs:415-419
     CK(cudaGetLastError());
     CK(cudaMemcpy(out_centroids, dC.p, (size_t)K * dim * 4, cudaMemcpyDeviceToHost));
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Data-parallel k-means (SURVEY 8e "Build path"): every rank holds a shard of the sample points, the centroids are
+// replicated, and one all-reduce per iteration sums the per-rank [K][dim] coordinate sums and [K] counts (135 MB at
+// K = 2^18, dim 128) -- over NCCL when the communicator came from pb_build_comm_init, or through the in-process shard
+// group (peer copies + a rank-ordered sum, identical on every rank) when it came from pb_build_comm_group.
+// ------------------------------------------------------------------------------------------
+struct pb_build_comm {
+    int device = 0, rank = 0, world = 1;
+    ncclComm_t nccl = nullptr;
+    pb_shard_group *group = nullptr;
+    cudaStream_t stream = nullptr;
+    DevBuf stage;
+};
+
+extern "C" pb_status pb_build_comm_init(const uint8_t *id128, int32_t rank, int32_t world, int32_t device, pb_build_comm **out) {
+    if (!id128 || !out) return pb_fail(PB_ERR_INVALID, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return pb_fail(PB_ERR_INVALID, "bad rank %d / world %d", rank, world);
+    CKS(check_device(device));
+    std::unique_ptr<pb_build_comm> c(new pb_build_comm());
+    c->device = device;
+    c->rank = rank;
+    c->world = world;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (world > 1) {
+        if (!g_nccl.load()) return pb_fail(PB_ERR_COMM, "libnccl.so.2 not found (%s)", dlerror());
+        ncclUniqueId id;
+        memcpy(id.internal, id128, 128);
+        CKN(g_nccl.CommInitRank(&c->nccl, world, id, rank));
+    }
+    *out = c.release();
+    return PB_OK;
+}
+extern "C" pb_status pb_build_comm_group(pb_shard_group *g, int32_t rank, int32_t device, pb_build_comm **out) {
+    if (!g || !out) return pb_fail(PB_ERR_INVALID, "null argument");
+    if (rank < 0 || rank >= g->world) return pb_fail(PB_ERR_INVALID, "bad rank %d / world %d", rank, g->world);
+    CKS(check_device(device));
+    std::unique_ptr<pb_build_comm> c(new pb_build_comm());
+    c->device = device;
+    c->rank = rank;
+    c->world = g->world;
+    c->group = g;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->dev[rank] = device;
+    }
+    *out = c.release();
+    return PB_OK;
+}
+extern "C" void pb_build_comm_destroy(pb_build_comm *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->nccl) g_nccl.CommDestroy(c->nccl);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// in-place sum of `count` floats over the ranks; the result is bit-identical on every rank
+static pb_status build_allreduce(pb_build_comm *c, float *buf, size_t count) {
+    if (c->world == 1) return PB_OK;
+    if (c->nccl) {
+        CKN(g_nccl.AllReduce(buf, buf, count, PB_NCCL_FLOAT32, PB_NCCL_SUM, c->nccl, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return PB_OK;
+    }
+    pb_shard_group *g = c->group;
+    CKS(c->stage.ensure((size_t)c->world * count * 4));
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    g->send[c->rank] = buf;
+    if (e != cudaSuccess || !g->barrier()) {
+        g->fail();
+        return pb_fail(PB_ERR_COMM, "shard group: a peer failed or timed out");
+    }
+    for (int p = 0; p < g->world && e == cudaSuccess; ++p)
+        e = cudaMemcpyPeerAsync(c->stage.as<float>() + (size_t)p * count, c->device, g->send[p], g->dev[p], count * 4, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess || !g->barrier()) {  // everyone has read every buffer: they may be overwritten now
+        g->fail();
+        return pb_fail(PB_ERR_COMM, "shard group all-reduce failed");
+    }
+    k_sum_ranks<<<c->stage.cap ? 296 : 1, 256, 0, c->stream>>>(c->stage.as<float>(), c->world, (long long)count, buf);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return PB_OK;
+}
+
+extern "C" pb_status pb_kmeans_fit_dp(pb_build_comm *c, const float *samples, int64_t n_local, int32_t dim, int64_t K,
+                                      int32_t niters, uint64_t seed, float *out_centroids) {
+    if (!c || (!samples && n_local) || !out_centroids) return pb_fail(PB_ERR_INVALID, "null argument");
+    if (n_local < 0 || K <= 0) return pb_fail(PB_ERR_INVALID, "bad sizes");
+    if (!dim_supported(dim)) return pb_fail(PB_ERR_UNSUPPORTED, "embedding_dim %d not built (32/64/96/128/256)", dim);
+    CK(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    const int sms = prop.multiProcessorCount;
+    const long long n = n_local;
+    // rank r seeds centroids [k0, k1) with distinct points of its shard; one all-reduce of the zero-padded table
+    // gives every rank the same start
+    const long long k0 = K * c->rank / c->world, k1 = K * (c->rank + 1) / c->world, kmine = k1 - k0;
+    if (kmine > n) return pb_fail(PB_ERR_INVALID, "rank %d holds %lld points but seeds %lld centroids", c->rank, n, kmine);
+    DevBuf dX, dC, dbias, dcodes, dacc, didx;
+    CKS(upload(dX, samples, (size_t)std::max<long long>(n, 1) * dim * 4, PB_MEM_HOST));
+    CKS(dC.ensure((size_t)K * dim * 4));
+    CKS(dbias.ensure((size_t)K * 4));
+    CKS(dcodes.ensure((size_t)std::max<long long>(n, 1) * 4));
+    CKS(dacc.ensure((size_t)K * (dim + 1) * 4));  // [K][dim] sums followed by [K] counts: one all-reduce
+    std::vector<long long> perm((size_t)n);
+    for (long long i = 0; i < n; ++i) perm[i] = i;
+    uint64_t s = (seed + 0x9e3779b97f4a7c15ull * (uint64_t)(c->rank + 1)) * 6364136223846793005ull + 1442695040888963407ull;
+    for (long long i = 0; i < kmine; ++i) {
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        long long j = i + (long long)((s >> 11) % (uint64_t)(n - i));
+        std::swap(perm[i], perm[j]);
+    }
+    CK(cudaMemsetAsync(dC.p, 0, (size_t)K * dim * 4, c->stream));
+    if (kmine > 0) {
+        CKS(upload(didx, perm.data(), (size_t)kmine * 8, PB_MEM_HOST));
+        k_gather_rows<<<sms * 4, 256, 0, c->stream>>>(dX.as<float>(), didx.as<long long>(), kmine, dim, dC.as<float>() + (size_t)k0 * dim);
+        CK(cudaGetLastError());
+    }
+    CKS(build_allreduce(c, dC.as<float>(), (size_t)K * dim));
+    float *sums = dacc.as<float>(), *counts = dacc.as<float>() + (size_t)K * dim;
+    for (int it = 0; it < niters; ++it) {
+        k_half_sqnorm<<<sms * 4, 256, 0, c->stream>>>(dC.as<float>(), K, dim, dbias.as<float>());
+        CKS(launch_assign(dim, sms, dX.as<float>(), n, dC.as<float>(), K, dbias.as<float>(), nullptr, dcodes.as<uint32_t>(), c->stream));
+        CK(cudaMemsetAsync(dacc.p, 0, (size_t)K * (dim + 1) * 4, c->stream));
+        if (n > 0) k_accumulate<<<sms * 8, 256, 0, c->stream>>>(dX.as<float>(), n, dim, dcodes.as<uint32_t>(), sums, counts);
+        CK(cudaGetLastError());
+        CKS(build_allreduce(c, dacc.as<float>(), (size_t)K * (dim + 1)));
+        k_update_centroids<<<sms * 4, 256, 0, c->stream>>>(dC.as<float>(), K, dim, sums, counts);
+        CK(cudaGetLastError());
+    }
+    k_normalize_rows<<<sms * 4, 256, 0, c->stream>>>(dC.as<float>(), K, dim);  // kmeans.rs:415-419
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_centroids, dC.p, (size_t)K * dim * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return PB_OK;
 }
 

@@ -549,3 +549,12 @@ __global__ void k_column_abs_mean(const float *__restrict__ R, long long n, int 
     for (long long r = 0; r < n; ++r) acc += (double)fabsf(R[(size_t)r * dim + j]);
     out[j] = n > 0 ? (float)(acc / (double)n) : 0.0f;
 }
+
+// out[i] = stage[0][i] + stage[1][i] + ... in rank order (the in-process all-reduce: identical bits on every rank)
+__global__ void k_sum_ranks(const float *__restrict__ stage, int world, long long count, float *__restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        float acc = stage[i];
+        for (int r = 1; r < world; ++r) acc += stage[(size_t)r * count + i];
+        out[i] = acc;
+    }
+}

@@ -82,7 +82,7 @@ EXPORTS = [
     "pb_codec_open", "pb_codec_close", "pb_codec_compress_into_codes", "pb_codec_compress_and_residuals",
     "pb_codec_encode_chunk", "pb_kmeans_fit", "pb_codec_train", "pb_kmeans_num_sample_docs",
     "pb_kmeans_num_partitions", "pb_codec_num_sample_docs", "pb_codec_heldout_tokens", "pb_create_index",
-    "pb_create_params_default", "pb_codec_last_assign_stats", "pb_codec_find_outliers",
+    "pb_create_params_default", "pb_build_comm_init", "pb_build_comm_group", "pb_build_comm_destroy", "pb_kmeans_fit_dp", "pb_codec_last_assign_stats", "pb_codec_find_outliers",
 ]
 
 _lib = None
@@ -154,6 +154,11 @@ def load_library():
         L.pb_create_index.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_char_p, C.c_void_p]
         L.pb_create_params_default.argtypes = [C.c_void_p]
         L.pb_create_params_default.restype = None
+        L.pb_build_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        L.pb_build_comm_group.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.pb_build_comm_destroy.argtypes = [C.c_void_p]
+        L.pb_build_comm_destroy.restype = None
+        L.pb_kmeans_fit_dp.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_void_p]
         L.pb_comm_unique_id.argtypes = [C.c_void_p]
         L.pb_index_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.pb_shard_group_create.argtypes = [C.c_int32, C.c_void_p]
@@ -526,6 +531,56 @@ def create_index(embeddings: Sequence[np.ndarray], index_dir: str, nbits: int = 
     h = C.c_void_p()
     _check(L.pb_create_index(_ptr(flat), _ptr(dl), len(dl), flat.shape[1], C.byref(p), index_dir.encode(), C.byref(h)))
     return MmapIndex(h.value)
+
+
+def kmeans_fit_dp(shards: Sequence[np.ndarray], K: int, niters: int = 4, seed: int = 42, device: int = 0,
+                  nccl: Optional[tuple] = None) -> np.ndarray:
+    """pb_kmeans_fit_dp.  Without `nccl`: the shards are fitted by len(shards) host threads of this process through an
+    in-process shard group (all on `device`); with nccl = (unique_id, rank, world) the single shard shards[0] is this
+    rank's part of an NCCL job.  Returns the centroids (identical on every rank)."""
+    L = load_library()
+    dim = shards[0].shape[1]
+    if nccl is not None:
+        uid, rank, world = nccl
+        buf = np.frombuffer(bytes(uid), np.uint8).copy()
+        h = C.c_void_p()
+        _check(L.pb_build_comm_init(_ptr(buf), rank, world, device, C.byref(h)))
+        x = np.ascontiguousarray(shards[0], np.float32)
+        out = np.zeros((K, dim), np.float32)
+        try:
+            _check(L.pb_kmeans_fit_dp(h, _ptr(x), x.shape[0], dim, K, niters, seed, _ptr(out)))
+        finally:
+            L.pb_build_comm_destroy(h)
+        return out
+    import threading
+    G = len(shards)
+    g = C.c_void_p()
+    _check(L.pb_shard_group_create(G, C.byref(g)))
+    outs, errs = [None] * G, [None] * G
+
+    def run(r):
+        try:
+            h = C.c_void_p()
+            _check(L.pb_build_comm_group(g, r, device, C.byref(h)))
+            x = np.ascontiguousarray(shards[r], np.float32)
+            out = np.zeros((K, dim), np.float32)
+            try:
+                _check(L.pb_kmeans_fit_dp(h, _ptr(x), x.shape[0], dim, K, niters, seed, _ptr(out)))
+            finally:
+                L.pb_build_comm_destroy(h)
+            outs[r] = out
+        except Exception as e:      # noqa: BLE001 - re-raised below
+            errs[r] = e
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(G)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    L.pb_shard_group_destroy(g)
+    for e in errs:
+        if e is not None:
+            raise e
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0]), "ranks disagree on the centroids"
+    return outs[0]
 
 
 def kmeans_sizing(num_documents: int, avg_sample_doclen: float, num_sample_tokens: int, num_embeddings: int) -> dict:

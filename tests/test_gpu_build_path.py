@@ -208,3 +208,28 @@ def test_adopted_device_residuals_are_used_in_place(oracle, npb):
             assert r.passage_ids.tolist() == w.passage_ids.tolist() and np.array_equal(r.scores, w.scores)
     finally:
         gpu.close()
+
+
+def test_data_parallel_kmeans_over_an_in_process_group(oracle, npb):
+    # SURVEY 8e "Build path": sample points sharded over ranks, centroids replicated, one all-reduce of the
+    # [K][dim] sums + [K] counts per iteration.  Ranks = host threads of this process on one GPU (the NCCL
+    # transport runs the same kernels, tests/gpu_sharded_check.py).  k-means is parity-unpinned: the checks are
+    # that every rank ends with the same unit-norm centroids, that well-separated blobs are recovered, and that the
+    # clustering is as tight as the single-GPU fit's.
+    rng = np.random.default_rng(3)
+    dim, n_blobs = 64, 48
+    centers = rng.standard_normal((n_blobs, dim)).astype(np.float32)
+    centers /= np.linalg.norm(centers, axis=1, keepdims=True)
+    pts = centers[rng.integers(0, n_blobs, 24_000)] + 0.05 * rng.standard_normal((24_000, dim)).astype(np.float32)
+    pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+
+    def inertia(c):
+        return float((1.0 - (pts @ c.T).max(1)).mean())
+    single = npb.kmeans_fit(pts, n_blobs, niters=8, seed=5)
+    for G in (2, 3):
+        shards = np.array_split(pts, G)
+        c = npb.kmeans_fit_dp(shards, n_blobs, niters=8, seed=5)        # asserts that the ranks agree bit for bit
+        assert c.shape == (n_blobs, dim) and np.abs(np.linalg.norm(c, axis=1) - 1.0).max() < 1e-5
+        assert inertia(c) <= 1.5 * inertia(single) + 1e-3
+        found = (centers @ c.T).max(1)
+        assert (found > 0.98).mean() >= 0.8          # most blobs have their own centroid (random init may merge a few)
