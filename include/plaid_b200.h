@@ -212,8 +212,7 @@ enum {
 
 /* Diagnostic switch for the approximate stage (default on): 1 = two-pass (16-bit first pass +
  * exact re-check of the docs that can still make the cut), 0 = single exact pass over every
- * candidate, 2 = two-pass behind an upper-bound pruning cascade (experimental, off by default).
- * All three produce the reference's cut bit for bit; tests compare them. */
+ * candidate.  Both produce the reference's cut bit for bit; tests compare them. */
 PB_API void pb_set_fast_approx(pb_index *ix, int32_t enabled);
 
 /* Diagnostic switch for the exact stage (default on): 1 = an fp16 tcgen05 estimate with a certified error bound

@@ -240,7 +240,7 @@ struct Workspace {
     cudaEvent_t kev[2 * PB_KERNEL_COUNT] = {};  // begin / end around the main kernel of a stage
     cudaEvent_t call_ev[2] = {};                // around a whole search call
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
-        exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2, cand3, ncand3, ub, theta, rel, cellbits,
+        exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2,  cellbits,
         gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc;
     HostBuf hq, hres, hcounts;
     pb_status init() {
@@ -287,8 +287,6 @@ struct pb_index {
     bool build_ivf = false;    // no inverted file was given: built from the codes at finalize (index.rs:850-873)
     float cmax = 1.0f;         // largest centroid L2 norm (range of the 16-bit score table)
     bool fast_approx = true;   // two-pass approximate stage (exact cut either way)
-    bool cascade = false;      // upper-bound pruning in front of it (PB_CASCADE=1): exact, but only pays when
-                               // the cut sits well above the background score level
     bool k1_tc = true;         // a2 on the tensor cores (k_scores16_tc) with its certified consumers: the default;
                                // PB_K1_TC=0 keeps every sub-batch on the exact fp32 kernel (the device-gated fallback)
     int k1_margin = 1;         // E: code units an estimate-built 16-bit code may differ from the exact one (PB_K1_TC_E widens it)
@@ -572,7 +570,6 @@ pb_status pb_index_finalize(pb_index *ix) {
         CK(cudaMemcpy(&m2, mx.p, 4, cudaMemcpyDeviceToHost));
         ix->cmax = sqrtf(m2);
         if (const char *e = getenv("PB_FAST_APPROX")) ix->fast_approx = atoi(e) != 0;
-        if (const char *e = getenv("PB_CASCADE")) ix->cascade = atoi(e) != 0;
         if (const char *e = getenv("PB_FAST_EXACT")) ix->fast_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
         if (const char *e = getenv("PB_FMA2_EXACT")) ix->fma2_exact = atoi(e) != 0;
@@ -691,8 +688,7 @@ extern "C" void pb_search_params_default(pb_search_params *p) {  // search.rs:58
 
 extern "C" void pb_set_fast_approx(pb_index *ix, int32_t enabled) {
     if (!ix) return;
-    ix->fast_approx = enabled != 0;  // 0 = single exact pass, 1 = two-pass, 2 = two-pass behind the pruning cascade
-    ix->cascade = enabled == 2;
+    ix->fast_approx = enabled != 0;  // 0 = single exact pass over every candidate, otherwise two-pass
 }
 extern "C" void pb_set_scores_tc(pb_index *ix, int32_t enabled) {
     if (ix) ix->k1_tc = enabled != 0;  // effective when the tensor-core operands were built at open (k1_tc_usable)
@@ -1169,9 +1165,9 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         int *L = g_stats.launches;
         const bool fast = ix->fast_approx && !io.trace;  // trace wants every candidate's exact approx score
         // the score table comes from the tensor cores unless something needs the dense fp32 S (an eligibility filter,
-        // the radix-select probe, the cascade, a trace) or the shape is outside the kernel's (DESIGN.md "a2")
+        // the radix-select probe, a trace) or the shape is outside the kernel's (DESIGN.md "a2")
         const int n_chunks_k = (int)((ix->K + 1023) / 1024);
-        const bool want_tc = k1_tc_usable(ix) && fast && !ix->k1_diag && !ix->cascade && !all_eligible && !big_probe && !d_elig &&
+        const bool want_tc = k1_tc_usable(ix) && fast && !ix->k1_diag && !all_eligible && !big_probe && !d_elig &&
                              QS / 8 <= 32 && n_chunks_k >= n_probe && n_probe <= 64;
         // One pass over the sub-batch.  use_tc: a flagged query or a probe-list overflow raises a device flag instead of
         // being read back mid-way; the pass then finishes on (memory-safe) garbage and *redo asks for the exact pass.
@@ -1329,43 +1325,10 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             const uint32_t *list = ws.cand.as<uint32_t>();
             const int *list_n = ws.ncand.as<int>();
             unsigned long long *cnt = ws.counters.as<unsigned long long>();
-            const size_t rel_bytes = (size_t)Wk * 4;
-            const bool cascade = ix->cascade && rel_bytes <= 200 * 1024;
-            if (cascade) {
-                // pruning cascade: certified upper bound first, 16-bit sums only where it matters
-                CKS(ws.cand3.ensure((size_t)B * ix->D * 4));
-                CKS(ws.ncand3.ensure((size_t)B * 4 + 16));
-                CKS(ws.ub.ensure((size_t)B * ix->D * 4));
-                CKS(ws.theta.ensure((size_t)B * 4 + 16));
-                CKS(ws.rel.ensure((size_t)B * rel_bytes));
-                k_theta16<<<B, 1024, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ws.theta.as<uint32_t>());
-                k_relevant_bits<<<dim3((unsigned)((Wk + 7) / 8), B), 256, 0, ws.stream>>>(
-                    st16, ws.qoff.as<int>(), ix->K, QS, ws.theta.as<uint32_t>(), ws.rel.as<uint32_t>(), Wk);
-                CKS(set_smem(k_approx_ub, rel_bytes));
-                k_approx_ub<<<ga, 256, rel_bytes, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
-                                                               ix->udoc_off.as<long long>(), list, ix->D, list_n,
-                                                               ws.theta.as<uint32_t>(), ws.rel.as<uint32_t>(), Wk,
-                                                               ws.ub.as<uint32_t>(), cnt);
-                // S' = top 2M by upper bound
-                k_select_u32<<<B, 1024, 0, ws.stream>>>(ws.ub.as<uint32_t>(), list_n, 2 * M, 0, ws.ub.as<uint32_t>(), list,
-                                                        list_n, ix->D, ws.qoff.as<int>(), ws.qflag.as<int>(),
-                                                        ws.cand2.as<uint32_t>(), ws.ncand2.as<int>());
-                (ix->approx_cg ? k_approx16<true> : k_approx16<false>)<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
-                                                      ix->udoc_off.as<long long>(), ws.cand2.as<uint32_t>(), ix->D,
-                                                      ws.ncand2.as<int>(), ws.lsum.as<uint32_t>(), cnt + B + 1);
-                // list2 = every candidate whose upper bound reaches tau' - W
-                k_select_u32<<<B, 1024, 0, ws.stream>>>(ws.lsum.as<uint32_t>(), ws.ncand2.as<int>(), M, 4, ws.ub.as<uint32_t>(),
-                                                        list, list_n, ix->D, ws.qoff.as<int>(), ws.qflag.as<int>(),
-                                                        ws.cand3.as<uint32_t>(), ws.ncand3.as<int>());
-                CK(cudaGetLastError());
-                L[PB_STAGE_APPROX] += 6;
-                list = ws.cand3.as<uint32_t>();
-                list_n = ws.ncand3.as<int>();
-            }
             KEV_BEGIN(PB_KERNEL_APPROX16);
             (ix->approx_cg ? k_approx16<true> : k_approx16<false>)<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
                                                   ix->udoc_off.as<long long>(), list, ix->D, list_n, ws.lsum.as<uint32_t>(),
-                                                  cascade ? cnt + B + 1 : cnt);
+                                                  cnt);
             KEV_END(PB_KERNEL_APPROX16);
             // band per query token in code units (W = band * nq + 8).  Exact table: +-1 code of rounding per token and side
             // plus the fp32 summation error -> 4.  Estimate table (k_scores_tc.cuh): W = nq (1.004 + 2 err) + nq^2/256 + 4

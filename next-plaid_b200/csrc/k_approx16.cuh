@@ -1,4 +1,4 @@
-// k_approx16.cuh -- a5 two-pass form: 16-bit first pass, band select, pruning cascade.
+// k_approx16.cuh -- a5 two-pass form: 16-bit first pass, band select.
 // Part of kernels.cuh (included from there, in order; not a standalone header).
 // ------------------------------------------------------------------------------------------
 // a5, two-pass form.  The approximate score only decides WHICH docs make the cut (search.rs:460-469),
@@ -163,7 +163,7 @@ k_approx16(const unsigned short *__restrict__ ST16, const int *__restrict__ q_of
     if (lane == 0 && my_tokens) atomicAdd(tok_counter, my_tokens);
 }
 
-// Generic "N-th largest with a band" selection used by the pruning cascade.  Per query:
+// "N-th largest with a band" selection.  Per query:
 //   tau = N-th largest of sel_keys[0..sel_n) (0 when sel_n < N or the query is flagged),
 //   thr = tau - (band_per_q * nq + 8) (0 when band_per_q < 0 ... see callers), and the output is every
 //   entry of filt_list whose filt_key >= thr (unordered).  grid = B, 1024 threads.
@@ -231,134 +231,3 @@ k_select_u32(const uint32_t *__restrict__ sel_keys, const int *__restrict__ sel_
     if (threadIdx.x == 0) out_n[b] = fill_s;
 }
 
-// ------------------------------------------------------------------------------------------
-// Pruning cascade in front of the approximate score (DESIGN.md "a5").  Bound per query: with
-// REL = {c : max_q code16(S[q,c]) >= theta16}, every centroid outside REL scores below theta on every
-// query token, so  code16(max_t S[q,code_t]) <= max(theta16, max over the doc's REL codes)  and the
-// sum over q, ub16(doc), is >= the exact 16-bit code sum lsum(doc) of k_approx16.  ub16 needs row
-// gathers only for the doc's REL codes (a per-query bitmap test in shared memory picks them).
-//   1. ub16 for every candidate                         (k_theta16, k_relevant_bits, k_approx_ub)
-//   2. S' = top 2M by ub16; lsum on S'; tau' = M-th largest (a lower bound of the true tau)
-//   3. list2 = {ub16 >= tau' - W} (superset of everything k_select on full lsum would keep)
-//   4. lsum on list2, tau = M-th largest, list3 = {lsum >= tau - W}; exact fp32 pass on list3
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_theta16(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
-          uint32_t *__restrict__ theta16) {
-    __shared__ int hist[4096];
-    const int b = blockIdx.x;
-    const int nq = q_off[b + 1] - q_off[b];
-    for (int i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const long long stride = max(1ll, K / 32768);  // a sample of <= 32k centroids fixes the efficiency knob
-    const unsigned short *STb = ST16 + (size_t)b * K * QS;
-    int n_samples = 0;
-    for (long long c = (long long)w * stride; c < K; c += (long long)nw * stride) {
-        uint32_t m = 0;
-        for (int q = lane; q < nq; q += 32) m = max(m, (uint32_t)STb[(size_t)c * QS + q]);
-        m = __reduce_max_sync(PB_FULL, m);
-        if (lane == 0) atomicAdd(&hist[m >> 4], 1);
-        ++n_samples;
-    }
-    __shared__ int total_s;
-    if (threadIdx.x == 0) total_s = 0;
-    __syncthreads();
-    if (lane == 0) atomicAdd(&total_s, n_samples);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int target = max(1, total_s / 128);  // ~0.8 % of the centroids count as relevant
-        int cum = 0, bin = 4095;
-        for (; bin > 0; --bin) {
-            cum += hist[bin];
-            if (cum >= target) break;
-        }
-        theta16[b] = max(1u, (uint32_t)bin << 4);
-    }
-}
-
-// bit c of rel[b] = any query token scores >= theta16 on centroid c.  grid = (ceil(K/256), B), 256 thr.
-__global__ void __launch_bounds__(256)
-k_relevant_bits(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
-                const uint32_t *__restrict__ theta16, uint32_t *__restrict__ rel, long long Wk) {
-    const int b = blockIdx.y;
-    const int nq = q_off[b + 1] - q_off[b];
-    const int lane = threadIdx.x & 31;
-    const long long word = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (word >= Wk) return;
-    const uint32_t th = theta16[b];
-    const unsigned short *STb = ST16 + (size_t)b * K * QS;
-    uint32_t bits = 0;
-    for (int j = 0; j < 32; ++j) {
-        const long long c = word * 32 + j;
-        if (c >= K) break;
-        uint32_t m = 0;
-        for (int q = lane; q < nq; q += 32) m = max(m, (uint32_t)STb[(size_t)c * QS + q]);
-        if (__any_sync(PB_FULL, m >= th)) bits |= 1u << j;
-    }
-    if (lane == 0) rel[(size_t)b * Wk + word] = bits;
-}
-
-// ub16 of every candidate.  grid = (blocks, B), 256 threads, dynamic smem = Wk*4 bytes (the bitmap).
-__global__ void __launch_bounds__(256)
-k_approx_ub(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
-            const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off,
-            const uint32_t *__restrict__ cand, long long cand_cap, const int *__restrict__ n_cand,
-            const uint32_t *__restrict__ theta16, const uint32_t *__restrict__ rel, long long Wk,
-            uint32_t *__restrict__ ub, unsigned long long *__restrict__ tok_counter) {
-    extern __shared__ __align__(16) uint32_t rel_s[];
-    const int b = blockIdx.y;
-    const int nq = q_off[b + 1] - q_off[b];
-    const int n = n_cand[b];
-    for (long long i = threadIdx.x; i < Wk; i += blockDim.x) rel_s[i] = rel[(size_t)b * Wk + i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
-    const unsigned short *STb = ST16 + (size_t)b * K * QS;
-    const uint32_t th = theta16[b];
-    unsigned long long my_tokens = 0;
-    int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    uint32_t d = 0;
-    long long t0 = 0, t1 = 0;
-    if (i < n) {
-        d = cand[(size_t)b * cand_cap + i];
-        t0 = udoc_off[d];
-        t1 = udoc_off[d + 1];
-    }
-    for (; i < n; i += warps_per_grid) {
-        const int i2 = i + warps_per_grid;
-        uint32_t dn = 0;
-        long long t0n = 0, t1n = 0;
-        if (i2 < n) {
-            dn = cand[(size_t)b * cand_cap + i2];
-            t0n = udoc_off[dn];
-            t1n = udoc_off[dn + 1];
-        }
-        my_tokens += (unsigned long long)(t1 - t0);
-        uint32_t total = 0;
-        for (int qc = 0; qc < nq; qc += 32) {
-            const int q = qc + lane;
-            const unsigned short *col = STb + (q < nq ? q : 0);
-            uint32_t m = th;  // every non-relevant code scores below theta16 on every query token
-            for (long long t = t0; t < t1; t += 32) {
-                const uint32_t code = (t + lane < t1) ? ucodes[t + lane] : 0xffffffffu;
-                bool hit = false;
-                if (code != 0xffffffffu) hit = (rel_s[code >> 5] >> (code & 31)) & 1u;
-                unsigned mask = __ballot_sync(PB_FULL, hit);
-                while (mask) {
-                    const int j = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const uint32_t cj = __shfl_sync(PB_FULL, code, j);
-                    m = max(m, (uint32_t)col[(size_t)cj * QS]);
-                }
-            }
-            if (q >= nq) m = 0;
-            total += __reduce_add_sync(PB_FULL, m);
-        }
-        if (lane == 0) ub[(size_t)b * cand_cap + i] = total;
-        d = dn;
-        t0 = t0n;
-        t1 = t1n;
-    }
-    if (lane == 0 && my_tokens) atomicAdd(tok_counter, my_tokens);
-}

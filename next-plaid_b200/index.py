@@ -444,7 +444,7 @@ class MmapIndex:
 
     # -- measurement hooks -------------------------------------------------------------------------
     def set_fast_approx(self, mode):
-        """0/False = single exact pass, 1/True = two-pass (default), 2 = two-pass + pruning cascade."""
+        """0/False = single exact pass over every candidate, 1/True = two-pass (default)."""
         load_library().pb_set_fast_approx(self._h, int(mode))
 
     def set_scores_tc(self, on: bool):

@@ -242,10 +242,11 @@ def test_two_pass_approx_equals_single_pass_and_oracle(oracle, npb, corpus):
         fast = gpu.search_batch(qs, pg)
         gpu.set_fast_approx(0)
         slow = gpu.search_batch(qs, pg)
-        gpu.set_fast_approx(2)
-        casc = gpu.search_batch(qs, pg)
+        gpu.set_scores_tc(False)                # two-pass on the exact fp32 table (the tensor-core table's fallback)
         gpu.set_fast_approx(1)
-        for q, f, s, c in zip(qs, fast, slow, casc):
+        mid = gpu.search_batch(qs, pg)
+        gpu.set_scores_tc(True)
+        for q, f, s, c in zip(qs, fast, slow, mid):
             w = oracle.search_one(ix, q, po)
             assert f.passage_ids.tolist() == s.passage_ids.tolist() == c.passage_ids.tolist() == w.passage_ids.tolist(), kw
             assert np.array_equal(f.scores, w.scores) and np.array_equal(s.scores, w.scores) and np.array_equal(c.scores, w.scores)
@@ -267,8 +268,8 @@ def test_two_pass_approx_with_massive_ties_and_odd_ranges(oracle, npb):
                dict(top_k=50, n_full_scores=100, centroid_score_threshold=None, n_ivf_probe=16),
                dict(top_k=5, n_full_scores=20, centroid_score_threshold=0.2)):
         pg, po = _params(npb, oracle, **kw)
-        for mode in (1, 2):
-            gpu.set_fast_approx(mode)
+        for mode in (1, 0):                     # certified paths on the tensor-core table / on the exact table
+            gpu.set_scores_tc(bool(mode))
             for q, r in zip(qs, gpu.search_batch(qs, pg)):
                 w = oracle.search_one(ix, q, po)
                 assert r.passage_ids.tolist() == w.passage_ids.tolist(), (kw, mode)
