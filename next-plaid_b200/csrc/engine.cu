@@ -301,7 +301,9 @@ struct pb_index {
     bool fast_exact = true;    // tcgen05 certified filter in front of the exact stage (same results either way)
     float vmin = 0.0f;         // smallest pre-normalisation token norm |c + w| over the index (error bound of the filter)
     float wmax = 0.0f;         // largest residual norm |w| over the index (same)
-    DevBuf centroids_f16;      // [K][dim] fp16 copy for the filter
+    DevBuf centroids_f16;      // [K][dim] fp16 copy for the filter (k_exact_tc, the variant without a score table)
+    DevBuf tok_inv_norm;       // [N] 1 / |c + w| for the linear filter (k_exact_tc2)
+    bool filter_v1 = false;    // PB_FILTER_V1=1: always the decompressing filter k_exact_tc (A/B measurement)
     bool profiling = false;
     size_t st_budget = (size_t)8 << 30;  // workspace budget of one search call (PB_WS_BUDGET_MB)
     ncclComm_t comm = nullptr;  // doc-sharded deployment: one rank per GPU
@@ -571,6 +573,7 @@ pb_status pb_index_finalize(pb_index *ix) {
         ix->cmax = sqrtf(m2);
         if (const char *e = getenv("PB_FAST_APPROX")) ix->fast_approx = atoi(e) != 0;
         if (const char *e = getenv("PB_FAST_EXACT")) ix->fast_exact = atoi(e) != 0;
+        if (const char *e = getenv("PB_FILTER_V1")) ix->filter_v1 = atoi(e) != 0;
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
         if (const char *e = getenv("PB_FMA2_EXACT")) ix->fma2_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC_DIAG")) ix->k1_diag = atoi(e) != 0;
@@ -588,12 +591,13 @@ pb_status pb_index_finalize(pb_index *ix) {
         CK(cudaGetLastError());
         DevBuf mn;
         CKS(mn.ensure(16));
+        CKS(ix->tok_inv_norm.ensure((size_t)ix->N * 4));  // 1 / |c + w| per token: operand of the linear filter (k_exact_tc2)
         const float init[2] = {3.0e38f, 0.0f};
         CK(cudaMemcpy(mn.p, init, 8, cudaMemcpyHostToDevice));
         switch (ix->dim) {
-            case 64: k_min_vnorm<64><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>()); break;
-            case 96: k_min_vnorm<96><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>()); break;
-            default: k_min_vnorm<128><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>()); break;
+            case 64: k_min_vnorm<64><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>(), ix->tok_inv_norm.as<float>()); break;
+            case 96: k_min_vnorm<96><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>(), ix->tok_inv_norm.as<float>()); break;
+            default: k_min_vnorm<128><<<ix->sm_count * 8, 256>>>(ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->N, mn.as<float>(), ix->tok_inv_norm.as<float>()); break;
         }
         CK(cudaGetLastError());
         if ((ix->k1_diag || ix->k1_tc) && ix->cmax > 0.0f && ix->cmax < 3.0e38f) {
@@ -951,16 +955,37 @@ static float filter_eps_unit(const pb_index *ix) {
     return u + (1.0f + u) * rho / (1.0f - 0.5f * rho) + sub + 4e-5f;
 }
 
+// the same for the linear filter (derivation above k_exact_tc2); E = code error of the score table (0 = exact table)
+static float filter_eps_unit2(const pb_index *ix, int E) {
+    const float u = 1.0f / 2048.0f;
+    const float vmin = ix->vmin * 0.9999f, wmax = ix->wmax * 1.0001f;
+    if (!(vmin > 0.0f) || !(ix->cmax < 3.0e4f) || !(wmax < 3.0e4f)) return 0.0f;
+    const float ds = ((float)E + 1.01f) * 2.0f * ix->cmax * 1.0001f / 65535.0f;
+    const float dw = wmax * (2.0f * u + u * u + 3.0517578e-5f);
+    const float eps = (ds + dw) / vmin + 8e-6f;
+    return eps < 0.05f ? eps : 0.0f;
+}
+
 // a7': tensor-core estimate of every kept doc, then the survivors that can still reach the top_k
 static pb_status launch_filter(pb_index *ix, Workspace &ws, const KeptView &in, const KeptView &out, int B, int QS, int Mcap,
-                               int top_k, long long max_tokens, float eps_unit, int nq_max, int *launches) {
+                               int top_k, long long max_tokens, float eps_unit, int nq_max, bool linear, int *launches) {
     long long chunks = (max_tokens + 127) / 128;
     long long want = std::max<long long>(1, ((long long)ix->sm_count * ix->xtc_grid + B - 1) / B);
     int gx = (int)std::max<long long>(1, std::min<long long>(chunks, want));
     const int nqt = nq_max <= 32 ? 32 : 64;
     const size_t sm = smem_exact_tc(ix->dim, ix->packed, nqt);
 #define PB_TC_LAUNCH(DV, NB)                                                                                           \
-    {                                                                                                                  \
+    if (linear) {                                                                                                      \
+        auto kern = nqt == 32 ? k_exact_tc2<DV, NB, 32> : k_exact_tc2<DV, NB, 64>;                                     \
+        CKS(set_smem(kern, sm));                                                                                       \
+        KEV_BEGIN(PB_KERNEL_FILTER);                                                                                   \
+        kern<<<dim3(gx, B), 128, sm, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS, ws.ST16.as<unsigned short>(), \
+                                                  ix->K, ws.qrange.as<float2>(), ws.qflag.as<int>(), ix->w_rev.as<float>(), \
+                                                  ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(),               \
+                                                  ix->tok_inv_norm.as<float>(), ix->doc_off.as<long long>(), in.kept,  \
+                                                  in.nkept, in.tokp, Mcap, ws.maxkey.as<uint32_t>());                  \
+        KEV_END(PB_KERNEL_FILTER);                                                                                     \
+    } else {                                                                                                           \
         auto kern = nqt == 32 ? k_exact_tc<DV, NB, 32> : k_exact_tc<DV, NB, 64>;                                       \
         CKS(set_smem(kern, sm));                                                                                       \
         KEV_BEGIN(PB_KERNEL_FILTER);                                                                                   \
@@ -1397,7 +1422,10 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         KeptView kv{ws.kept.as<uint32_t>(), ws.nkept.as<int>(), ws.tokp.as<long long>(),
                     sharded ? ws.krank.as<uint32_t>() : nullptr};
         // only the top_k need exact scores: the tensor-core filter drops the docs that provably cannot reach them
-        const float eps_unit = filter_eps_unit(ix);
+        // the linear form needs the 16-bit score table of this pass (a flagged query publishes no estimate and keeps
+        // every doc); without a table (PB_FAST_APPROX=0) the decompressing form estimates from fp16 centroids
+        const bool linear = fast && !ix->filter_v1 && ix->tok_inv_norm.p;
+        const float eps_unit = linear ? filter_eps_unit2(ix, tc ? ix->k1_margin : 0) : filter_eps_unit(ix);
         const bool filt = ix->fast_exact && !io.trace && ix->centroids_f16.p && eps_unit > 0.0f && nq_max <= 64 &&
                           top_k < Mcap && ix->packed % 4 == 0;
         if (filt) {
@@ -1412,7 +1440,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             CK(cudaGetLastError());
             KeptView kv2{ws.kept2.as<uint32_t>(), ws.nkept2.as<int>(), ws.tokp2.as<long long>(), ws.krank2.as<uint32_t>()};
             CKS(launch_filter(ix, ws, kv, kv2, B, QS, Mcap, top_k, (long long)Mcap * std::max(ix->max_doclen, 1), eps_unit,
-                              nq_max, &L[PB_STAGE_EXACT]));
+                              nq_max, linear, &L[PB_STAGE_EXACT]));
             L[PB_STAGE_EXACT] += 1;
             kv = kv2;
             if (!sharded) kv.krank = nullptr;  // survivors keep their order, so position breaks ties the same way

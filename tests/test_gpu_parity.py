@@ -421,3 +421,30 @@ def test_long_queries_keep_the_fast_paths(oracle, npb, corpus, nq):
             w = oracle.search_one(ix, q, po)
             assert r.passage_ids.tolist() == w.passage_ids.tolist(), (kw, nq)
             assert np.array_equal(r.scores, w.scores), (kw, nq)
+
+
+@pytest.mark.parametrize("env", [{"PB_FILTER_V1": "1"}, {"PB_FAST_APPROX": "0"}, {"PB_K1_TC": "0"}, {}])
+def test_both_filter_kernels_and_their_score_tables(oracle, npb, corpus, monkeypatch, env):
+    # the linear filter (k_exact_tc2: centroid score from the 16-bit table + residual part on the tensor cores) on the
+    # tensor-core table (default) and on the exact table (PB_K1_TC=0); the decompressing filter (k_exact_tc) when
+    # forced (PB_FILTER_V1=1) or when there is no table (PB_FAST_APPROX=0)
+    docs, ix, qs, src, _ = corpus
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    gpu = _gpu_index(npb, ix)
+    for k in env:
+        monkeypatch.delenv(k)
+    try:
+        long_q, _ = oracle.synthetic_queries(docs, 3, nq=48, seed=77)
+        batch = qs[:6] + long_q + [qs[6] * 5.0, qs[7][:3]]
+        for kw in (dict(top_k=5, n_full_scores=2048), dict(top_k=40, n_full_scores=400, centroid_batch_size=128)):
+            pg, po = _params(npb, oracle, **kw)
+            res = gpu.search_batch(batch, pg)
+            w = gpu.last_work_counters()
+            assert 0 < w["n_exact_docs"] < w["n_filter_docs"], (env, kw, w)
+            for q, r in zip(batch, res):
+                want = oracle.search_one(ix, q, po)
+                assert r.passage_ids.tolist() == want.passage_ids.tolist(), (env, kw)
+                assert np.array_equal(r.scores, want.scores), (env, kw)
+    finally:
+        gpu.close()
