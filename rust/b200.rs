@@ -42,6 +42,7 @@ impl From<&SearchParameters> for PbSearchParams {
 extern "C" {
     fn pb_index_load(index_dir: *const c_char, device: i32, out: *mut *mut c_void) -> c_int;
     fn pb_index_close(ix: *mut c_void);
+    fn pb_index_embedding_dim(ix: *const c_void) -> i32;
     fn pb_search_batch(
         ix: *mut c_void,
         queries: *const f32,
@@ -91,13 +92,15 @@ impl B200Index {
         params: &SearchParameters,
         subset: Option<&[i64]>,
     ) -> Result<Vec<QueryResult>> {
-        let dim = queries.first().map(|q| q.ncols()).unwrap_or(0);
+        // pb_search_batch has no dim argument and reads rows * embedding_dim floats: reject a query of another
+        // width here, as the Python binding does (Error::Shape, not an out-of-bounds host read)
+        let dim = unsafe { pb_index_embedding_dim(self.handle) } as usize;
         let mut offsets = Vec::with_capacity(queries.len() + 1);
         offsets.push(0i64);
         let mut flat: Vec<f32> = Vec::new();
         for q in queries {
             if q.ncols() != dim {
-                return Err(Error::Shape("queries disagree on embedding_dim".into()));
+                return Err(Error::Shape(format!("query has {} columns, the index embedding_dim is {}", q.ncols(), dim)));
             }
             flat.extend(q.as_standard_layout().iter());
             offsets.push(offsets.last().unwrap() + q.nrows() as i64);
