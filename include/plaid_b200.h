@@ -224,7 +224,7 @@ PB_API void pb_set_fast_exact(pb_index *ix, int32_t enabled);
 /* Diagnostic switch for a2 (default on): 1 = the score table comes from the tcgen05 split-fp16 GEMM (k_scores16_tc) and
  * the values that decide something are recomputed as pinned-order fp32 dots; 0 = the dense fp32 FFMA2 kernel
  * (k_centroid_scores), which is also the device-gated fallback for flagged queries and shapes outside the tensor-core
- * kernel's (dim not in {64, 96, 128}, eligibility filters, effective n_ivf_probe > 64 or > K/1024).  Same results bit
+ * kernel's (dim not in {64, 96, 128}, eligibility filters, the dense variant's radix-select probe for n_ivf_probe > 64, n_ivf_probe > K/1024).  Same results bit
  * for bit; tests and bench.py compare both.  (PB_K1_TC=0 in the environment sets the default.) */
 PB_API void pb_set_scores_tc(pb_index *ix, int32_t enabled);
 

@@ -241,7 +241,7 @@ struct Workspace {
     cudaEvent_t call_ev[2] = {};                // around a whole search call
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2,  cellbits,
-        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc;
+        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc, mslot;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -803,7 +803,7 @@ static pb_status run_k1_tc(pb_index *ix, Workspace &ws, const pb_search_params *
     k_interleave_query_rows<<<dim3(8, B), 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->dim, ws.Qi.as<float>());
     CKS(launch_k1_table(ix, ws, B, QS, ws.ST16.as<unsigned short>(), ws.qflag.as<int>()));
     L[PB_STAGE_CENTROID_SCORES] += 4;
-    const int cap = n * std::max(1, 128 / n);
+    const int cap = n * std::max(2, 128 / n);
     const int cells_cap = (int)std::min<long long>((long long)QS * n, ix->K);
     CKS(ws.cmax16.ensure((size_t)B * n_chunks * QS * 2));
     CKS(ws.tau16.ensure((size_t)B * QS * 4));
@@ -1068,8 +1068,6 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
     const int Mcap = std::max(M, 1);
     const bool batched = p->centroid_batch_size > 0 && ix->K > p->centroid_batch_size;  // search.rs:337
     const bool sharded = ix->world > 1;
-    if (sharded && (long long)ix->world * M > 16384)
-        return pb_fail(PB_ERR_UNSUPPORTED, "shards x kept docs = %lld exceeds 16384", (long long)ix->world * M);
     if (sharded && io.has_subset && !batched)
         return pb_fail(PB_ERR_UNSUPPORTED, "subset with the dense variant needs the global eligible-centroid set; "
                                             "not built for doc-sharded indices");
@@ -1154,11 +1152,12 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             else n_probe = (int)scaled;
         }
     }
-    // effective n_ivf_probe beyond the streaming lists: row-wise radix select (dense variant only; the
-    // batched variant's heap-order threshold rule is tied to the streaming formulation)
-    const bool big_probe = !all_eligible && n_probe > 64;
+    // effective n_ivf_probe beyond 64: the dense variant switches to a row-wise radix select; the batched variant's
+    // heap-order threshold rule is tied to the streaming formulation, whose per-lane lists hold up to 192 entries
+    const int stream_max = batched ? 192 : 64;
+    const bool big_probe = !all_eligible && n_probe > stream_max;
     if (big_probe && batched)
-        return pb_fail(PB_ERR_UNSUPPORTED, "n_ivf_probe %d > 64 with the batched variant is not built", n_probe);
+        return pb_fail(PB_ERR_UNSUPPORTED, "n_ivf_probe %d > 192 with the batched variant is not built", n_probe);
 
     // ---- sub-batching: bound the transposed score matrix ----
     int nq_max_all = 0;
@@ -1193,7 +1192,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         // the radix-select probe, a trace) or the shape is outside the kernel's (DESIGN.md "a2")
         const int n_chunks_k = (int)((ix->K + 1023) / 1024);
         const bool want_tc = k1_tc_usable(ix) && fast && !ix->k1_diag && !all_eligible && !big_probe && !d_elig &&
-                             QS / 8 <= 32 && n_chunks_k >= n_probe && n_probe <= 64;
+                             QS / 8 <= 32 && n_chunks_k >= n_probe && n_probe <= 192;
         // One pass over the sub-batch.  use_tc: a flagged query or a probe-list overflow raises a device flag instead of
         // being read back mid-way; the pass then finishes on (memory-safe) garbage and *redo asks for the exact pass.
         auto run_sub = [&](const bool use_tc, bool *redo) -> pb_status {
@@ -1279,11 +1278,11 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             // threshold-first selection on the 16-bit table when there is one (k_chunkmax16 / k_collect16);
             // the per-lane list scan of k_topn_partial otherwise, or when the device raises `fallback`
             const int GQ = QS / 8;
-            const bool thr_path = fast && !d_elig && ix->probe16 && GQ <= 32 && n_chunks >= n && n <= 64;
+            const bool thr_path = fast && !d_elig && ix->probe16 && GQ <= 32 && n_chunks >= n && n <= 192;
             int *d_fallback = nullptr;
             probe_list_only = !thr_path;
             if (thr_path) {
-                const int cap = n * std::max(1, 128 / n);
+                const int cap = n * std::max(2, 128 / n);
                 CKS(ws.cmax16.ensure((size_t)B * n_chunks * QS * 2));
                 CKS(ws.tau16.ensure((size_t)B * QS * 4));
                 CKS(ws.plist.ensure((size_t)B * QS * cap * 8));
@@ -1403,13 +1402,10 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             CKS(ws.gkeys.ensure((size_t)G * B * M * 8));
             CKS(ws.krank.ensure((size_t)B * Mcap * 4));
             CKS(shard_allgather(ix, ws.stream, ws.lkeys.p, ws.gkeys.p, (size_t)B * M));
-            int Pg = 1;
-            while (Pg < G * M) Pg <<= 1;
-            CKS(set_smem(k_merge_cut, (size_t)Pg * 8));
-            k_merge_cut<<<B, 1024, (size_t)Pg * 8, ws.stream>>>(ws.gkeys.as<u64>(), G, B, M, (uint32_t)ix->doc_id_base, ix->D,
-                                                                ix->doc_off.as<long long>(), ws.kept.as<uint32_t>(),
-                                                                ws.krank.as<uint32_t>(), ws.nkept.as<int>(),
-                                                                ws.tokp.as<long long>(), ws.counters.as<long long>() + 1);
+            k_merge_cut<<<B, 1024, 0, ws.stream>>>(ws.gkeys.as<u64>(), G, ix->rank, B, M, (uint32_t)ix->doc_id_base, ix->D,
+                                                   ix->doc_off.as<long long>(), ws.kept.as<uint32_t>(),
+                                                   ws.krank.as<uint32_t>(), ws.nkept.as<int>(),
+                                                   ws.tokp.as<long long>(), ws.counters.as<long long>() + 1);
             CK(cudaGetLastError());
             L[PB_STAGE_CUT] += 2;
         }
@@ -1480,11 +1476,10 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             CKS(ws.gpayload.ensure((size_t)G * B * M * 8));
             CKS(shard_allgather(ix, ws.stream, ws.fkeys.p, ws.gfkeys.p, (size_t)B * M));
             CKS(shard_allgather(ix, ws.stream, ws.payload.p, ws.gpayload.p, (size_t)B * M));
-            int Pg = 1;
-            while (Pg < G * M) Pg <<= 1;
-            size_t sm = (size_t)Pg * 8 + (size_t)M * 8;
-            CKS(set_smem(k_merge_topk, sm));
-            k_merge_topk<<<B, 1024, sm, ws.stream>>>(ws.gfkeys.as<u64>(), ws.gpayload.as<u64>(), G, B, M, top_k, d_ids, d_sc, d_cn);
+            CKS(ws.mslot.ensure((size_t)B * Mcap * 4));
+            CKS(set_smem(k_merge_topk, (size_t)Pm * 8));
+            k_merge_topk<<<B, 1024, (size_t)Pm * 8, ws.stream>>>(ws.gfkeys.as<u64>(), ws.gpayload.as<u64>(), G, B, M, top_k,
+                                                                ws.mslot.as<uint32_t>(), d_ids, d_sc, d_cn);
             CK(cudaGetLastError());
             L[PB_STAGE_TOPK] += 3;
         } else {

@@ -96,38 +96,40 @@ k_cells_filter_list(const uint32_t *__restrict__ list, const int *__restrict__ l
 // global cut and exact-scores only its own members, then the exact triples are exchanged and merged
 // with the stable-sort rule of search.rs:496.  Both kernels: grid = B, 1024 threads.
 // ------------------------------------------------------------------------------------------
+// k_merge_cut: every shard's list is sorted (best first) and keys are unique (global doc id in the low word), so the
+// global rank of my j-th entry is j + the number of smaller keys in every other shard's list (one binary search
+// each); it is in the global cut iff that rank < M.  No sort, no shared memory: any number of shards.
 __global__ void __launch_bounds__(1024)
-k_merge_cut(const u64 *__restrict__ gkeys, int G, int B, int M, uint32_t doc_id_base, long long D,
+k_merge_cut(const u64 *__restrict__ gkeys, int G, int my_rank, int B, int M, uint32_t doc_id_base, long long D,
             const long long *__restrict__ doc_off, uint32_t *__restrict__ kept, uint32_t *__restrict__ krank,
             int *__restrict__ n_kept, long long *__restrict__ tok_prefix, long long *__restrict__ kept_tokens) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *sk = reinterpret_cast<u64 *>(smem_raw);
     __shared__ int scan_tmp[33];
     const int b = blockIdx.x;
-    const int total = G * M;
-    const int P = next_pow2(max(total, 1));
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        u64 v = ~0ull;
-        if (i < total) {
-            int g = i / M, j = i - g * M;
-            v = gkeys[((size_t)g * B + b) * M + j];
-        }
-        sk[i] = v;
-    }
-    __syncthreads();
-    bitonic_sort_u64(sk, P);
-    // the global cut = first M real keys; mine = those whose doc id falls in [base, base + D)
+    const u64 *mine = gkeys + ((size_t)my_rank * B + b) * M;
     long long run = 0;
     int outn = 0;
     for (int base = 0; base < M; base += blockDim.x) {
-        const int i = base + threadIdx.x;
+        const int j = base + threadIdx.x;
         int f = 0, len = 0;
-        uint32_t d = 0;
-        if (i < M && sk[i] != ~0ull) {
-            const long long gd = (long long)(uint32_t)sk[i] - (long long)doc_id_base;
-            if (gd >= 0 && gd < D) {
+        uint32_t d = 0, grank = 0;
+        if (j < M && mine[j] != ~0ull) {
+            const u64 key = mine[j];
+            int r = j;
+            for (int g = 0; g < G && r < M; ++g) {
+                if (g == my_rank) continue;
+                const u64 *lst = gkeys + ((size_t)g * B + b) * M;
+                int lo = 0, hi = M;  // first position with lst[pos] >= key (~0 padding sorts last)
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (lst[mid] < key) lo = mid + 1; else hi = mid;
+                }
+                r += lo;
+            }
+            const long long gd = (long long)(uint32_t)key - (long long)doc_id_base;
+            if (r < M && gd >= 0 && gd < D) {
                 f = 1;
                 d = (uint32_t)gd;
+                grank = (uint32_t)r;
                 len = (int)(doc_off[d + 1] - doc_off[d]);
             }
         }
@@ -136,7 +138,7 @@ k_merge_cut(const u64 *__restrict__ gkeys, int G, int B, int M, uint32_t doc_id_
         const int tpos = block_exclusive_scan(len, scan_tmp, &ttot);
         if (f) {
             kept[(size_t)b * M + outn + pos] = d;
-            krank[(size_t)b * M + outn + pos] = (uint32_t)i;
+            krank[(size_t)b * M + outn + pos] = grank;
             tok_prefix[(size_t)b * (M + 1) + outn + pos] = run + tpos;
         }
         outn += tot;
@@ -149,38 +151,42 @@ k_merge_cut(const u64 *__restrict__ gkeys, int G, int B, int M, uint32_t doc_id_
     }
 }
 
+// k_merge_topk: the global cut has at most M members and every global approximate rank belongs to exactly one shard,
+// so the real entries of all shards fit M slots indexed by rank: sort those (smem = pow2(M) keys), payloads stay in
+// global memory.  `slot` is scratch [B][M] (source position of every rank).
 __global__ void __launch_bounds__(1024)
 k_merge_topk(const u64 *__restrict__ gfkeys, const u64 *__restrict__ gpayload, int G, int B, int M, int top_k,
-             long long *__restrict__ out_ids, float *__restrict__ out_scores, int *__restrict__ out_counts) {
+             uint32_t *__restrict__ slot, long long *__restrict__ out_ids, float *__restrict__ out_scores,
+             int *__restrict__ out_counts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
-    const int total = G * M;
-    const int P = next_pow2(max(total, 1));
-    u64 *sk = reinterpret_cast<u64 *>(smem_raw);  // [P]
-    u64 *pay = sk + P;                            // [M], indexed by global approximate rank
+    const int P = next_pow2(max(M, 1));
+    u64 *sk = reinterpret_cast<u64 *>(smem_raw);  // [P], indexed by global approximate rank before the sort
+    uint32_t *sl = slot + (size_t)b * M;
     __shared__ int n_real;
     if (threadIdx.x == 0) n_real = 0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) sk[i] = ~0ull;
     __syncthreads();
     int mine = 0;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        u64 v = ~0ull;
-        if (i < total) {
-            int g = i / M, j = i - g * M;
-            const size_t src = ((size_t)g * B + b) * M + j;
-            v = gfkeys[src];
-            if (v != ~0ull) {
-                pay[(uint32_t)v] = gpayload[src];  // each global rank belongs to exactly one shard
-                ++mine;
-            }
+    for (int i = threadIdx.x; i < G * M; i += blockDim.x) {
+        const int g = i / M, j = i - g * M;
+        const size_t src = ((size_t)g * B + b) * M + j;
+        const u64 v = gfkeys[src];
+        if (v != ~0ull) {
+            const uint32_t r = (uint32_t)v;  // global approximate rank < M
+            sk[r] = v;
+            sl[r] = (uint32_t)i;
+            ++mine;
         }
-        sk[i] = v;
     }
     if (mine) atomicAdd(&n_real, mine);
     __syncthreads();
     bitonic_sort_u64(sk, P);
     const int cnt = min(top_k, n_real);
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-        const u64 pv = pay[(uint32_t)sk[i]];
+        const uint32_t src = sl[(uint32_t)sk[i]];
+        const int g = (int)(src / (uint32_t)M), j = (int)(src - (uint32_t)g * (uint32_t)M);
+        const u64 pv = gpayload[((size_t)g * B + b) * M + j];
         out_ids[(size_t)b * top_k + i] = (long long)(pv >> 32);
         out_scores[(size_t)b * top_k + i] = __uint_as_float((uint32_t)pv);
     }

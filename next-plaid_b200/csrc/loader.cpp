@@ -5,8 +5,7 @@
 // {i}.codes.npy / {i}.residuals.npy, and uploads chunk by chunk so the host never holds the whole
 // corpus.  The derived caches merged_codes.npy / merged_residuals.npy (mmap.rs:1266,1483) are not
 // needed: their only extra content is the zero padding rows of index.rs:1113-1120.
-// fast-plaid directories (f16 tensors, mmap.rs:1757-1811) are rejected with PB_ERR_UNSUPPORTED;
-// run the reference's one-time conversion first.
+// fast-plaid directories (f16 tensors, i64 ivf_lengths, mmap.rs:1757-1811) load too: widened / narrowed in memory.
 #include "engine_internal.h"
 
 #include <fcntl.h>
@@ -113,6 +112,43 @@ struct Npy {
     }
 };
 
+// IEEE half -> float (fast-plaid directories store their float tensors as <f2, mmap.rs:1757-1811)
+float half_to_float(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 31u, man = h & 1023u;
+    uint32_t bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else {  // subnormal: renormalise
+            int e = -1;
+            uint32_t m = man;
+            do {
+                ++e;
+                m <<= 1;
+            } while (!(m & 1024u));
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((m & 1023u) << 13);
+        }
+    } else if (exp == 31) bits = sign | 0x7f800000u | (man << 13);
+    else bits = sign | ((exp - 15 + 127) << 23) | (man << 13);
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+
+// a float tensor of the directory as f32: <f4 is used in place, <f2 (fast-plaid) is widened into `store`
+pb_status as_f32(const Npy &a, const char *name, std::vector<float> &store, const float **out) {
+    if (a.is("f4")) {
+        *out = (const float *)a.data;
+        return PB_OK;
+    }
+    if (!a.is("f2")) return pb_fail(PB_ERR_IO, "%s must be <f4 (next-plaid) or <f2 (fast-plaid)", name);
+    const long long n = a.count();
+    store.resize((size_t)n);
+    const uint16_t *src = (const uint16_t *)a.data;
+    for (long long i = 0; i < n; ++i) store[(size_t)i] = half_to_float(src[i]);
+    *out = store.data();
+    return PB_OK;
+}
+
 pb_status read_text(const std::string &path, std::string &out) {
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) return pb_fail(PB_ERR_IO, "cannot open %s", path.c_str());
@@ -156,12 +192,26 @@ extern "C" pb_status pb_index_load(const char *index_dir, int32_t device, pb_ind
     if (pb_status s = wts.open(dir + "bucket_weights.npy")) return s;
     if (pb_status s = ivf.open(dir + "ivf.npy")) return s;
     if (pb_status s = ivfl.open(dir + "ivf_lengths.npy")) return s;
-    if (cent.is("f2") || wts.is("f2"))
-        return pb_fail(PB_ERR_UNSUPPORTED, "fast-plaid f16 index: convert with next-plaid first (mmap.rs:1757)");
-    if (!cent.is("f4") || cent.shape.size() != 2) return pb_fail(PB_ERR_IO, "centroids.npy must be <f4 [K, dim]");
-    if (!wts.is("f4")) return pb_fail(PB_ERR_IO, "bucket_weights.npy must be <f4");
+    // fast-plaid directories (mmap.rs:1757-1811 converts them in place on the reference's first load): float tensors
+    // as <f2, ivf_lengths as <i8, residuals described as <u1.  They are read as they are -- widened / narrowed in
+    // memory, which gives the same values as the reference's conversion -- and never modified.
+    std::vector<float> cent_store, wts_store;
+    std::vector<int32_t> ivfl_store;
+    const float *cent_f32 = nullptr, *wts_f32 = nullptr;
+    if (cent.shape.size() != 2) return pb_fail(PB_ERR_IO, "centroids.npy must be [K, dim]");
+    if (pb_status s = as_f32(cent, "centroids.npy", cent_store, &cent_f32)) return s;
+    if (pb_status s = as_f32(wts, "bucket_weights.npy", wts_store, &wts_f32)) return s;
     if (!ivf.is("i8")) return pb_fail(PB_ERR_IO, "ivf.npy must be <i8");
-    if (!ivfl.is("i4")) return pb_fail(PB_ERR_IO, "ivf_lengths.npy must be <i4");
+    const int32_t *ivfl_i32 = (const int32_t *)ivfl.data;
+    if (ivfl.is("i8")) {
+        const int64_t *src = (const int64_t *)ivfl.data;
+        ivfl_store.resize((size_t)ivfl.count());
+        for (long long i = 0; i < ivfl.count(); ++i) {
+            if (src[i] < 0 || src[i] > 0x7fffffffll) return pb_fail(PB_ERR_IO, "ivf_lengths.npy[%lld] out of range", i);
+            ivfl_store[(size_t)i] = (int32_t)src[i];
+        }
+        ivfl_i32 = ivfl_store.data();
+    } else if (!ivfl.is("i4")) return pb_fail(PB_ERR_IO, "ivf_lengths.npy must be <i4 (next-plaid) or <i8 (fast-plaid)");
     const long long K = cent.shape[0];
     const int dim = (int)cent.shape[1];
     const int nb = (int)nbits;
@@ -198,15 +248,15 @@ extern "C" pb_status pb_index_load(const char *index_dir, int32_t device, pb_ind
     d.num_centroids = K;
     d.num_documents = (int64_t)doclens.size();
     d.num_embeddings = N;
-    d.centroids = (const float *)cent.data;
-    d.bucket_weights = (const float *)wts.data;
+    d.centroids = cent_f32;
+    d.bucket_weights = wts_f32;
     d.doc_lengths = doclens.data();
     d.ivf = (const int64_t *)ivf.data;
-    d.ivf_lengths = (const int32_t *)ivfl.data;
+    d.ivf_lengths = ivfl_i32;
     d.device = device;
     d.memory_space = PB_MEM_HOST;
     long long ivf_sum = 0;
-    for (long long i = 0; i < K; ++i) ivf_sum += ((const int32_t *)ivfl.data)[i];
+    for (long long i = 0; i < K; ++i) ivf_sum += ivfl_i32[i];
     if (ivf_sum != ivf.count()) return pb_fail(PB_ERR_IO, "ivf.npy has %lld entries, ivf_lengths sum to %lld", ivf.count(), ivf_sum);
     const long long packed = (long long)dim * nb / 8;
     // every chunk file is checked (header, dtype, shape, payload size) before the device is touched: a bad

@@ -448,3 +448,28 @@ def test_both_filter_kernels_and_their_score_tables(oracle, npb, corpus, monkeyp
                 assert np.array_equal(r.scores, want.scores), (env, kw)
     finally:
         gpu.close()
+
+
+def test_fast_plaid_directory_serves_the_same_results(oracle, npb, corpus, tmp_path):
+    # mmap.rs:1757-1811: a fast-plaid directory (f16 floats, i64 ivf_lengths) is equivalent to its f32 widening; the
+    # loader reads it as it is and the searches equal the oracle's on the widened index
+    docs, ix, qs, src, _ = corpus
+    path = str(tmp_path / "fp")
+    oracle.write_index(ix, path, chunk_docs=1000)
+    import os
+    for name in ("centroids.npy", "bucket_weights.npy", "bucket_cutoffs.npy"):
+        p = os.path.join(path, name)
+        if os.path.exists(p):
+            np.save(p, np.load(p).astype(np.float16))
+    np.save(os.path.join(path, "ivf_lengths.npy"), np.load(os.path.join(path, "ivf_lengths.npy")).astype(np.int64))
+    wide = oracle.Index(ix.centroids.astype(np.float16).astype(np.float32),
+                        ix.bucket_weights.astype(np.float16).astype(np.float32), None, ix.codes, ix.residuals,
+                        ix.doc_lengths, ix.ivf, ix.ivf_lengths, ix.nbits)
+    gpu = npb.MmapIndex.load(path)
+    try:
+        pg, po = _params(npb, oracle, top_k=10, n_ivf_probe=8, n_full_scores=256)
+        for q, r in zip(qs[:6], gpu.search_batch(qs[:6], pg)):
+            w = oracle.search_one(wide, q, po)
+            assert r.passage_ids.tolist() == w.passage_ids.tolist() and np.array_equal(r.scores, w.scores)
+    finally:
+        gpu.close()

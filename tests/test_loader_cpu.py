@@ -48,12 +48,32 @@ def test_well_formed_directory_reaches_the_device(npb, index_dir):
         assert st == 2, msg                                  # PB_ERR_CUDA: parsed fine, no device, no fallback
 
 
-def test_fast_plaid_f16_directory_is_refused(npb, index_dir, tmp_path):
+def _as_fast_plaid(path):
+    """Rewrite a next-plaid directory with fast-plaid's dtypes (mmap.rs:1757-1811): <f2 floats, <i8 ivf_lengths."""
+    for name in ("centroids.npy", "bucket_weights.npy", "bucket_cutoffs.npy", "avg_residual.npy"):
+        p = os.path.join(path, name)
+        if os.path.exists(p):
+            np.save(p, np.load(p).astype(np.float16))
+    p = os.path.join(path, "ivf_lengths.npy")
+    np.save(p, np.load(p).astype(np.int64))
+
+
+def test_fast_plaid_directory_parses(npb, index_dir, tmp_path):
+    # read as it is (widened / narrowed in memory), never modified; without a device the load still ends in PB_ERR_CUDA
     path = _copy(index_dir[0], tmp_path)
-    c = np.load(os.path.join(path, "centroids.npy"))
-    np.save(os.path.join(path, "centroids.npy"), c.astype(np.float16))
+    _as_fast_plaid(path)
+    before = {f: os.path.getmtime(os.path.join(path, f)) for f in os.listdir(path)}
+    if npb.device_count() > 0:
+        gpu = npb.MmapIndex.load(path)
+        assert gpu.num_documents() == index_dir[1].num_documents
+        gpu.close()
+    else:
+        st, msg = _status(npb, path)
+        assert st == 2, msg
+    assert before == {f: os.path.getmtime(os.path.join(path, f)) for f in os.listdir(path)}
+    np.save(os.path.join(path, "ivf_lengths.npy"), np.load(os.path.join(path, "ivf_lengths.npy")).astype(np.float64))
     st, msg = _status(npb, path)
-    assert st == 4 and "f16" in msg                          # PB_ERR_UNSUPPORTED, mmap.rs:1757-1811 conversion needed
+    assert st == 3 and "ivf_lengths" in msg
 
 
 def test_truncated_payload(npb, index_dir, tmp_path):
