@@ -473,3 +473,19 @@ def test_fast_plaid_directory_serves_the_same_results(oracle, npb, corpus, tmp_p
             assert r.passage_ids.tolist() == w.passage_ids.tolist() and np.array_equal(r.scores, w.scores)
     finally:
         gpu.close()
+
+
+def test_batched_variant_with_more_than_64_probes(oracle, npb, corpus):
+    # colgrep exposes n_ivf_probe (COLGREP_N_IVF_PROBE, colgrep/src/index/mod.rs:792-820): the batched variant's
+    # streaming selection holds up to 192 entries per token; beyond that the call is refused, never silently different
+    docs, ix, qs, src, gpu = corpus
+    for n in (65, 100, 192):
+        kw = dict(top_k=10, n_ivf_probe=n, n_full_scores=512, centroid_batch_size=128, centroid_score_threshold=0.45)
+        pg, po = _params(npb, oracle, **kw)
+        for q, r in zip(qs[:5], gpu.search_batch(qs[:5], pg)):
+            w = oracle.search_one(ix, q, po)
+            assert r.passage_ids.tolist() == w.passage_ids.tolist(), n
+            assert np.array_equal(r.scores, w.scores), n
+    with pytest.raises(npb.PlaidError) as e:
+        gpu.search_batch(qs[:2], npb.SearchParameters(top_k=10, n_ivf_probe=193, centroid_batch_size=128))
+    assert e.value.status == 4
