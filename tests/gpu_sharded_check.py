@@ -41,6 +41,21 @@ def main():
             w = oracle.search_one(ix, q, po, subset=subset)
             if r.passage_ids.tolist() != w.passage_ids.tolist() or not np.array_equal(r.scores, w.scores):
                 bad += 1
+    # data-parallel k-means over NCCL (pb_kmeans_fit_dp): every rank must end with the same unit-norm centroids
+    rng = np.random.default_rng(3)
+    centers = rng.standard_normal((32, 64)).astype(np.float32)
+    centers /= np.linalg.norm(centers, axis=1, keepdims=True)
+    prng = np.random.default_rng(100 + rank)
+    pts = centers[prng.integers(0, 32, 6000)] + 0.05 * prng.standard_normal((6000, 64)).astype(np.float32)
+    pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+    uid2 = [npb.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid2, src=0)
+    cent = npb.kmeans_fit_dp([pts], 32, niters=6, seed=5, device=local, nccl=(uid2[0], rank, world))
+    allc = [None] * world
+    dist.all_gather_object(allc, cent.tobytes())
+    if any(c != allc[0] for c in allc) or np.abs(np.linalg.norm(cent, axis=1) - 1.0).max() > 1e-5 or \
+            ((centers @ cent.T).max(1) > 0.98).mean() < 0.75:
+        bad += 1
     t = torch.tensor([bad], device="cuda")
     dist.all_reduce(t)
     if rank == 0:

@@ -133,3 +133,53 @@ def test_trace_of_the_tensor_core_pass_matches_the_oracle_stage_by_stage(oracle,
             assert _same(r, oracle.search_one(ix, q, po))
     finally:
         gpu.set_fast_exact(True)
+
+
+def _codec_domain_index(oracle, K, D, T, dim=128, nbits=4, seed=5, docs_per_topic=64, pool=64):
+    """A bench-style index drawn directly in the codec domain (random unit centroids, topic pools, random residual
+    bytes): K can be 2^17 without running k-means on the CPU."""
+    rng = np.random.default_rng(seed)
+    cent = rng.standard_normal((K, dim), dtype=np.float32)
+    cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+    n_topics = max(D // docs_per_topic, 4)
+    pools = rng.integers(0, K, (n_topics, pool))
+    topic = np.repeat(rng.integers(0, n_topics, D), T)
+    u = rng.random(D * T)
+    from_pool = pools[topic, np.minimum((u * u * pool).astype(np.int64), pool - 1)]
+    sel = rng.random(D * T)
+    codes = np.where(sel < 0.75, from_pool, rng.integers(0, K, D * T)).astype(np.int64)
+    res = rng.integers(0, 256, (D * T, dim * nbits // 8), dtype=np.uint8)
+    nb = 1 << nbits
+    w = (0.05 * np.linspace(-1.8, 1.8, nb)).astype(np.float32)
+    dl = np.full(D, T, np.int64)
+    ivf, ivf_lengths = oracle.build_ivf(codes, dl, K)
+    return oracle.Index(cent, w, None, codes, res, dl, ivf, ivf_lengths, nbits)
+
+
+def test_scale_shaped_parity_at_k_2_17_with_the_default_slab(oracle, npb):
+    # K = 2^17 > centroid_batch_size = 100 000 (the reference default): the batched variant with its real slab
+    # boundary (100 000 + 31 072), 128 probe chunks, 64 queries, default parameters -- on the tensor-core table and
+    # on the exact one
+    ix = _codec_domain_index(oracle, 1 << 17, 20_000, 64)
+    rng = np.random.default_rng(11)
+    qs = []
+    for d in rng.integers(0, ix.num_documents, 64):
+        tok = oracle.get_document_embeddings(ix, int(d))[rng.integers(0, 64, 32)]
+        nz = rng.standard_normal(tok.shape).astype(np.float32)
+        q = tok + 0.15 * nz / np.linalg.norm(nz, axis=1, keepdims=True)
+        qs.append((q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32))
+    gpu = _gpu_index(npb, ix)
+    try:
+        for kw in (dict(top_k=100), dict(top_k=10, n_ivf_probe=16, n_full_scores=1024, centroid_score_threshold=0.35)):
+            pg, po = npb.SearchParameters(**kw), oracle.SearchParameters(**kw)
+            want = [oracle.search_one(ix, q, po) for q in qs]
+            for tc in (True, False):
+                gpu.set_scores_tc(tc)
+                res = gpu.search_batch(qs, pg)
+                w = gpu.last_work_counters()
+                assert (w["n_k1_tc"] > 0) == tc and w["n_k1_tc_redo"] == 0 and w["n_probe_list"] == 0, (tc, w)
+                assert w["n_candidates"] > 64 * 100                 # the searches are not trivially empty
+                assert sum(_same(r, x) for r, x in zip(res, want)) == 64, (kw, tc)
+    finally:
+        gpu.set_scores_tc(True)
+        gpu.close()
