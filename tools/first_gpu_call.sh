@@ -1,22 +1,24 @@
 #!/bin/bash
-# First GPU call of a round, one box, ~6 minutes: the GPU test-suite, the default bench, every measurement knob
-# (tools/variant_sweep.py, parity checked per variant), then a launch list and full captures of the kernels that
-# changed last.  Everything lands in gpurun_out/.
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/first_gpu_call.sh'
+# First GPU call of a round, one box, ~15 minutes: the GPU test-suite, smoke, a short default bench and the variant
+# sweep (tools/variant_sweep.py, self-parity checked per variant).  Everything lands in gpurun_out/.
+#   tools/gpurun_retry.sh 1100 gpurun_out/call1.txt 'bash tools/first_gpu_call.sh'
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -q -m gpu 2>&1 | tail -25
-timeout 200 python -m pytest tests/test_loader_cpu.py -x -q 2>&1 | tail -3
-timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -1
-timeout 250 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+nvidia-smi --query-gpu=name,memory.total --format=csv,noheader | head -2
+free -g | head -2; nproc
+timeout 600 python -m pytest tests -q -m gpu --durations=8 --deselect tests/test_gpu_create_index.py::test_baseline_config_a > gpurun_out/pytest_gpu.txt 2>&1; tail -45 gpurun_out/pytest_gpu.txt | cut -c1-220
+timeout 100 python __graft_entry__.py --smoke 2>&1 | tail -1
+timeout 300 python bench.py --steps 10 --warmup 3 --recall-queries 64 --parity-queries 16 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+tail -3 gpurun_out/bench_n1.err
 python - <<'PY'
 import json
-d = json.load(open("gpurun_out/bench_n1.json"))
-print({k: d[k] for k in ("value", "ms_per_step", "recall_at_k", "parity")},
-      {k: round(v, 3) for k, v in d["stage_ms_per_step"].items()}, d["e2e"]["value"], d["clocks"])
+try:
+    d = json.load(open("gpurun_out/bench_n1.json"))
+    print({k: d[k] for k in ("value", "ms_per_step", "wall_ms_per_step", "recall_at_k", "parity", "self_parity")})
+    print({k: round(v, 3) for k, v in d["stage_ms_per_step"].items()})
+    print({k: round(v, 3) for k, v in d["kernel_ms_per_step"].items()}, d["e2e"]["value"], d["clocks"])
+    print(d["work_per_step"])
+except Exception as e:
+    print("bench output unreadable:", e)
 PY
-timeout 600 python tools/variant_sweep.py --steps 10 --only "default,exact,E=2,FFMA2,cg" 2>&1 | tee gpurun_out/variant_sweep.txt
-timeout 200 ncu --set full --import-source on --clock-control none \
-    -k "regex:^k_(scores16_tc|approx_recheck|approx16)$" -s 3 -c 3 -o gpurun_out/ncu_k1 \
-    python bench.py --steps 3 --warmup 2 --no-cpu --recall-queries 0 > gpurun_out/ncu_k1.log 2>&1
-tail -c 300 gpurun_out/ncu_k1.log
+timeout 420 python tools/variant_sweep.py --steps 10 --only "exact fp32,code-diff,E=2,FFMA2 in k_exact,cg,FILTER_V1,nq=48" 2>&1 | tee gpurun_out/variant_sweep.txt

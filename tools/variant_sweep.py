@@ -18,6 +18,8 @@ VARIANTS = [
     ("approx grid x4", {"PB_APPROX_GRID": "4"}),
     ("filter off", {"PB_FAST_EXACT": "0"}),
     ("list-scan probe (exact a2)", {"PB_PROBE16": "0", "PB_K1_TC": "0"}),
+    ("decompressing filter (PB_FILTER_V1)", {"PB_FILTER_V1": "1"}),
+    ("nq=48 queries", {"__args__": "--nq 48"}),
 ]
 
 
@@ -30,9 +32,11 @@ def main():
     for name, env in VARIANTS:
         if args.only and not any(s in name for s in args.only.split(",")):
             continue
+        env = dict(env)
+        extra = env.pop("__args__", "").split()
         e = dict(os.environ, **env)
         cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(args.steps), "--warmup", "3",
-               "--recall-queries", "0"]
+               "--recall-queries", "0", "--no-cpu", "--threads", "1"] + extra
         out = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=600)
         line = [l for l in out.stdout.splitlines() if l.startswith("{")]
         if out.returncode != 0 or not line:
@@ -45,7 +49,7 @@ def main():
             print(f"{name:34s} FAILED {err}")
             continue
         st = d["stage_ms_per_step"]
-        par = d.get("parity") or {}
+        par = d.get("self_parity") or {}
         print(f"{name:34s} {d['value']:8.0f} q/s  " + "  ".join(f"{k}={st[k]:.3f}" for k in
               ("centroid_scores", "probe", "approx", "exact")) +
               f"  parity {par.get('ids_identical')}/{par.get('queries')} dmax={par.get('max_abs_score_diff')}"
