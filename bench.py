@@ -52,7 +52,10 @@ if "--impl" in sys.argv and "reference" in sys.argv:
 
 import numpy as np  # noqa: E402
 
-CHUNK_DOCS = 50_000
+CHUNK_DOCS = int(os.environ.get("PB_BENCH_CHUNK_DOCS", 50_000))
+# dry-run hooks for tests/test_bench_harness_cpu.py: a stand-in library module and a CPU torch device
+LIB_MODULE = os.environ.get("PB_BENCH_LIB", "next_plaid_b200")
+DEVICE_TYPE = os.environ.get("PB_BENCH_DEVICE", "cuda")
 
 
 def parse_args():
@@ -322,15 +325,19 @@ def run_b200(args):
     import ctypes as C
     import torch
     import torch.distributed as dist
-    import next_plaid_b200 as npb
+    import importlib
+    npb = importlib.import_module(LIB_MODULE)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(minutes=30))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
+    on_gpu = DEVICE_TYPE == "cuda"
+    dev = torch.device("cuda", local) if on_gpu else torch.device("cpu")
+    sync = (lambda: torch.cuda.synchronize(dev)) if on_gpu else (lambda: None)
+    if on_gpu:
+        torch.cuda.set_device(dev)
     t0 = time.time()
     G = corpus_globals(args, dev)
     sh = build_shard(args, G, rank, world, dev)
@@ -338,7 +345,8 @@ def run_b200(args):
     per_rank = sh["D"]
     gpu = open_shard(npb, args, G, sh, local, rank * per_rank)
     del sh["codes"]                                   # the library narrowed them to u32; residuals stay (adopted)
-    torch.cuda.empty_cache()
+    if on_gpu:
+        torch.cuda.empty_cache()
     t_build = time.time() - t0
     if world > 1:   # doc-sharded: the library runs its own NCCL all-gathers; torch only ships the unique id
         uid = [npb.comm_unique_id() if rank == 0 else None]
@@ -384,11 +392,11 @@ def run_b200(args):
     d_sc = torch.empty((args.batch, args.top_k), dtype=torch.float32, device=dev)
     d_cn = torch.empty((args.batch,), dtype=torch.int32, device=dev)
     gpu.set_profiling(True)
-    sampler = ClockSampler(local)       # spans warm-up + both timed regions (nvidia-smi needs ~0.2 s to start)
+    sampler = ClockSampler(local if on_gpu else -1)       # spans warm-up + both timed regions (nvidia-smi needs ~0.2 s to start)
     for i in range(args.warmup):
         gpu.search_batch_device(d_q[i % n_batches].data_ptr(), offs, params, d_ids.data_ptr(), d_sc.data_ptr(),
                                 d_cn.data_ptr())
-    torch.cuda.synchronize(dev)
+    sync()
     if world > 1:
         dist.barrier()
     stage_ms, kern_ms, work = {}, {}, {}
@@ -406,14 +414,14 @@ def run_b200(args):
         launches += sum(ln.values())
         for k, v in gpu.last_work_counters().items():
             work[k] = work.get(k, 0) + v
-    torch.cuda.synchronize(dev)
+    sync()
     wall_ms = 1e3 * (time.perf_counter() - tw)
     if world > 1:
         dist.barrier()
     gpu.set_profiling(False)
 
     # ---- end-to-end through the public API: pinned host queries in, host results out ----
-    pinned = [torch.from_numpy(f).pin_memory() for f in flat]
+    pinned = [torch.from_numpy(f).pin_memory() if on_gpu else torch.from_numpy(f) for f in flat]
     L = npb.load_library()
     h_ids = np.zeros((args.batch, args.top_k), np.int64)
     h_sc = np.zeros((args.batch, args.top_k), np.float32)
@@ -429,13 +437,13 @@ def run_b200(args):
             raise RuntimeError(L.pb_last_error().decode())
     for i in range(args.warmup):
         e2e_step(i)
-    torch.cuda.synchronize(dev)
+    sync()
     if world > 1:
         dist.barrier()
     t1 = time.perf_counter()
     for i in range(args.steps):
         e2e_step(args.warmup + i)
-    torch.cuda.synchronize(dev)
+    sync()
     e2e_s = time.perf_counter() - t1
     if world > 1:
         dist.barrier()
@@ -450,11 +458,11 @@ def run_b200(args):
                 e2e_step(args.warmup + i, bufs)
         for rep in range(2):          # first repetition creates the extra workspaces
             ths = [threading.Thread(target=worker, args=(t,)) for t in range(args.threads)]
-            torch.cuda.synchronize(dev)
+            sync()
             tc0 = time.perf_counter()
             [t.start() for t in ths]
             [t.join() for t in ths]
-            torch.cuda.synchronize(dev)
+            sync()
             tc = time.perf_counter() - tc0
         concurrent = {"host_threads": args.threads, "value": args.batch * args.steps / tc, "unit": "queries/s",
                       "ms_per_step": 1e3 * tc / args.steps,
@@ -620,8 +628,11 @@ def run_reference(args):
         return
     import torch
     from oracle import oracle
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
-    torch.cuda.set_device(dev)
+    if DEVICE_TYPE == "cuda":
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+        torch.cuda.set_device(dev)
+    else:
+        dev = torch.device("cpu")
     G = corpus_globals(args, dev)
     n_batches = min(max(args.steps + args.warmup, 4), 24)
     n_q = max(n_batches * args.batch, args.recall_queries, args.parity_queries)
