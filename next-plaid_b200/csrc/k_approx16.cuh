@@ -69,21 +69,29 @@ PB_DEV uint4 gather16(const char *p) {
     return CG ? __ldcg(reinterpret_cast<const uint4 *>(p)) : *reinterpret_cast<const uint4 *>(p);
 }
 // CG: row gathers with ld.global.cg (no L1 allocation; PB_APPROX_CG=1, to be measured)
+// chunked = 1: a CTA walks one contiguous slice of the list (its 8 warps side by side), so docs that are neighbours in
+// the list meet in the same L1 -- the point of sorting the candidates by signature (PB_APPROX_SORT); 0: grid-stride.
 template <bool CG>
 __global__ void __launch_bounds__(256, 4)
 k_approx16(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
            const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off,
            const uint32_t *__restrict__ cand, long long cand_cap, const int *__restrict__ n_cand,
-           uint32_t *__restrict__ lsum, unsigned long long *__restrict__ tok_counter) {
+           uint32_t *__restrict__ lsum, unsigned long long *__restrict__ tok_counter, int chunked) {
     const int b = blockIdx.y;
     const int nq = q_off[b + 1] - q_off[b];
-    const int n = n_cand[b];
+    int n = n_cand[b];
     const int lane = threadIdx.x & 31, r = lane >> 2, sl = lane & 3;  // 8 row groups x 4 lanes x 16 bytes
-    const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    int warps_per_grid = gridDim.x * (blockDim.x >> 5);
     const char *STb = reinterpret_cast<const char *>(ST16 + (size_t)b * K * QS);
     const unsigned rowb = (unsigned)QS * 2u;
     unsigned long long my_tokens = 0;
     int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (chunked) {
+        const int per = (n + gridDim.x - 1) / gridDim.x;
+        i = blockIdx.x * per + (threadIdx.x >> 5);
+        n = min(n, (int)(blockIdx.x + 1) * per);
+        warps_per_grid = blockDim.x >> 5;
+    }
     uint32_t d = 0;
     long long t0 = 0, t1 = 0;
     if (i < n) {

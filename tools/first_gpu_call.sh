@@ -21,4 +21,4 @@ try:
 except Exception as e:
     print("bench output unreadable:", e)
 PY
-timeout 420 python tools/variant_sweep.py --steps 10 --only "exact fp32,code-diff,E=2,FFMA2 in k_exact,cg,FILTER_V1,nq=48" 2>&1 | tee gpurun_out/variant_sweep.txt
+timeout 420 python tools/variant_sweep.py --steps 10 --only "exact fp32,code-diff,E=2,FFMA2 in k_exact,cg,FILTER_V1,nq=48,signature" 2>&1 | tee gpurun_out/variant_sweep.txt

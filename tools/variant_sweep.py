@@ -20,6 +20,7 @@ VARIANTS = [
     ("list-scan probe (exact a2)", {"PB_PROBE16": "0", "PB_K1_TC": "0"}),
     ("decompressing filter (PB_FILTER_V1)", {"PB_FILTER_V1": "1"}),
     ("nq=48 queries", {"__args__": "--nq 48"}),
+    ("candidates sorted by signature", {"PB_APPROX_SORT": "1"}),
 ]
 
 
