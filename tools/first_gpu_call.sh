@@ -22,3 +22,7 @@ except Exception as e:
     print("bench output unreadable:", e)
 PY
 timeout 420 python tools/variant_sweep.py --steps 10 --only "exact fp32,code-diff,E=2,FFMA2 in k_exact,cg,FILTER_V1,nq=48,signature" 2>&1 | tee gpurun_out/variant_sweep.txt
+# a5 design question: random-row gather rate of an L2-resident table, LSU vs TMA gather4 (tools/tma_gather_bench.cu)
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo tools/tma_gather_bench.cu -o /tmp/tma_gather_bench 2>&1 | tail -3
+for rb in 64 32; do timeout 60 /tmp/tma_gather_bench $rb 18 256 1; done 2>&1 | tee gpurun_out/tma_gather_bench.txt
+timeout 60 /tmp/tma_gather_bench 64 18 256 4 2>&1 | tail -1 | tee -a gpurun_out/tma_gather_bench.txt
