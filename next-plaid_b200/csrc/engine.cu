@@ -2038,10 +2038,10 @@ static pb_status assign_codes(pb_codec *c, const float *dX, long long m, long lo
     switch (c->dim) {
 #define PB_TC_CASE(DV)                                                                                     \
     case DV: {                                                                                             \
-        auto kern = k_assign_tc<DV>;                                                                       \
+        auto kern = k_assign_tc<DV, false>;                                                                \
         CKS(set_smem(kern, sm));                                                                           \
         kern<<<blocks, 320, sm>>>(xb.as<__nv_bfloat16>(), m, c->cent_bf16.as<__nv_bfloat16>(), c->K, ts.as<float>(), \
-                                  ti.as<uint32_t>());                                                      \
+                                  ti.as<uint32_t>(), nullptr);                                             \
     } break;
         PB_TC_CASE(64) PB_TC_CASE(96) PB_TC_CASE(128)
 #undef PB_TC_CASE
@@ -2239,6 +2239,58 @@ extern "C" int64_t pb_codec_heldout_tokens(int64_t num_embeddings) {  // min(0.0
     return (int64_t)std::min(0.05 * (double)num_embeddings, 50000.0);
 }
 
+// k-means assignment step.  dims 64 / 96 / 128 with K >= 256: the bf16 tcgen05 GEMM of the encode path with the
+// -|c|^2/2 bias added in its epilogue, best shortlist entry taken as is; otherwise the exact fp32 kernel.
+struct KmeansAssign {
+    DevBuf xb, cb, bias, ts, ti, scratch;
+    bool tc = false;
+    long long n = 0, K = 0;
+    int dim = 0, sms = 0;
+    pb_status init(const float *dX, long long n_, int dim_, long long K_, int sms_, cudaStream_t st) {
+        n = n_; K = K_; dim = dim_; sms = sms_;
+        tc = (dim == 64 || dim == 96 || dim == 128) && K >= 256 && n > 0 && !getenv("PB_KMEANS_EXACT");
+        if (!tc) return PB_OK;
+        const size_t npad = (size_t)((n + 255) / 256) * 256, kpad = (size_t)((K + 127) / 128) * 128;
+        CKS(xb.ensure(npad * dim * 2));
+        CKS(cb.ensure(kpad * dim * 2));
+        CKS(bias.ensure(kpad * 4));
+        CKS(ts.ensure((size_t)n * 16));
+        CKS(ti.ensure((size_t)n * 16));
+        CKS(scratch.ensure(std::max<size_t>((size_t)std::max(n, K) * 4, 16)));
+        CK(cudaMemsetAsync(xb.p, 0, npad * dim * 2, st));
+        k_rows_to_bf16<<<sms * 8, 256, 0, st>>>(dX, n, dim, xb.as<__nv_bfloat16>(), scratch.as<float>());
+        CK(cudaGetLastError());
+        return PB_OK;
+    }
+    pb_status run(const float *dX, const float *dC, float *dbias_exact, uint32_t *codes, cudaStream_t st) {
+        if (!tc) {
+            k_half_sqnorm<<<sms * 4, 256, 0, st>>>(dC, K, dim, dbias_exact);
+            return launch_assign(dim, sms, dX, n, dC, K, dbias_exact, nullptr, codes, st);
+        }
+        const size_t kpad = (size_t)((K + 127) / 128) * 128;
+        CK(cudaMemsetAsync(cb.p, 0, kpad * dim * 2, st));
+        k_rows_to_bf16<<<sms * 8, 256, 0, st>>>(dC, K, dim, cb.as<__nv_bfloat16>(), scratch.as<float>());
+        k_half_sqnorm_padded<<<sms * 4, 256, 0, st>>>(dC, K, (long long)kpad, dim, bias.as<float>());
+        const unsigned blocks = (unsigned)((n + 2 * PB_TC_M - 1) / (2 * PB_TC_M));
+        const size_t sm = (size_t)2 * PB_TC_M * dim * 2 + (size_t)PB_TC_STAGES * PB_TC_N * dim * 2 + (2 * PB_TC_STAGES + 5) * 8 + 16;
+        switch (dim) {
+#define PB_KM_CASE(DV)                                                                                                 \
+    case DV: {                                                                                                         \
+        auto kern = k_assign_tc<DV, true>;                                                                             \
+        CKS(set_smem(kern, sm));                                                                                       \
+        kern<<<blocks, 320, sm, st>>>(xb.as<__nv_bfloat16>(), n, cb.as<__nv_bfloat16>(), K, ts.as<float>(),            \
+                                      ti.as<uint32_t>(), bias.as<float>());                                            \
+    } break;
+            PB_KM_CASE(64) PB_KM_CASE(96) PB_KM_CASE(128)
+#undef PB_KM_CASE
+            default: return pb_fail(PB_ERR_UNSUPPORTED, "tensor-core k-means assignment not built for dim %d", dim);
+        }
+        k_take_top1<<<sms * 4, 256, 0, st>>>(ti.as<uint32_t>(), n, codes);
+        CK(cudaGetLastError());
+        return PB_OK;
+    }
+};
+
 extern "C" pb_status pb_kmeans_fit(int32_t device, const float *samples, int64_t n, int32_t dim, int64_t K, int32_t niters,
                                    uint64_t seed, float *out_centroids) {
     if (!samples || !out_centroids) return pb_fail(PB_ERR_INVALID, "null argument");
@@ -2267,9 +2319,10 @@ extern "C" pb_status pb_kmeans_fit(int32_t device, const float *samples, int64_t
     CKS(upload(didx, perm.data(), (size_t)K * 8, PB_MEM_HOST));
     k_gather_rows<<<sms * 4, 256>>>(dX.as<float>(), didx.as<long long>(), K, dim, dC.as<float>());
     CK(cudaGetLastError());
+    KmeansAssign ka;
+    CKS(ka.init(dX.as<float>(), n, dim, K, sms, 0));
     for (int it = 0; it < niters; ++it) {
-        k_half_sqnorm<<<sms * 4, 256>>>(dC.as<float>(), K, dim, dbias.as<float>());
-        CKS(launch_assign(dim, sms, dX.as<float>(), n, dC.as<float>(), K, dbias.as<float>(), nullptr, dcodes.as<uint32_t>(), 0));
+        CKS(ka.run(dX.as<float>(), dC.as<float>(), dbias.as<float>(), dcodes.as<uint32_t>(), 0));
         CK(cudaMemset(dsums.p, 0, (size_t)K * dim * 4));
         CK(cudaMemset(dcnt.p, 0, (size_t)K * 4));
         k_accumulate<<<sms * 8, 256>>>(dX.as<float>(), n, dim, dcodes.as<uint32_t>(), dsums.as<float>(), dcnt.as<float>());
@@ -2404,9 +2457,10 @@ extern "C" pb_status pb_kmeans_fit_dp(pb_build_comm *c, const float *samples, in
     }
     CKS(build_allreduce(c, dC.as<float>(), (size_t)K * dim));
     float *sums = dacc.as<float>(), *counts = dacc.as<float>() + (size_t)K * dim;
+    KmeansAssign ka;
+    CKS(ka.init(dX.as<float>(), n, dim, K, sms, c->stream));
     for (int it = 0; it < niters; ++it) {
-        k_half_sqnorm<<<sms * 4, 256, 0, c->stream>>>(dC.as<float>(), K, dim, dbias.as<float>());
-        CKS(launch_assign(dim, sms, dX.as<float>(), n, dC.as<float>(), K, dbias.as<float>(), nullptr, dcodes.as<uint32_t>(), c->stream));
+        CKS(ka.run(dX.as<float>(), dC.as<float>(), dbias.as<float>(), dcodes.as<uint32_t>(), c->stream));
         CK(cudaMemsetAsync(dacc.p, 0, (size_t)K * (dim + 1) * 4, c->stream));
         if (n > 0) k_accumulate<<<sms * 8, 256, 0, c->stream>>>(dX.as<float>(), n, dim, dcodes.as<uint32_t>(), sums, counts);
         CK(cudaGetLastError());

@@ -293,10 +293,13 @@ __global__ void k_rows_to_bf16(const float *__restrict__ X, long long n, int dim
     }
 }
 
-template <int DIM>
+// BIAS: rank x.c + bias[c] instead of x.c (k-means: bias = -|c|^2 / 2 turns the maximum into the L2-nearest centroid);
+// the encode path instantiates BIAS = false.
+template <int DIM, bool BIAS>
 __global__ void __launch_bounds__(320, 1)
 k_assign_tc(const __nv_bfloat16 *__restrict__ Xb, long long n, const __nv_bfloat16 *__restrict__ Cb, long long K,
-            float *__restrict__ top_s /* [n][4] */, uint32_t *__restrict__ top_i /* [n][4] */) {
+            float *__restrict__ top_s /* [n][4] */, uint32_t *__restrict__ top_i /* [n][4] */,
+            const float *__restrict__ bias /* [ceil(K/128)*128] or NULL */) {
     // 256 tokens per CTA = two UMMA M=128 operand tiles that share every centroid tile (halves the L2
     // traffic per token); N = 128 centroids per tile; TMEM = 2 buffers x 2 halves x 128 fp32 columns.
     // warps 0-7 epilogue (warp w: token half w/4, TMEM lanes 32*(w%4)..), warp 8 loader, warp 9 MMA issuer.
@@ -395,6 +398,10 @@ k_assign_tc(const __nv_bfloat16 *__restrict__ Xb, long long n, const __nv_bfloat
             for (int cb = 0; cb < PB_TC_N / 32; ++cb) {
                 uint32_t rr[32];
                 tc_ld32(tmem_base + ((uint32_t)(32 * lg) << 16) + acc * 256 + half * PB_TC_N + cb * 32, rr);
+                if (BIAS) {  // warp-uniform addresses: one broadcast load per column
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) rr[j] = __float_as_uint(__uint_as_float(rr[j]) + __ldg(bias + c0 + cb * 32 + j));
+                }
                 // one max tree per 32 columns; the insertion path runs only when the batch can matter
                 float m = __uint_as_float(rr[0]);
 #pragma unroll
@@ -556,5 +563,29 @@ __global__ void k_sum_ranks(const float *__restrict__ stage, int world, long lon
         float acc = stage[i];
         for (int r = 1; r < world; ++r) acc += stage[(size_t)r * count + i];
         out[i] = acc;
+    }
+}
+
+// k-means assignment from the tensor-core shortlist: the best (score + bias) wins, no exact re-score (the iteration is
+// parity-unpinned; bf16 rounding only moves points that sit between two centroids)
+__global__ void k_take_top1(const uint32_t *__restrict__ top_i, long long n, uint32_t *__restrict__ codes) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const uint32_t c = top_i[4 * t];
+        codes[t] = c == 0xffffffffu ? 0u : c;
+    }
+}
+// bias[c] = -|c|^2 / 2 for c < K, 0 for the padding columns of the last tile
+__global__ void k_half_sqnorm_padded(const float *__restrict__ C, long long K, long long Kpad, int dim, float *__restrict__ bias) {
+    const int lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long c = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < Kpad; c += nw) {
+        float p = 0.0f;
+        if (c < K)
+            for (int j = lane; j < dim; j += 32) {
+                const float v = C[(size_t)c * dim + j];
+                p = fmaf(v, v, p);
+            }
+        for (int m = 16; m >= 1; m >>= 1) p += __shfl_xor_sync(PB_FULL, p, m);
+        if (lane == 0) bias[c] = -0.5f * p;
     }
 }

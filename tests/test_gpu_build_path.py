@@ -233,3 +233,21 @@ def test_data_parallel_kmeans_over_an_in_process_group(oracle, npb):
         assert inertia(c) <= 1.5 * inertia(single) + 1e-3
         found = (centers @ c.T).max(1)
         assert (found > 0.98).mean() >= 0.8          # most blobs have their own centroid (random init may merge a few)
+
+
+def test_kmeans_on_the_tensor_cores_matches_the_fp32_assignment_statistically(oracle, npb, monkeypatch):
+    # dims 64/96/128 with K >= 256: the Lloyd assignment step runs as the bf16 tcgen05 GEMM with the -|c|^2/2 bias in
+    # its epilogue (k_assign_tc<., true>); PB_KMEANS_EXACT=1 keeps the fp32 kernel.  Same seed -> same start; bf16
+    # rounding may move points that sit between two centroids, the clustering quality must not change.
+    docs = oracle.synthetic_corpus(1500, 32, dim=128, seed=8)
+    x = np.concatenate(docs, 0)
+    K = 512
+    tc = npb.kmeans_fit(x, K, niters=5, seed=7)
+    monkeypatch.setenv("PB_KMEANS_EXACT", "1")
+    ex = npb.kmeans_fit(x, K, niters=5, seed=7)
+    monkeypatch.delenv("PB_KMEANS_EXACT")
+    assert np.allclose(np.linalg.norm(tc, axis=1), 1.0, atol=1e-5)
+    q_tc, q_ex = (x @ tc.T).max(1).mean(), (x @ ex.T).max(1).mean()
+    assert abs(q_tc - q_ex) < 5e-3, (q_tc, q_ex)
+    agree = ((x @ tc.T).argmax(1) == (x @ ex.T).argmax(1)).mean()
+    assert agree > 0.9, agree
