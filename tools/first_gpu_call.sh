@@ -6,7 +6,7 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total --format=csv,noheader | head -2
 free -g | head -2; nproc
-timeout 600 python -m pytest tests -q -m gpu --durations=8 --deselect tests/test_gpu_create_index.py::test_baseline_config_a > gpurun_out/pytest_gpu.txt 2>&1; tail -45 gpurun_out/pytest_gpu.txt | cut -c1-220
+timeout 600 python -m pytest tests -q -m gpu -rf --durations=8 --deselect tests/test_gpu_create_index.py::test_baseline_config_a > gpurun_out/pytest_gpu.txt 2>&1; tail -45 gpurun_out/pytest_gpu.txt | cut -c1-220
 timeout 100 python __graft_entry__.py --smoke 2>&1 | tail -1
 timeout 300 python bench.py --steps 10 --warmup 3 --recall-queries 64 --parity-queries 16 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 tail -3 gpurun_out/bench_n1.err
