@@ -242,7 +242,7 @@ struct Workspace {
     cudaEvent_t call_ev[2] = {};                // around a whole search call
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2,  cellbits,
-        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc, mslot, skeys, skeys2, cand3, segs, sorttmp;
+        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc, mslot, skeys, skeys2, cand3, segs, sorttmp, slicecnt;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -1229,8 +1229,10 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             CKS(ws.qrange.ensure((size_t)B * 8 + 16));
             CKS(ws.qflag.ensure((size_t)B * 4 + 16));
             CKS(ws.qexp.ensure((size_t)B * 4 + 16));
-            k_query_range<<<B, 32, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), ix->dim, ix->cmax,
-                                                   ws.qrange.as<float2>(), ws.qflag.as<int>(), ws.qexp.as<int>());
+            CKS(ws.qnmax.ensure((size_t)B * 4 + 16));
+            k_query_range<<<B, 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), ix->dim, ix->cmax,
+                                                    ws.qrange.as<float2>(), ws.qflag.as<int>(), ws.qexp.as<int>(),
+                                                    ws.qnmax.as<float>());
             CK(cudaGetLastError());
             L[PB_STAGE_CENTROID_SCORES] += 1;
         }
@@ -1333,10 +1335,13 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         k_mark<<<dim3(cells_cap, B), 128, 0, ws.stream>>>(ws.cells.as<uint32_t>(), ws.ncells.as<int>(), cells_cap,
                                                          ix->ivf.as<uint32_t>(), ix->ivf_off.as<long long>(), d_subset_bits,
                                                          ws.bitmap.as<uint32_t>(), Wd);
-        k_compact<<<B, 1024, 0, ws.stream>>>(ws.bitmap.as<uint32_t>(), Wd, ws.cand.as<uint32_t>(), ix->D,
-                                             ws.ncand.as<int>());
+        const int slices = (int)std::max<long long>(1, std::min<long long>(32, (4ll * ix->sm_count + B - 1) / B));
+        CKS(ws.slicecnt.ensure((size_t)B * slices * 4));
+        k_compact_count<<<dim3(slices, B), 256, 0, ws.stream>>>(ws.bitmap.as<uint32_t>(), Wd, ws.slicecnt.as<int>());
+        k_compact_emit<<<dim3(slices, B), 256, 0, ws.stream>>>(ws.bitmap.as<uint32_t>(), Wd, ws.slicecnt.as<int>(),
+                                                               ws.cand.as<uint32_t>(), ix->D, ws.ncand.as<int>());
         CK(cudaGetLastError());
-        L[PB_STAGE_CANDIDATES] += 2;
+        L[PB_STAGE_CANDIDATES] += 3;
         if (prof) CK(cudaEventRecord(ws.ev[4], ws.stream));
 
         // ---- a5 approximate scores ----
@@ -1460,13 +1465,16 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             CKS(ws.nkept2.ensure((size_t)B * 4 + 16));
             CKS(ws.tokp2.ensure((size_t)B * (Mcap + 1) * 8));
             CKS(ws.ktok2.ensure((size_t)B * 8 + 16));
-            CKS(ws.qnmax.ensure((size_t)B * 4 + 16));
-            k_query_norm_max<<<B, 32, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), ix->dim, ws.qnmax.as<float>());
-            CK(cudaGetLastError());
+            if (!fast) {  // the two-pass mode computed it with the score range
+                CKS(ws.qnmax.ensure((size_t)B * 4 + 16));
+                k_query_range<<<B, 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), ix->dim, ix->cmax, nullptr, nullptr,
+                                                        nullptr, ws.qnmax.as<float>());
+                CK(cudaGetLastError());
+                L[PB_STAGE_EXACT] += 1;
+            }
             KeptView kv2{ws.kept2.as<uint32_t>(), ws.nkept2.as<int>(), ws.tokp2.as<long long>(), ws.krank2.as<uint32_t>()};
             CKS(launch_filter(ix, ws, kv, kv2, B, QS, Mcap, top_k, (long long)Mcap * std::max(ix->max_doclen, 1), eps_unit,
                               nq_max, linear, &L[PB_STAGE_EXACT]));
-            L[PB_STAGE_EXACT] += 1;
             kv = kv2;
             if (!sharded) kv.krank = nullptr;  // survivors keep their order, so position breaks ties the same way
         }

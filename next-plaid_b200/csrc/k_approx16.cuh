@@ -10,14 +10,22 @@
 //   => doc X certainly outranks doc Y when L_X - L_Y > 3.25*nq; band W = 4*nq + 8 code units.
 // Queries whose scores leave [-R, R] or are non-finite (qflag) skip the shortcut entirely.
 // ------------------------------------------------------------------------------------------
-// qexp[b]: the power of two that brings the query's largest token norm into [1, 2) (operand scaling of k_scores16_tc)
-__global__ void k_query_range(const float *__restrict__ Q, const int *__restrict__ q_off, int dim, float cmax,
-                              float2 *__restrict__ qrange, int *__restrict__ qflag, int *__restrict__ qexp) {
-    const int b = blockIdx.x, lane = threadIdx.x;
+// Per query: the largest token norm, and what the stages derive from it --
+//   qrange[b] = (R*scale, scale) of the 16-bit score code, R = max|c| * max|q| * (1 + 1e-4), scale = 65535 / 2R
+//   qflag[b]  = 1 when the range is unusable (non-finite or degenerate norms): the query takes the exact paths
+//   qexp[b]   = the power of two that brings the largest token norm into [1, 2) (operand scaling of k_scores16_tc)
+//   qnmax[b]  = max|q| * (1 + 1e-4), the scale of the MaxSim filter's error bound
+// grid = B, 256 threads: a warp per token row.
+__global__ void __launch_bounds__(256)
+k_query_range(const float *__restrict__ Q, const int *__restrict__ q_off, int dim, float cmax,
+              float2 *__restrict__ qrange, int *__restrict__ qflag, int *__restrict__ qexp, float *__restrict__ qnmax) {
+    __shared__ float best_s[8];
+    __shared__ int bad_s[8];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int r0 = q_off[b], nq = q_off[b + 1] - r0;
     float best = 0.0f;
     bool bad = false;
-    for (int r = 0; r < nq; ++r) {
+    for (int r = w; r < nq; r += 8) {
         float p = 0.0f;
         for (int j = lane; j < dim; j += 32) {
             const float v = Q[(size_t)(r0 + r) * dim + j];
@@ -25,21 +33,29 @@ __global__ void k_query_range(const float *__restrict__ Q, const int *__restrict
         }
         for (int m = 16; m >= 1; m >>= 1) p += __shfl_xor_sync(PB_FULL, p, m);
         bad |= !(p <= 3.0e38f);
-        best = fmaxf(best, p);
+        best = fmaxf(best, p == p ? p : INFINITY);
     }
     if (lane == 0) {
+        best_s[w] = best;
+        bad_s[w] = bad ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) {
+            best = fmaxf(best, best_s[i]);
+            bad |= bad_s[i] != 0;
+        }
         float R = cmax * sqrtf(best) * 1.0001f;
-        int kq = 0;
+        int kq = 0, flag = 0;
         if (!(R > 1e-30f) || !(R < 1e30f) || bad) {
             R = 1.0f;
-            qflag[b] = nq > 0 ? 1 : 0;
-        } else {
-            qflag[b] = 0;
-            kq = -ilogbf(sqrtf(best));
-        }
-        if (qexp) qexp[b] = kq;
+            flag = nq > 0 ? 1 : 0;
+        } else kq = -ilogbf(sqrtf(best));
         const float scale = 65535.0f / (2.0f * R);
-        qrange[b] = make_float2(R * scale, scale);
+        if (qrange) qrange[b] = make_float2(R * scale, scale);
+        if (qflag) qflag[b] = flag;
+        if (qexp) qexp[b] = kq;
+        if (qnmax) qnmax[b] = sqrtf(best) * 1.0001f;
     }
 }
 
@@ -202,9 +218,14 @@ k_select_u32(const uint32_t *__restrict__ sel_keys, const int *__restrict__ sel_
             for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
             __syncthreads();
             const uint32_t prefix = prefix_s, mask = mask_s;
-            for (int i = threadIdx.x; i < ns; i += blockDim.x) {
-                const uint32_t k = ~L[i];
-                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
+            // the sums of a query crowd into a few digits: one atomic per distinct digit of a warp, not per element
+            for (int i0 = 0; i0 < ns; i0 += blockDim.x) {
+                const int i = i0 + threadIdx.x;
+                const uint32_t k = i < ns ? ~L[i] : 0u;
+                const bool in = i < ns && (k & mask) == prefix;
+                const uint32_t digit = in ? ((k >> shift) & 255u) : 256u + (threadIdx.x & 31);
+                const unsigned peers = __match_any_sync(PB_FULL, digit);
+                if (in && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
             }
             __syncthreads();
             if (threadIdx.x == 0) {

@@ -2,8 +2,8 @@
 // Part of kernels.cuh (included from there, in order; not a standalone header).
 // ------------------------------------------------------------------------------------------
 // a4: candidates = sorted unique union of the posting lists of the surviving cells.
-// k_mark: grid = (cells_cap, B): set one bit per (query, doc).  k_compact: one CTA per query turns
-// the bitmap into an ascending doc-id list (and clears it for the next call).
+// k_mark: grid = (cells_cap, B): set one bit per (query, doc).  k_compact_count / k_compact_emit turn the bitmap
+// into an ascending doc-id list (and clear it for the next call).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_mark(const uint32_t *__restrict__ cells, const int *__restrict__ n_cells, int cells_cap,
@@ -20,29 +20,54 @@ k_mark(const uint32_t *__restrict__ cells, const int *__restrict__ n_cells, int 
     }
 }
 
-__global__ void __launch_bounds__(1024)
-k_compact(uint32_t *__restrict__ bitmap, long long W, uint32_t *__restrict__ cand, long long cand_cap,
-          int *__restrict__ n_cand) {
-    __shared__ int scan_tmp[33];
-    const int b = blockIdx.x;
-    uint32_t *bm = bitmap + (size_t)b * W;
-    const long long per = (W + blockDim.x - 1) / blockDim.x;
-    const long long w0 = min(W, (long long)threadIdx.x * per), w1 = min(W, w0 + per);
+// k_compact_count / k_compact_emit: grid = (slices, B), 256 threads.  A query's bitmap is cut into `slices` equal word
+// ranges; pass 1 counts the bits of every slice, pass 2 places its slice after the slices before it (ascending doc
+// ids overall), clears the words for the next call and -- the last slice -- publishes the total.
+__global__ void __launch_bounds__(256)
+k_compact_count(const uint32_t *__restrict__ bitmap, long long W, int *__restrict__ slice_counts) {
+    __shared__ int red[8];
+    const int b = blockIdx.y, S = gridDim.x;
+    const long long per = (W + S - 1) / S, w0 = min(W, (long long)blockIdx.x * per), w1 = min(W, w0 + per);
+    const uint32_t *bm = bitmap + (size_t)b * W;
     int cnt = 0;
-    for (long long i = w0; i < w1; ++i) cnt += __popc(bm[i]);
+    for (long long i = w0 + threadIdx.x; i < w1; i += blockDim.x) cnt += __popc(bm[i]);
+    cnt = __reduce_add_sync(PB_FULL, cnt);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        slice_counts[(size_t)b * S + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_compact_emit(uint32_t *__restrict__ bitmap, long long W, const int *__restrict__ slice_counts, uint32_t *__restrict__ cand,
+               long long cand_cap, int *__restrict__ n_cand) {
+    __shared__ int scan_tmp[33];
+    const int b = blockIdx.y, S = gridDim.x;
+    const long long per = (W + S - 1) / S, w0 = min(W, (long long)blockIdx.x * per), w1 = min(W, w0 + per);
+    uint32_t *bm = bitmap + (size_t)b * W;
+    int base = 0;
+    for (int i = 0; i < (int)blockIdx.x; ++i) base += slice_counts[(size_t)b * S + i];
+    // each thread owns a contiguous run of the slice's words, so positions ascend with the doc id
+    const long long tper = (w1 - w0 + blockDim.x - 1) / blockDim.x;
+    const long long t0 = min(w1, w0 + (long long)threadIdx.x * tper), t1 = min(w1, t0 + tper);
+    int cnt = 0;
+    for (long long i = t0; i < t1; ++i) cnt += __popc(bm[i]);
     int total;
-    int pos = block_exclusive_scan(cnt, scan_tmp, &total);
+    int pos = base + block_exclusive_scan(cnt, scan_tmp, &total);
     uint32_t *out = cand + (size_t)b * cand_cap;
-    for (long long i = w0; i < w1; ++i) {
+    for (long long i = t0; i < t1; ++i) {
         uint32_t x = bm[i];
         if (x) bm[i] = 0u;
         while (x) {
-            int bit = __ffs(x) - 1;
+            const int bit = __ffs(x) - 1;
             x &= x - 1;
             out[pos++] = (uint32_t)(i * 32 + bit);
         }
     }
-    if (threadIdx.x == 0) n_cand[b] = total;
+    if (blockIdx.x == S - 1 && threadIdx.x == 0) n_cand[b] = base + total;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -271,9 +296,13 @@ k_cut(const u64 *__restrict__ keys, const float *__restrict__ approx_in, long lo
             for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
             __syncthreads();
             const u64 prefix = prefix_s, mask = mask_s;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                u64 k = kb[i];
-                if ((k & mask) == prefix) atomicAdd(&hist[(int)((k >> shift) & 255ull)], 1);
+            for (int i0 = 0; i0 < n; i0 += blockDim.x) {  // warp-aggregated: one atomic per distinct digit of a warp
+                const int i = i0 + threadIdx.x;
+                const u64 k = i < n ? kb[i] : 0ull;
+                const bool in = i < n && (k & mask) == prefix;
+                const uint32_t digit = in ? (uint32_t)((k >> shift) & 255ull) : 256u + (threadIdx.x & 31);
+                const unsigned peers = __match_any_sync(PB_FULL, digit);
+                if (in && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
             }
             __syncthreads();
             if (threadIdx.x == 0) {

@@ -608,19 +608,3 @@ k_tc_select(const float *__restrict__ est, const uint32_t *__restrict__ kept, co
         kept_tokens2[b] = run;
     }
 }
-
-__global__ void k_query_norm_max(const float *__restrict__ Q, const int *__restrict__ q_off, int dim, float *__restrict__ qnmax) {
-    const int b = blockIdx.x, lane = threadIdx.x;
-    const int r0 = q_off[b], nq = q_off[b + 1] - r0;
-    float best = 0.0f;
-    for (int r = 0; r < nq; ++r) {
-        float p = 0.0f;
-        for (int j = lane; j < dim; j += 32) {
-            const float v = Q[(size_t)(r0 + r) * dim + j];
-            p = fmaf(v, v, p);
-        }
-        for (int m = 16; m >= 1; m >>= 1) p += __shfl_xor_sync(PB_FULL, p, m);
-        best = fmaxf(best, p == p ? p : INFINITY);
-    }
-    if (lane == 0) qnmax[b] = sqrtf(best) * 1.0001f;
-}
