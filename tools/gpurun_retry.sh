@@ -1,10 +1,10 @@
 #!/bin/bash
 # retry a gpurun call while the pod answers "busy" (exit 3, nothing charged): tools/gpurun_retry.sh <timeout> <logfile> <command...>
 t=$1; log=$2; shift 2
-for i in $(seq 1 30); do
+for i in $(seq 1 200); do
   /usr/local/graft/bin/gpurun --timeout "$t" -- "$@" > "$log" 2>&1
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
-  sleep 90
+  sleep 8
 done
 exit 3
