@@ -798,12 +798,22 @@ static pb_status launch_k1_diag(pb_index *ix, Workspace &ws, int B, int QS) {
     return PB_OK;
 }
 
+// chunk size of the threshold-first probe: 1024 centroids, fewer for small K so that at least 2n chunks exist (tau is
+// the n-th largest chunk maximum); *n_chunks < n means the path cannot run
+static int probe_chunk_rows(long long K, int n, int *n_chunks) {
+    int rows = 1024;
+    while (rows > 32 && (K + rows - 1) / rows < 2ll * n) rows >>= 1;
+    *n_chunks = (int)((K + rows - 1) / rows);
+    return rows;
+}
+
 // a2 + a3 on the tensor-core table.  Nothing is read back here: a flagged query or a probe-list overflow raises
 // *d_fallback on the device, the kernels after it stay memory-safe, and the caller redoes the sub-batch on the
 // exact path once it sees the flag at the end.
 static pb_status run_k1_tc(pb_index *ix, Workspace &ws, const pb_search_params *p, int B, int QS, int nq_max, int n,
                            bool batched, int *L, int *cells_cap_out, const int **d_fallback_out) {
-    const int n_chunks = (int)((ix->K + 1023) / 1024);
+    int n_chunks = 0;
+    const int chunk_rows = probe_chunk_rows(ix->K, n, &n_chunks);
     const int cm = 2 * ix->k1_margin + 1;
     CKS(ws.Qi.ensure((size_t)B * QS * ix->dim * 4));
     k_interleave_query_rows<<<dim3(8, B), 256, 0, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->dim, ws.Qi.as<float>());
@@ -825,12 +835,12 @@ static pb_status run_k1_tc(pb_index *ix, Workspace &ws, const pb_search_params *
     CK(cudaMemsetAsync(ws.pcount.p, 0, (size_t)B * QS * 4 + 16, ws.stream));
     int *d_fallback = ws.pcount.as<int>() + (size_t)B * QS;
     k_chunkmax16<<<dim3((n_chunks + 3) / 4, B), 128, 0, ws.stream>>>(ws.ST16.as<unsigned short>(), ix->K, QS, n_chunks,
-                                                                     ws.cmax16.as<unsigned short>());
+                                                                     chunk_rows, ws.cmax16.as<unsigned short>());
     k_tau16<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.cmax16.as<unsigned short>(), ws.qoff.as<int>(), QS, n, n_chunks,
                                               ws.qflag.as<int>(), ws.tau16.as<uint32_t>(), d_fallback);
     k_collect16_tc<<<dim3((n_chunks + 3) / 4, B), 128, 0, ws.stream>>>(
         ws.ST16.as<unsigned short>(), ws.Q.as<float>(), ws.qoff.as<int>(), ix->centroids.as<float>(), ix->dim, cm, ix->K, QS,
-        n_chunks, ws.tau16.as<uint32_t>(), cap, ws.pcount.as<int>(), ws.plist.as<u64>(), d_fallback);
+        n_chunks, chunk_rows, ws.tau16.as<uint32_t>(), cap, ws.pcount.as<int>(), ws.plist.as<u64>(), d_fallback);
     k_topn_merge<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.plist.as<u64>(), ws.qoff.as<int>(), QS, n, cap / n, ws.sel.as<u64>(),
                                                   nullptr, 0);
     // the selected centroids, their exact rows, the variant's threshold rule
@@ -1196,7 +1206,8 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         const bool fast = ix->fast_approx && !io.trace;  // trace wants every candidate's exact approx score
         // the score table comes from the tensor cores unless something needs the dense fp32 S (an eligibility filter,
         // the radix-select probe, a trace) or the shape is outside the kernel's (DESIGN.md "a2")
-        const int n_chunks_k = (int)((ix->K + 1023) / 1024);
+        int n_chunks_k = 0;
+        probe_chunk_rows(ix->K, n_probe, &n_chunks_k);
         const bool want_tc = k1_tc_usable(ix) && fast && !ix->k1_diag && !all_eligible && !big_probe && !d_elig &&
                              QS / 8 <= 32 && n_chunks_k >= n_probe && n_probe <= 192;
         // One pass over the sub-batch.  use_tc: a flagged query or a probe-list overflow raises a device flag instead of
@@ -1286,12 +1297,14 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             // threshold-first selection on the 16-bit table when there is one (k_chunkmax16 / k_collect16);
             // the per-lane list scan of k_topn_partial otherwise, or when the device raises `fallback`
             const int GQ = QS / 8;
-            const bool thr_path = fast && !d_elig && ix->probe16 && GQ <= 32 && n_chunks >= n && n <= 192;
+            int t_chunks = 0;
+            const int t_rows = probe_chunk_rows(ix->K, n, &t_chunks);
+            const bool thr_path = fast && !d_elig && ix->probe16 && GQ <= 32 && t_chunks >= n && n <= 192;
             int *d_fallback = nullptr;
             probe_list_only = !thr_path;
             if (thr_path) {
                 const int cap = n * std::max(2, 128 / n);
-                CKS(ws.cmax16.ensure((size_t)B * n_chunks * QS * 2));
+                CKS(ws.cmax16.ensure((size_t)B * t_chunks * QS * 2));
                 CKS(ws.tau16.ensure((size_t)B * QS * 4));
                 CKS(ws.plist.ensure((size_t)B * QS * cap * 8));
                 CKS(ws.pcount.ensure((size_t)B * QS * 4 + 16));
@@ -1299,12 +1312,12 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
                 CK(cudaMemsetAsync(ws.pcount.p, 0, (size_t)B * QS * 4 + 16, ws.stream));
                 d_fallback = ws.pcount.as<int>() + (size_t)B * QS;
                 d_probe_fallback = d_fallback;
-                k_chunkmax16<<<dim3((n_chunks + 3) / 4, B), 128, 0, ws.stream>>>(ws.ST16.as<unsigned short>(), ix->K, QS, n_chunks,
-                                                                                 ws.cmax16.as<unsigned short>());
-                k_tau16<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.cmax16.as<unsigned short>(), ws.qoff.as<int>(), QS, n, n_chunks,
+                k_chunkmax16<<<dim3((t_chunks + 3) / 4, B), 128, 0, ws.stream>>>(ws.ST16.as<unsigned short>(), ix->K, QS, t_chunks,
+                                                                                 t_rows, ws.cmax16.as<unsigned short>());
+                k_tau16<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.cmax16.as<unsigned short>(), ws.qoff.as<int>(), QS, n, t_chunks,
                                                           ws.qflag.as<int>(), ws.tau16.as<uint32_t>(), d_fallback);
-                k_collect16<<<dim3((n_chunks + 3) / 4, B), 128, 0, ws.stream>>>(
-                    ws.ST16.as<unsigned short>(), ws.ST.as<float>(), ix->K, QS, n_chunks, ws.tau16.as<uint32_t>(), cap,
+                k_collect16<<<dim3((t_chunks + 3) / 4, B), 128, 0, ws.stream>>>(
+                    ws.ST16.as<unsigned short>(), ws.ST.as<float>(), ix->K, QS, t_chunks, t_rows, ws.tau16.as<uint32_t>(), cap,
                     ws.pcount.as<int>(), ws.plist.as<u64>(), d_fallback);
                 k_topn_merge<<<dim3(QS, B), 32, 0, ws.stream>>>(ws.plist.as<u64>(), ws.qoff.as<int>(), QS, n, cap / n,
                                                               ws.sel.as<u64>(), d_fallback, 0);

@@ -80,10 +80,11 @@ k_topn_partial(const float *__restrict__ ST, const int *__restrict__ q_off, long
 // query (non-finite scores, no valid table) or an eligibility filter fall back to k_topn_partial: *fallback
 // is set on the device and gates the two paths.
 // ST16 rows are QS codes; a lane owns one 16-byte group (8 query tokens) of a row, GQ = QS/8 lanes per row.
-// grid = (ceil(n_chunks/4), B), 128 threads, one warp per 1024-centroid chunk.
+// grid = (ceil(n_chunks/4), B), 128 threads, one warp per chunk of `chunk_rows` centroids (1024, fewer for small K so
+// that at least n chunks exist).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-k_chunkmax16(const unsigned short *__restrict__ ST16, long long K, int QS, int n_chunks,
+k_chunkmax16(const unsigned short *__restrict__ ST16, long long K, int QS, int n_chunks, int chunk_rows,
              unsigned short *__restrict__ cmax) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
     const int chunk = blockIdx.x * 4 + w;
@@ -91,8 +92,8 @@ k_chunkmax16(const unsigned short *__restrict__ ST16, long long K, int QS, int n
     // GQ lanes cover one row; L = the largest multiple of GQ that fits a warp, so a lane keeps its 8 query
     // tokens for the whole scan (GQ a power of two: L = 32; nq = 48: GQ = 6, L = 30, two lanes idle)
     const int GQ = QS >> 3, L = (32 / GQ) * GQ;
-    const long long c0 = (long long)chunk * 1024;
-    const int rows = (int)min(1024ll, K - c0);
+    const long long c0 = (long long)chunk * chunk_rows;
+    const int rows = (int)min((long long)chunk_rows, K - c0);
     const uint4 *base = reinterpret_cast<const uint4 *>(ST16 + ((size_t)b * K + c0) * QS);
     const int total = rows * GQ;
     uint4 acc = make_uint4(0, 0, 0, 0);
@@ -155,15 +156,15 @@ __global__ void k_tau16(const unsigned short *__restrict__ cmax, const int *__re
 
 __global__ void __launch_bounds__(128)
 k_collect16(const unsigned short *__restrict__ ST16, const float *__restrict__ ST, long long K, int QS, int n_chunks,
-            const uint32_t *__restrict__ tau, int cap, int *__restrict__ counts, u64 *__restrict__ list,
+            int chunk_rows, const uint32_t *__restrict__ tau, int cap, int *__restrict__ counts, u64 *__restrict__ list,
             int *__restrict__ fallback) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
     const int chunk = blockIdx.x * 4 + w;
     if (chunk >= n_chunks || *fallback) return;
     const int GQ = QS >> 3, L = (32 / GQ) * GQ, g = lane % GQ;  // lane -> query-token group as in k_chunkmax16
     if (lane >= L) return;
-    const long long c0 = (long long)chunk * 1024;
-    const int rows = (int)min(1024ll, K - c0);
+    const long long c0 = (long long)chunk * chunk_rows;
+    const int rows = (int)min((long long)chunk_rows, K - c0);
     const uint4 *base = reinterpret_cast<const uint4 *>(ST16 + ((size_t)b * K + c0) * QS);
     const int total = rows * GQ;
     // this lane's 8 thresholds as packed halfwords; padding rows (tau = 65536) never match

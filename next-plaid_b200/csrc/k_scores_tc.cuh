@@ -280,7 +280,7 @@ PB_DEV float pinned_dot(const float *__restrict__ q, const float *__restrict__ c
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_collect16_tc(const unsigned short *__restrict__ ST16, const float *__restrict__ Q, const int *__restrict__ q_off,
-               const float *__restrict__ C, int dim, int code_margin, long long K, int QS, int n_chunks,
+               const float *__restrict__ C, int dim, int code_margin, long long K, int QS, int n_chunks, int chunk_rows,
                const uint32_t *__restrict__ tau, int cap, int *__restrict__ counts, u64 *__restrict__ list,
                int *__restrict__ fallback) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
@@ -288,8 +288,8 @@ k_collect16_tc(const unsigned short *__restrict__ ST16, const float *__restrict_
     if (chunk >= n_chunks || *fallback) return;
     const int GQ = QS >> 3, L = (32 / GQ) * GQ, g = lane % GQ;  // lane -> query-token group as in k_chunkmax16
     if (lane >= L) return;
-    const long long c0 = (long long)chunk * 1024;
-    const int rows = (int)min(1024ll, K - c0);
+    const long long c0 = (long long)chunk * chunk_rows;
+    const int rows = (int)min((long long)chunk_rows, K - c0);
     const uint4 *base = reinterpret_cast<const uint4 *>(ST16 + ((size_t)b * K + c0) * QS);
     const int total = rows * GQ;
     // this lane's 8 thresholds as packed halfwords; padding rows (tau = 65536) never match
