@@ -54,7 +54,8 @@ def test_tensor_core_table_equals_exact_path_and_oracle(oracle, npb, corpus, kw,
         wb = plain.last_work_counters()
         assert wa["n_k1_tc"] > 0 and wa["n_k1_tc_redo"] == 0, wa            # the tensor-core pass did the work
         assert wb["n_k1_tc"] == 0 and wb["n_probe_threshold"] > 0, wb
-        for k in ("n_cells", "n_candidates", "n_filter_docs", "n_exact_docs"):   # same cells, candidates, kept docs
+        for k in ("n_cells", "n_candidates", "n_filter_docs"):   # same cells, candidates, kept docs (the filter's
+            # survivor count may differ: its error bound includes the table's code error)
             assert wa[k] == wb[k], (k, wa, wb)
         for q, x, y in zip(qs, a, b):
             w = oracle.search_one(ix, q, po)
