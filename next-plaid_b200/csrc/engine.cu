@@ -1208,7 +1208,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         // the radix-select probe, a trace) or the shape is outside the kernel's (DESIGN.md "a2")
         int n_chunks_k = 0;
         probe_chunk_rows(ix->K, n_probe, &n_chunks_k);
-        const bool want_tc = k1_tc_usable(ix) && fast && !ix->k1_diag && !all_eligible && !big_probe && !d_elig &&
+        const bool want_tc = k1_tc_usable(ix) && fast && ix->probe16 && !ix->k1_diag && !all_eligible && !big_probe && !d_elig &&
                              QS / 8 <= 32 && n_chunks_k >= n_probe && n_probe <= 192;
         // One pass over the sub-batch.  use_tc: a flagged query or a probe-list overflow raises a device flag instead of
         // being read back mid-way; the pass then finishes on (memory-safe) garbage and *redo asks for the exact pass.
