@@ -6,7 +6,6 @@
 #include "kernels.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_segmented_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 
 #include <algorithm>
@@ -242,7 +241,7 @@ struct Workspace {
     cudaEvent_t call_ev[2] = {};                // around a whole search call
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2,  cellbits,
-        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc, mslot, skeys, skeys2, cand3, segs, sorttmp, slicecnt;
+        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc, mslot, slicecnt;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -294,10 +293,6 @@ struct pb_index {
     int cent_exp = 0;          // centroids enter the tensor-core operands scaled by 2^cent_exp (max norm in [1, 2))
     bool k1_diag = false;      // also run the exact table and report the largest code difference (PB_K1_TC_DIAG=1)
     DevBuf cent_h16t, cent_l16t;  // its centroid operands: fp16 hi / lo, UMMA tile order
-    bool fma2_exact = false;   // FFMA2 dots in k_exact (PB_FMA2_EXACT=1; prepared, to be measured)
-    bool approx_cg = false;    // k_approx16 row gathers bypass L1 allocation (PB_APPROX_CG=1)
-    bool approx_sort = false;  // PB_APPROX_SORT=1 (experiment): candidates sorted by topical signature before the first pass
-    DevBuf doc_sig;            // [D] most frequent code of every doc (only with approx_sort)
     int approx_grid = 8;       // k_approx16 CTAs per SM and query (PB_APPROX_GRID)
     int xtc_grid = 32;         // k_exact_tc CTAs per SM across the batch (PB_XTC_GRID)
     bool probe16 = true;       // a3 threshold-first selection on the 16-bit table (PB_PROBE16=0: per-lane lists only)
@@ -355,7 +350,8 @@ static size_t smem_exact(int dim, int packed) {
 }
 
 template <class Kern> static pb_status set_smem(Kern k, size_t bytes) {
-    if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // a kernel's static shared memory counts towards the 48 KB a launch may use without opting in
+    if (bytes > 40 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return PB_OK;
 }
 
@@ -559,7 +555,7 @@ pb_status pb_index_finalize(pb_index *ix) {
         CKS(counts.ensure((size_t)ix->D * 4));
         const int blocks = (int)std::min<long long>(ix->D, (long long)ix->sm_count * 16);
         k_unique_codes<<<blocks, 128>>>(ix->codes.as<uint32_t>(), ix->doc_off.as<long long>(), ix->D, nullptr, nullptr,
-                                        counts.as<int>(), nullptr);
+                                        counts.as<int>());
         CK(cudaGetLastError());
         std::vector<int> hc((size_t)ix->D);
         CK(cudaMemcpy(hc.data(), counts.p, hc.size() * 4, cudaMemcpyDeviceToHost));
@@ -578,12 +574,9 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_FAST_EXACT")) ix->fast_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_FILTER_V1")) ix->filter_v1 = atoi(e) != 0;
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
-        if (const char *e = getenv("PB_FMA2_EXACT")) ix->fma2_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC_DIAG")) ix->k1_diag = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC")) ix->k1_tc = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC_E")) ix->k1_margin = std::max(1, atoi(e));
-        if (const char *e = getenv("PB_APPROX_CG")) ix->approx_cg = atoi(e) != 0;
-        if (const char *e = getenv("PB_APPROX_SORT")) ix->approx_sort = atoi(e) != 0;
         if (const char *e = getenv("PB_APPROX_GRID")) ix->approx_grid = std::max(1, atoi(e));
         if (const char *e = getenv("PB_XTC_GRID")) ix->xtc_grid = std::max(1, atoi(e));
     }
@@ -626,10 +619,8 @@ pb_status pb_index_finalize(pb_index *ix) {
     CKS(ix->ucodes.ensure(std::max<size_t>((size_t)ix->n_ucodes * 4, 16)));
     if (ix->D > 0) {
         const int blocks = (int)std::min<long long>(ix->D, (long long)ix->sm_count * 16);
-        if (ix->approx_sort) CKS(ix->doc_sig.ensure((size_t)ix->D * 4));
         k_unique_codes<<<blocks, 128>>>(ix->codes.as<uint32_t>(), ix->doc_off.as<long long>(), ix->D,
-                                        ix->udoc_off.as<long long>(), ix->ucodes.as<uint32_t>(), nullptr,
-                                        ix->approx_sort ? ix->doc_sig.as<uint32_t>() : nullptr);
+                                        ix->udoc_off.as<long long>(), ix->ucodes.as<uint32_t>(), nullptr);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
     }
@@ -941,7 +932,7 @@ static pb_status launch_exact(pb_index *ix, Workspace &ws, const KeptView &kv, i
     long long want = std::max<long long>(1, ((long long)ix->sm_count * 16 + B - 1) / B);
     int gx = (int)std::max<long long>(1, std::min<long long>(chunks, want));
     PB_DIM_SWITCH(ix->dim, {
-        auto kern = ix->fma2_exact ? k_exact<DIM, false, true> : k_exact<DIM, false, false>;
+        auto kern = k_exact<DIM, false>;
         CKS(set_smem(kern, smem_exact(DIM, ix->packed)));
         KEV_BEGIN(PB_KERNEL_EXACT);
         kern<<<dim3(gx, B), 128, smem_exact(DIM, ix->packed), ws.stream>>>(
@@ -1373,33 +1364,9 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             const uint32_t *list = ws.cand.as<uint32_t>();
             const int *list_n = ws.ncand.as<int>();
             unsigned long long *cnt = ws.counters.as<unsigned long long>();
-            if (ix->approx_sort && ix->doc_sig.p) {
-                // experiment: one segmented radix sort of every query's candidates by their doc signature, so that
-                // neighbours in the list share score-table rows in L1 (the first pass then walks contiguous slices)
-                CKS(ws.skeys.ensure((size_t)B * ix->D * 4));
-                CKS(ws.skeys2.ensure((size_t)B * ix->D * 4));
-                CKS(ws.cand3.ensure((size_t)B * ix->D * 4));
-                CKS(ws.segs.ensure((size_t)B * 16 + 16));
-                long long *seg_b = ws.segs.as<long long>(), *seg_e = ws.segs.as<long long>() + B;
-                k_cand_signatures<<<dim3(ix->sm_count, B), 256, 0, ws.stream>>>(list, ix->D, list_n, ix->doc_sig.as<uint32_t>(),
-                                                                               ws.skeys.as<uint32_t>(), seg_b, seg_e);
-                int kbits = 1;
-                while ((1ll << kbits) < ix->K) ++kbits;
-                size_t tb = 0;
-                CK(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tb, ws.skeys.as<uint32_t>(), ws.skeys2.as<uint32_t>(), list,
-                                                            ws.cand3.as<uint32_t>(), (int)((long long)B * ix->D), B, seg_b, seg_e, 0,
-                                                            kbits, ws.stream));
-                CKS(ws.sorttmp.ensure(tb + 16));
-                CK(cub::DeviceSegmentedRadixSort::SortPairs(ws.sorttmp.p, tb, ws.skeys.as<uint32_t>(), ws.skeys2.as<uint32_t>(), list,
-                                                            ws.cand3.as<uint32_t>(), (int)((long long)B * ix->D), B, seg_b, seg_e, 0,
-                                                            kbits, ws.stream));
-                list = ws.cand3.as<uint32_t>();
-                L[PB_STAGE_APPROX] += 2;
-            }
             KEV_BEGIN(PB_KERNEL_APPROX16);
-            (ix->approx_cg ? k_approx16<true> : k_approx16<false>)<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
-                                                  ix->udoc_off.as<long long>(), list, ix->D, list_n, ws.lsum.as<uint32_t>(),
-                                                  cnt, ix->approx_sort && ix->doc_sig.p ? 1 : 0);
+            k_approx16<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
+                                                  ix->udoc_off.as<long long>(), list, ix->D, list_n, ws.lsum.as<uint32_t>(), cnt);
             KEV_END(PB_KERNEL_APPROX16);
             // band per query token in code units (W = band * nq + 8).  Exact table: +-1 code of rounding per token and side
             // plus the fp32 summation error -> 4.  Estimate table (k_scores_tc.cuh): W = nq (1.004 + 2 err) + nq^2/256 + 4
@@ -1821,7 +1788,7 @@ extern "C" pb_status pb_maxsim_scores(int32_t device, const float *query, int32_
     switch (dim) {
 #define PB_CASE(DV)                                                                                              \
     case DV: {                                                                                                   \
-        auto kern = k_exact<DV, true, false>;                                                                           \
+        auto kern = k_exact<DV, true>;                                                                           \
         CKS(set_smem(kern, smem_exact(DV, 0)));                                                                  \
         kern<<<dim3(gx, 1), 128, smem_exact(DV, 0)>>>(dQ.as<float>(), dqoff.as<int>(), QS, nullptr, nullptr, 8, nullptr, \
                                                    nullptr, nullptr, dtok.as<float>(), dkept.as<uint32_t>(),    \

@@ -80,34 +80,23 @@ __global__ void k_max_row_norm(const float *__restrict__ C, long long K, int dim
 // row of code r of each group of four codes; maxima stay packed (u16x2 SIMD max).
 PB_DEV uint32_t pick4(const uint4 &c, int r) { return r == 0 ? c.x : (r == 1 ? c.y : (r == 2 ? c.z : c.w)); }
 
-template <bool CG>
-PB_DEV uint4 gather16(const char *p) {
-    return CG ? __ldcg(reinterpret_cast<const uint4 *>(p)) : *reinterpret_cast<const uint4 *>(p);
-}
-// CG: row gathers with ld.global.cg (no L1 allocation; PB_APPROX_CG=1, to be measured)
-// chunked = 1: a CTA walks one contiguous slice of the list (its 8 warps side by side), so docs that are neighbours in
-// the list meet in the same L1 -- the point of sorting the candidates by signature (PB_APPROX_SORT); 0: grid-stride.
-template <bool CG>
+PB_DEV uint4 gather16(const char *p) { return *reinterpret_cast<const uint4 *>(p); }
+// (ld.global.cg row gathers and a signature-sorted candidate order with contiguous slices per CTA were measured on
+// config B -- 3.10 / 3.37 ms for the stage against 3.07 -- and removed; tools/tma_gather_bench.cu has the ceiling.)
 __global__ void __launch_bounds__(256, 4)
 k_approx16(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
            const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off,
            const uint32_t *__restrict__ cand, long long cand_cap, const int *__restrict__ n_cand,
-           uint32_t *__restrict__ lsum, unsigned long long *__restrict__ tok_counter, int chunked) {
+           uint32_t *__restrict__ lsum, unsigned long long *__restrict__ tok_counter) {
     const int b = blockIdx.y;
     const int nq = q_off[b + 1] - q_off[b];
-    int n = n_cand[b];
+    const int n = n_cand[b];
     const int lane = threadIdx.x & 31, r = lane >> 2, sl = lane & 3;  // 8 row groups x 4 lanes x 16 bytes
-    int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
     const char *STb = reinterpret_cast<const char *>(ST16 + (size_t)b * K * QS);
     const unsigned rowb = (unsigned)QS * 2u;
     unsigned long long my_tokens = 0;
     int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (chunked) {
-        const int per = (n + gridDim.x - 1) / gridDim.x;
-        i = blockIdx.x * per + (threadIdx.x >> 5);
-        n = min(n, (int)(blockIdx.x + 1) * per);
-        warps_per_grid = blockDim.x >> 5;
-    }
     uint32_t d = 0;
     long long t0 = 0, t1 = 0;
     if (i < n) {
@@ -140,7 +129,7 @@ k_approx16(const unsigned short *__restrict__ ST16, const int *__restrict__ q_of
                     uint4 v[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e)
-                        v[e] = gather16<CG>(col + (size_t)__shfl_sync(PB_FULL, e < 4 ? cl0 : cl1, 8 * (e & 3) + r) * rowb);
+                        v[e] = gather16(col + (size_t)__shfl_sync(PB_FULL, e < 4 ? cl0 : cl1, 8 * (e & 3) + r) * rowb);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         m0 = __vmaxu2(m0, v[e].x);
@@ -151,7 +140,7 @@ k_approx16(const unsigned short *__restrict__ ST16, const int *__restrict__ q_of
                 } else {
                     const int ne = (int)((t1 - t + 7) >> 3);
                     for (int e = 0; e < ne; ++e) {
-                        const uint4 va = gather16<CG>(col + (size_t)__shfl_sync(PB_FULL, e < 4 ? cl0 : cl1, 8 * (e & 3) + r) * rowb);
+                        const uint4 va = gather16(col + (size_t)__shfl_sync(PB_FULL, e < 4 ? cl0 : cl1, 8 * (e & 3) + r) * rowb);
                         m0 = __vmaxu2(m0, va.x);
                         m1 = __vmaxu2(m1, va.y);
                         m2 = __vmaxu2(m2, va.z);

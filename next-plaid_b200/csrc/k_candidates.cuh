@@ -204,22 +204,17 @@ k_approx(const float *__restrict__ ST, const int *__restrict__ q_off, long long 
 // per doc, bitonic sort in shared memory; docs longer than PB_UCODE_MAX keep their raw code list
 // (duplicates are harmless for a max).  pass 0 counts (padded to 8), pass 1 writes.
 #define PB_UCODE_MAX 4096
-// sig (optional, pass 1): the doc's most frequent code (ties: the smaller code) -- a cheap topical signature; sorting
-// a query's candidates by it makes consecutive docs share score-table rows in L1 (PB_APPROX_SORT, k_approx16).
 __global__ void __launch_bounds__(128)
 k_unique_codes(const uint32_t *__restrict__ codes, const long long *__restrict__ doc_off, long long D,
-               const long long *__restrict__ udoc_off, uint32_t *__restrict__ ucodes, int *__restrict__ counts,
-               uint32_t *__restrict__ sig) {
+               const long long *__restrict__ udoc_off, uint32_t *__restrict__ ucodes, int *__restrict__ counts) {
     __shared__ u64 sk[PB_UCODE_MAX];
     __shared__ int scan_tmp[33];
-    __shared__ unsigned long long best_s;
     for (long long d = blockIdx.x; d < D; d += gridDim.x) {
         const long long t0 = doc_off[d];
         const int len = (int)(doc_off[d + 1] - t0);
         __syncthreads();
         if (len > PB_UCODE_MAX) {  // raw copy
             const int padded = (len + 7) & ~7;
-            if (sig && threadIdx.x == 0) sig[d] = codes[t0];
             if (!ucodes) {
                 if (threadIdx.x == 0) counts[d] = padded;
             } else {
@@ -233,24 +228,13 @@ k_unique_codes(const uint32_t *__restrict__ codes, const long long *__restrict__
         __syncthreads();
         bitonic_sort_u64(sk, P);
         int nu = 0;
-        if (sig && threadIdx.x == 0) best_s = 0ull;
-        __syncthreads();
         for (int base = 0; base < P; base += blockDim.x) {
             const int i = base + threadIdx.x;
             const int f = (i < len && (i == 0 || sk[i - 1] != sk[i])) ? 1 : 0;
             int tot;
             const int pos = block_exclusive_scan(f, scan_tmp, &tot);
             if (f && ucodes) ucodes[udoc_off[d] + nu + pos] = (uint32_t)sk[i];
-            if (f && sig) {  // run length of this code; (count, ~code) maximal = most frequent, smaller code on ties
-                int run = 1;
-                while (i + run < len && sk[i + run] == sk[i]) ++run;
-                atomicMax(&best_s, ((unsigned long long)run << 32) | (uint32_t)(~(uint32_t)sk[i]));
-            }
             nu += tot;
-        }
-        if (sig) {
-            __syncthreads();
-            if (threadIdx.x == 0) sig[d] = len ? ~(uint32_t)best_s : 0u;
         }
         const int padded = (nu + 7) & ~7;
         if (!ucodes) {
@@ -356,15 +340,3 @@ k_cut(const u64 *__restrict__ keys, const float *__restrict__ approx_in, long lo
     (void)approx_in;
 }
 
-// keys[b][i] = sig[cand[b][i]] for the segmented sort of PB_APPROX_SORT; seg_end[b] = b*stride + n_cand[b]
-__global__ void k_cand_signatures(const uint32_t *__restrict__ cand, long long stride, const int *__restrict__ n_cand,
-                                  const uint32_t *__restrict__ sig, uint32_t *__restrict__ keys, long long *__restrict__ seg_begin,
-                                  long long *__restrict__ seg_end) {
-    const int b = blockIdx.y, n = n_cand[b];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        keys[(size_t)b * stride + i] = sig[cand[(size_t)b * stride + i]];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        seg_begin[b] = (long long)b * stride;
-        seg_end[b] = (long long)b * stride + n;
-    }
-}

@@ -117,16 +117,6 @@ __global__ void k_interleave_query_rows(const float *__restrict__ Q, const int *
     }
 }
 
-// rows -> the pairwise-interleaved tile of tile_dots_f2 (element (r, j) at (r/2)*2*DIM + 2j + (r&1)), zero rows
-// beyond n_valid; plain loads, for tiles that are loaded once per CTA
-template <int DIM>
-PB_DEV void load_rows_interleaved(float *__restrict__ dst, const float *__restrict__ src, int n_valid, int rows) {
-    for (int idx = threadIdx.x; idx < rows * DIM; idx += blockDim.x) {
-        const int r = idx / DIM, j = idx - r * DIM;
-        dst[(r >> 1) * 2 * DIM + 2 * j + (r & 1)] = r < n_valid ? src[(size_t)r * DIM + j] : 0.0f;
-    }
-}
-
 // contiguous async copy of n_valid row pairs (2*DIM floats each), zero fill up to `pairs`
 template <int DIM>
 PB_DEV void load_pairs_async(float *__restrict__ dst, const float *__restrict__ src, int n_valid, int pairs) {

@@ -232,7 +232,8 @@ def test_data_parallel_kmeans_over_an_in_process_group(oracle, npb):
         assert c.shape == (n_blobs, dim) and np.abs(np.linalg.norm(c, axis=1) - 1.0).max() < 1e-5
         assert inertia(c) <= 1.5 * inertia(single) + 1e-3
         found = (centers @ c.T).max(1)
-        assert (found > 0.98).mean() >= 0.8          # most blobs have their own centroid (random init may merge a few)
+        found_single = (centers @ single.T).max(1)
+        assert (found > 0.98).mean() >= (found_single > 0.98).mean() - 0.2     # as many blobs recovered as by the single fit
 
 
 def test_kmeans_on_the_tensor_cores_matches_the_fp32_assignment_statistically(oracle, npb, monkeypatch):

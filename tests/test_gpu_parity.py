@@ -423,7 +423,7 @@ def test_long_queries_keep_the_fast_paths(oracle, npb, corpus, nq):
             assert np.array_equal(r.scores, w.scores), (kw, nq)
 
 
-@pytest.mark.parametrize("env", [{"PB_FILTER_V1": "1"}, {"PB_FAST_APPROX": "0"}, {"PB_K1_TC": "0"}, {"PB_APPROX_SORT": "1"}, {}])
+@pytest.mark.parametrize("env", [{"PB_FILTER_V1": "1"}, {"PB_FAST_APPROX": "0"}, {"PB_K1_TC": "0"}, {}])
 def test_both_filter_kernels_and_their_score_tables(oracle, npb, corpus, monkeypatch, env):
     # the linear filter (k_exact_tc2: centroid score from the 16-bit table + residual part on the tensor cores) on the
     # tensor-core table (default) and on the exact table (PB_K1_TC=0); the decompressing filter (k_exact_tc) when

@@ -13,14 +13,11 @@ VARIANTS = [
     ("exact fp32 a2 (PB_K1_TC=0)", {"PB_K1_TC": "0"}),
     ("exact a2 + code-diff diagnostic", {"PB_K1_TC_DIAG": "1"}),
     ("tensor cores, E=2", {"PB_K1_TC_E": "2"}),
-    ("FFMA2 in k_exact", {"PB_FMA2_EXACT": "1"}),
-    ("ld.global.cg gathers", {"PB_APPROX_CG": "1"}),
     ("approx grid x4", {"PB_APPROX_GRID": "4"}),
     ("filter off", {"PB_FAST_EXACT": "0"}),
     ("list-scan probe (exact a2)", {"PB_PROBE16": "0", "PB_K1_TC": "0"}),
     ("decompressing filter (PB_FILTER_V1)", {"PB_FILTER_V1": "1"}),
     ("nq=48 queries", {"__args__": "--nq 48"}),
-    ("candidates sorted by signature", {"PB_APPROX_SORT": "1"}),
 ]
 
 
