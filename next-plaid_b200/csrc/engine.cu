@@ -760,7 +760,7 @@ static pb_status launch_k1_table(pb_index *ix, Workspace &ws, int B, int QS, uns
         auto kern = k_scores16_tc<DV>;                                                                                 \
         CKS(set_smem(kern, sm));                                                                                       \
         KEV_BEGIN(PB_KERNEL_SCORES);                                                                                   \
-        kern<<<tiles, 192, sm, ws.stream>>>(ix->cent_h16t.as<__half>(), ix->cent_l16t.as<__half>(), ix->K,             \
+        kern<<<tiles, 320, sm, ws.stream>>>(ix->cent_h16t.as<__half>(), ix->cent_l16t.as<__half>(), ix->K,             \
                                             ws.Qh16t.as<__half>(), ws.Ql16t.as<__half>(), n_groups, B, QS,             \
                                             ws.qoff.as<int>(), ws.qrange_tc.as<float2>(), table, flags);               \
         KEV_END(PB_KERNEL_SCORES);                                                                                     \
@@ -1365,8 +1365,9 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             const int *list_n = ws.ncand.as<int>();
             unsigned long long *cnt = ws.counters.as<unsigned long long>();
             KEV_BEGIN(PB_KERNEL_APPROX16);
-            k_approx16<<<ga, 256, 0, ws.stream>>>(st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(),
-                                                  ix->udoc_off.as<long long>(), list, ix->D, list_n, ws.lsum.as<uint32_t>(), cnt);
+            (QS <= 32 ? k_approx16<4> : k_approx16<8>)<<<ga, 256, 0, ws.stream>>>(
+                st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(), list, ix->D, list_n,
+                ws.lsum.as<uint32_t>(), cnt);
             KEV_END(PB_KERNEL_APPROX16);
             // band per query token in code units (W = band * nq + 8).  Exact table: +-1 code of rounding per token and side
             // plus the fp32 summation error -> 4.  Estimate table (k_scores_tc.cuh): W = nq (1.004 + 2 err) + nq^2/256 + 4
@@ -1380,11 +1381,16 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             cand_list = ws.cand2.as<uint32_t>();
             cand_n = ws.ncand2.as<int>();
         }
-        if (tc)  // the exact approximate score of the docs around the cut from pinned-order dots (no dense fp32 S)
-            k_approx_recheck<<<dim3(ix->sm_count * 4, B), 256, 0, ws.stream>>>(
+        if (tc) {  // the exact approximate score of the docs around the cut from pinned-order dots (no dense fp32 S)
+            const size_t smr = (size_t)4 * PB_RECHECK_TILE + (size_t)nq_max * (ix->dim + 4) * 4 +
+                               (size_t)4 * (2 * (PB_RECHECK_LIST + 32) + QS) * 4;
+            CKS(set_smem(k_approx_recheck, smr));
+            const int gx = std::max(1, (8 * ix->sm_count + B - 1) / B);
+            k_approx_recheck<<<dim3(gx, B), 128, smr, ws.stream>>>(
                 ws.ST16.as<unsigned short>(), ws.Q.as<float>(), ws.qoff.as<int>(), ix->centroids.as<float>(), ix->dim, ix->K, QS,
                 ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(), cand_list, ix->D, cand_n, 2 * ix->k1_margin + 1,
                 ws.approx.as<float>(), ws.keys.as<u64>(), ws.counters.as<unsigned long long>() + B + 1, (uint32_t)ix->doc_id_base);
+        }
         else
             k_approx<<<dim3(ix->sm_count * 8, B), 256, 0, ws.stream>>>(
                 ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(),

@@ -82,16 +82,23 @@ PB_DEV uint32_t pick4(const uint4 &c, int r) { return r == 0 ? c.x : (r == 1 ? c
 
 PB_DEV uint4 gather16(const char *p) { return *reinterpret_cast<const uint4 *>(p); }
 // (ld.global.cg row gathers and a signature-sorted candidate order with contiguous slices per CTA were measured on
-// config B -- 3.10 / 3.37 ms for the stage against 3.07 -- and removed; tools/tma_gather_bench.cu has the ceiling.)
+// config B -- 3.10 / 3.37 ms for the stage against 3.07 -- and removed; tools/tma_gather_bench.cu has the ceiling:
+// 231 G rows/s for bare 64-byte LSU gathers, 264 G for 32-byte rows, 13.7 G through TMA gather4.)
+// LPR = lanes per row: 4 (rows up to 64 bytes: nq <= 32, eight rows per load instruction) or 8 (up to 128 bytes:
+// nq <= 64 in ONE pass over the codes, four rows per instruction).  Longer queries loop over 8*LPR-token column blocks.
+template <int LPR>
 __global__ void __launch_bounds__(256, 4)
 k_approx16(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
            const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off,
            const uint32_t *__restrict__ cand, long long cand_cap, const int *__restrict__ n_cand,
            uint32_t *__restrict__ lsum, unsigned long long *__restrict__ tok_counter) {
+    constexpr int RG = 32 / LPR;   // row groups of a warp = rows per load instruction
+    constexpr int QB = 8 * LPR;    // query tokens covered by one pass
+    constexpr int NI = 64 / RG;    // load instructions per 64 codes
     const int b = blockIdx.y;
     const int nq = q_off[b + 1] - q_off[b];
     const int n = n_cand[b];
-    const int lane = threadIdx.x & 31, r = lane >> 2, sl = lane & 3;  // 8 row groups x 4 lanes x 16 bytes
+    const int lane = threadIdx.x & 31, r = lane / LPR, sl = lane % LPR;
     const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
     const char *STb = reinterpret_cast<const char *>(ST16 + (size_t)b * K * QS);
     const unsigned rowb = (unsigned)QS * 2u;
@@ -115,32 +122,30 @@ k_approx16(const unsigned short *__restrict__ ST16, const int *__restrict__ q_of
         }
         my_tokens += (unsigned long long)(t1 - t0);
         uint32_t total = 0;
-        for (int qc = 0; qc < nq; qc += 32) {
+        for (int qc = 0; qc < nq; qc += QB) {
             const bool in_row = qc + 8 * sl < QS;  // QS is a multiple of 8: groups past the row are skipped
             const char *col = STb + (in_row ? (qc + 8 * sl) * 2 : 0);
-            uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;  // packed maxima of query tokens 8s .. 8s+7
-            // 64 codes per step: two coalesced loads (lane = code), handed to the eight row groups by shuffle; a row
-            // is 4 lanes x 16 bytes.  (Lists are padded to 8 with the last code; indices past the end repeat it,
-            // a max does not care.  The uniform 16-byte code loads this replaces cost one L1 tag lookup each --
-            // a fifth of all lookups of a kernel that is bound by them.)
+            uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;  // packed maxima of query tokens qc + 8 sl .. + 7
+            // 64 codes per step: two coalesced loads (lane = code), handed to the row groups by shuffle.  (Lists are
+            // padded to 8 with the last code; indices past the end repeat it, a max does not care.)
             for (long long t = t0; t < t1; t += 64) {
                 const uint32_t cl0 = ucodes[min(t + lane, t1 - 1)], cl1 = ucodes[min(t + 32 + lane, t1 - 1)];
                 if (t + 64 <= t1) {
-                    uint4 v[8];
+                    uint4 v[NI];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        v[e] = gather16(col + (size_t)__shfl_sync(PB_FULL, e < 4 ? cl0 : cl1, 8 * (e & 3) + r) * rowb);
+                    for (int e = 0; e < NI; ++e)
+                        v[e] = gather16(col + (size_t)__shfl_sync(PB_FULL, e < NI / 2 ? cl0 : cl1, RG * (e % (NI / 2)) + r) * rowb);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
+                    for (int e = 0; e < NI; ++e) {
                         m0 = __vmaxu2(m0, v[e].x);
                         m1 = __vmaxu2(m1, v[e].y);
                         m2 = __vmaxu2(m2, v[e].z);
                         m3 = __vmaxu2(m3, v[e].w);
                     }
                 } else {
-                    const int ne = (int)((t1 - t + 7) >> 3);
+                    const int ne = (int)((t1 - t + RG - 1) / RG);
                     for (int e = 0; e < ne; ++e) {
-                        const uint4 va = gather16(col + (size_t)__shfl_sync(PB_FULL, e < 4 ? cl0 : cl1, 8 * (e & 3) + r) * rowb);
+                        const uint4 va = gather16(col + (size_t)__shfl_sync(PB_FULL, e < NI / 2 ? cl0 : cl1, RG * (e % (NI / 2)) + r) * rowb);
                         m0 = __vmaxu2(m0, va.x);
                         m1 = __vmaxu2(m1, va.y);
                         m2 = __vmaxu2(m2, va.z);
@@ -148,9 +153,9 @@ k_approx16(const unsigned short *__restrict__ ST16, const int *__restrict__ q_of
                     }
                 }
             }
-            // combine the eight row groups, then add up this lane's (real) query tokens
+            // combine the row groups, then add up this lane's (real) query tokens
 #pragma unroll
-            for (int m = 4; m < 32; m <<= 1) {
+            for (int m = LPR; m < 32; m <<= 1) {
                 m0 = __vmaxu2(m0, __shfl_xor_sync(PB_FULL, m0, m));
                 m1 = __vmaxu2(m1, __shfl_xor_sync(PB_FULL, m1, m));
                 m2 = __vmaxu2(m2, __shfl_xor_sync(PB_FULL, m2, m));

@@ -23,7 +23,8 @@
 // E = 1.  Consumers use: code margin 2E + 1 = 3 for "could still be the maximum / in the top n", and the band
 // W = nq (1.004 + 2 err) + nq^2 / 256 + 4 for the first approximate pass (derivations at each kernel).
 // PB_K1_TC_DIAG=1 measures the largest code difference against the exact table (pb_work_counters).
-// grid = ceil(K/128) CTAs, 192 threads: warps 0-3 epilogue, warp 4 bulk-copy loader, warp 5 MMA issuer.
+// grid = ceil(K/128) CTAs, 320 threads: warps 0-7 epilogue (warp w: TMEM lanes 32*(w%4).., column half w/4), warp 8
+// bulk-copy loader, warp 9 MMA issuer.
 // ==========================================================================================
 
 // fp16 hi/lo split of `n` rows, scaled by 2^kexp, into UMMA tile order (128-row tiles, K-major core matrices);
@@ -82,7 +83,7 @@ __global__ void k_query_range_tc(const float2 *__restrict__ qrange, const int *_
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 k_scores16_tc(const __half *__restrict__ Ch, const __half *__restrict__ Cl, long long K, const __half *__restrict__ Qh,
               const __half *__restrict__ Ql, int n_groups, int B, int QS, const int *__restrict__ q_off,
               const float2 *__restrict__ qrange_tc, unsigned short *__restrict__ ST16, int *__restrict__ qflag) {
@@ -102,12 +103,12 @@ k_scores16_tc(const __half *__restrict__ Ch, const __half *__restrict__ Cl, long
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 128);
+            mbar_init(&tempty[i], 256);
         }
         mbar_init(abar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (w == 5) {
+    if (w == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -115,7 +116,7 @@ k_scores16_tc(const __half *__restrict__ Ch, const __half *__restrict__ Cl, long
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (w == 4) {
+    if (w == 8) {
         // ---------------- loader ----------------
         if (lane == 0) {
             mbar_expect_tx(abar, 2 * T_BYTES);
@@ -129,7 +130,7 @@ k_scores16_tc(const __half *__restrict__ Ch, const __half *__restrict__ Cl, long
                 bulk_g2s(Bs + (size_t)(2 * st + 1) * T_BYTES, reinterpret_cast<const unsigned char *>(Ql) + (size_t)g * T_BYTES, T_BYTES, &full[st]);
             }
         }
-    } else if (w == 5) {
+    } else if (w == 9) {
         // ---------------- MMA issuer: 3 products per k-step into one fp32 accumulator ----------------
         // instruction descriptor: c = f32, a = b = f16 (format 0), K-major, N = 128, M = 128
         const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -156,16 +157,17 @@ k_scores16_tc(const __half *__restrict__ Ch, const __half *__restrict__ Cl, long
             __syncwarp();
         }
     } else {
-        // ---------------- epilogue: thread = centroid row; 128 columns = 128 padded query rows ----------------
-        const long long c = c0 + threadIdx.x;
+        // ---------------- epilogue: thread = centroid row (TMEM lane), 64 of the 128 padded query rows ----------------
+        const int lg = w & 3, ch = w >> 2;
+        const long long c = c0 + 32 * lg + lane;
         for (int g = 0; g < n_groups; ++g) {
             const int acc = g & 1;
             mbar_wait(&tfull[acc], (uint32_t)((g >> 1) & 1));
             tc_fence_after();
 #pragma unroll 1
-            for (int cb = 0; cb < 4; ++cb) {
+            for (int cb = 2 * ch; cb < 2 * ch + 2; ++cb) {
                 uint32_t rr[32];
-                tc_ld32(tmem_base + ((uint32_t)(32 * w) << 16) + acc * 128 + cb * 32, rr);
+                tc_ld32(tmem_base + ((uint32_t)(32 * lg) << 16) + acc * 128 + cb * 32, rr);
 #pragma unroll
                 for (int sub = 0; sub < 4; ++sub) {
                     const long long row0 = (long long)g * 128 + cb * 32 + sub * 8;  // 8 query rows of one query (QS % 8 == 0)
@@ -192,7 +194,7 @@ k_scores16_tc(const __half *__restrict__ Ch, const __half *__restrict__ Cl, long
     }
     tc_fence_before();
     __syncthreads();
-    if (w == 5) {
+    if (w == 9) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
     }
@@ -450,90 +452,148 @@ k_cells_thr(const u64 *__restrict__ sel, const float *__restrict__ rows, const u
 // the doc's distinct codes; the code c* that attains the exact maximum satisfies code(c*) >= m_q - (2E + 1)
 // (e(c*) >= e(c^) for the estimate's argmax c^, so t(c*) >= t(c^) - 2 delta), so the exact per-token maximum is the
 // maximum of the pinned-order dots over the (typically one or two) codes within `code_margin` of m_q.
-// One warp per doc: pass A lane = query token gathers the 16-bit rows for m_q; pass B finds the (q, code) pairs
-// within the margin and queues them in a per-warp list, which the lanes then work off as independent dots
-// (one 128-bit-load FMA chain per lane).  Emits what k_approx emits: approx[b][i] and the cut key.
-// grid = (CTAs, B), 256 threads.
+// One warp per doc, 4 warps per CTA.  The doc's table rows (2*QS bytes per distinct code) are gathered ONCE, 16 bytes
+// per lane, into a 16 KB shared-memory tile of the warp; the column maxima and the margin test then read shared memory
+// (lane = query token), the (code, q) pairs inside the margin are queued, and the lanes work the queue off as
+// independent dots against the query rows staged in shared memory.  Docs with more distinct codes than a tile holds
+// take both passes tile by tile.  Emits what k_approx emits: approx[b][i] and the cut key.
+// grid = (CTAs, B), 128 threads, dynamic smem = recheck_smem_bytes(nq, dim).
 // ------------------------------------------------------------------------------------------
 #define PB_RECHECK_LIST 96
-__global__ void __launch_bounds__(256)
+#define PB_RECHECK_TILE 16384
+PB_DEV void recheck_flush(const float *__restrict__ Qs, int qld, const float *__restrict__ C, int dim, const uint32_t *pc,
+                          const uint32_t *pq, int cnt, uint32_t *qm, int lane) {
+    for (int j = lane; j < cnt; j += 32) {
+        const float *q = Qs + (size_t)pq[j] * qld, *c = C + (size_t)pc[j] * dim;
+        float s = 0.0f;
+#pragma unroll 8
+        for (int d = 0; d < dim; d += 4) {
+            const float4 a = *reinterpret_cast<const float4 *>(q + d), v = __ldg(reinterpret_cast<const float4 *>(c + d));
+            s = __fmaf_rn(a.x, v.x, s);
+            s = __fmaf_rn(a.y, v.y, s);
+            s = __fmaf_rn(a.z, v.z, s);
+            s = __fmaf_rn(a.w, v.w, s);
+        }
+        atomicMax(&qm[pq[j]], score_key_asc(s));
+    }
+}
+
+__global__ void __launch_bounds__(128)
 k_approx_recheck(const unsigned short *__restrict__ ST16, const float *__restrict__ Q, const int *__restrict__ q_off,
                  const float *__restrict__ C, int dim, long long K, int QS, const uint32_t *__restrict__ ucodes,
                  const long long *__restrict__ udoc_off, const uint32_t *__restrict__ cand, long long cand_cap,
                  const int *__restrict__ n_cand, int code_margin, float *__restrict__ approx, u64 *__restrict__ keys,
                  unsigned long long *__restrict__ tok_counter, uint32_t doc_id_base) {
-    __shared__ uint32_t pair_s[8][PB_RECHECK_LIST + 32];  // queued pairs of a warp: centroid ids ...
-    __shared__ uint32_t pairq_s[8][PB_RECHECK_LIST + 32];  // ... and their query tokens
-    __shared__ uint32_t qmax_s[8][32];
+    extern __shared__ __align__(16) unsigned char smem_rc[];
     const int b = blockIdx.y;
     const int r0 = q_off[b], nq = q_off[b + 1] - r0;
     const int n = n_cand[b];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
-    const unsigned short *STb = ST16 + (size_t)b * K * QS;
-    const unsigned rowb = (unsigned)QS * 2u;
-    uint32_t *pc = pair_s[w], *pq = pairq_s[w], *qm = qmax_s[w];
+    const int qld = dim + 4;
+    // layout: 4 row tiles | query rows [nq][dim + 4] | per warp: pair codes, pair tokens, per-token maxima [QS]
+    unsigned char *tile = smem_rc + (size_t)w * PB_RECHECK_TILE;
+    float *Qs = reinterpret_cast<float *>(smem_rc + 4 * PB_RECHECK_TILE);
+    uint32_t *wbase = reinterpret_cast<uint32_t *>(Qs + (size_t)nq * qld) + (size_t)w * (2 * (PB_RECHECK_LIST + 32) + QS);
+    uint32_t *pc = wbase, *pq = wbase + (PB_RECHECK_LIST + 32), *qm = pq + (PB_RECHECK_LIST + 32);
+    if (blockIdx.x * 4 >= n) return;
+    for (int idx = threadIdx.x; idx < nq * (dim / 4); idx += blockDim.x) {
+        const int r = idx / (dim / 4), g = idx - r * (dim / 4);
+        *reinterpret_cast<float4 *>(Qs + (size_t)r * qld + 4 * g) = reinterpret_cast<const float4 *>(Q + (size_t)(r0 + r) * dim)[g];
+    }
+    __syncthreads();
+    const char *STb = reinterpret_cast<const char *>(ST16 + (size_t)b * K * QS);
+    const int rowb = QS * 2;                     // bytes per table row (multiple of 16)
+    const int lpr = rowb / 16;                   // lanes per row when a row is copied 16 bytes per lane
+    const int rpi = lpr <= 32 ? 32 / lpr : 1;    // rows per copy instruction
+    const int cap_rows = PB_RECHECK_TILE / rowb; // rows a tile holds
+    const int n_qc = (nq + 31) / 32;             // 32-token column chunks (QS <= 256)
     unsigned long long my_tokens = 0;
-    for (int i = blockIdx.x * (blockDim.x >> 5) + w; i < n; i += warps_per_grid) {
+    for (int i = blockIdx.x * 4 + w; i < n; i += gridDim.x * 4) {
         const uint32_t d = cand[(size_t)b * cand_cap + i];
         const long long t0 = udoc_off[d], t1 = udoc_off[d + 1];
-        my_tokens += (unsigned long long)(t1 - t0);
-        float score = 0.0f;
-        for (int qc = 0; qc < nq; qc += 32) {
-            const int q = qc + lane;
-            const bool live = q < nq;
-            const char *col = reinterpret_cast<const char *>(STb + (live ? q : 0));
-            // pass A: the largest estimate code per query token
-            const uint32_t m = gather_max<GatherU16>(col, rowb, ucodes, t0, t1);
-            const uint32_t lo = m > (uint32_t)code_margin ? m - (uint32_t)code_margin : 0u;
-            qm[lane] = 0u;  // exact maxima as score keys (0 = none: a doc without codes)
-            __syncwarp();
-            // pass B: queue the (code, q) pairs within the margin; the lanes work the queue off as independent dots
-            // whenever another step could overflow it, and once at the end
-            int cnt = 0;
-            for (long long t = t0; t < t1; t += 8) {
-                const uint4 ca = *reinterpret_cast<const uint4 *>(ucodes + t);
-                const uint4 cb = *reinterpret_cast<const uint4 *>(ucodes + t + 4);
-                const uint32_t cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-                uint32_t v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const unsigned short *>(col + (size_t)cs[e] * rowb);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    // lists are padded to 8 with the last code: a code equal to its predecessor is a repeat
-                    const bool hit = live && v[e] >= lo && (e == 0 || cs[e] != cs[e - 1]);
-                    const unsigned bal = __ballot_sync(PB_FULL, hit);
-                    if (hit) {
-                        const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
-                        pc[pos] = cs[e];
-                        pq[pos] = (uint32_t)q;
-                    }
-                    cnt += __popc(bal);
-                    if (cnt > PB_RECHECK_LIST || (t + 8 >= t1 && e == 7 && cnt > 0)) {
-                        __syncwarp();
-                        for (int j = lane; j < cnt; j += 32) {
-                            const float sdot = pinned_dot(Q + (size_t)(r0 + pq[j]) * dim, C + (size_t)pc[j] * dim, dim);
-                            atomicMax(&qm[pq[j] - qc], score_key_asc(sdot));
+        const int n_codes = (int)(t1 - t0);
+        my_tokens += (unsigned long long)n_codes;
+        const int n_tiles = (n_codes + cap_rows - 1) / cap_rows;
+        for (int q = lane; q < QS; q += 32) qm[q] = 0u;  // exact maxima as score keys (0 = none)
+        uint32_t m[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        int cnt = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int tl = 0; tl < n_tiles; ++tl) {
+                const int base = tl * cap_rows, rows = min(cap_rows, n_codes - base);
+                if (pass == 0 || n_tiles > 1) {  // a single-tile doc stays resident for the second pass
+                    __syncwarp();
+                    if (lpr <= 32) {
+                        const int rl = lane / lpr, piece = lane - rl * lpr;
+                        for (int r = rl; r < rows && rl < rpi; r += rpi) {
+                            const uint32_t c = ucodes[t0 + base + r];
+                            *reinterpret_cast<uint4 *>(tile + (size_t)r * rowb + 16 * piece) =
+                                *reinterpret_cast<const uint4 *>(STb + (size_t)c * rowb + 16 * piece);
                         }
-                        __syncwarp();
-                        cnt = 0;
+                    }
+                    __syncwarp();
+                }
+                if (pass == 0) {  // column maxima: lane = query token, one 2*32-byte smem wavefront per row
+#pragma unroll
+                    for (int qc = 0; qc < 8; ++qc) {
+                        if (qc >= n_qc) break;
+                        const int q = 32 * qc + lane;
+                        if (q < QS) {
+                            uint32_t mm = m[qc];
+                            const unsigned short *col = reinterpret_cast<const unsigned short *>(tile) + q;
+                            for (int r = 0; r < rows; ++r) mm = max(mm, (uint32_t)col[(size_t)r * QS]);
+                            m[qc] = mm;
+                        }
+                    }
+                } else {  // pairs within the margin of the maximum
+#pragma unroll
+                    for (int qc = 0; qc < 8; ++qc) {
+                        if (qc >= n_qc) break;
+                        const int q = 32 * qc + lane;
+                        const bool live = q < nq;
+                        const uint32_t lo = m[qc] > (uint32_t)code_margin ? m[qc] - (uint32_t)code_margin : 0u;
+                        const unsigned short *col = reinterpret_cast<const unsigned short *>(tile) + (q < QS ? q : 0);
+                        for (int r = 0; r < rows; ++r) {
+                            const uint32_t c = ucodes[t0 + base + r];  // warp-uniform
+                            // lists are padded to 8 with the last code: a code equal to its predecessor is a repeat
+                            const bool rep = base + r > 0 && c == ucodes[t0 + base + r - 1];
+                            const bool hit = live && !rep && (uint32_t)col[(size_t)r * QS] >= lo;
+                            const unsigned bal = __ballot_sync(PB_FULL, hit);
+                            if (bal == 0u) continue;
+                            if (hit) {
+                                const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+                                pc[pos] = c;
+                                pq[pos] = (uint32_t)q;
+                            }
+                            cnt += __popc(bal);
+                            if (cnt > PB_RECHECK_LIST) {
+                                __syncwarp();
+                                recheck_flush(Qs, qld, C, dim, pc, pq, cnt, qm, lane);
+                                __syncwarp();
+                                cnt = 0;
+                            }
+                        }
                     }
                 }
             }
-            __syncwarp();
-            // score += max for q ascending, skipping rows without a finite maximum (search.rs:318-320)
-            const uint32_t mk = qm[lane];
+        }
+        __syncwarp();
+        if (cnt > 0) recheck_flush(Qs, qld, C, dim, pc, pq, cnt, qm, lane);
+        __syncwarp();
+        // score += max for q ascending, skipping rows without a finite maximum (search.rs:318-320)
+        float score = 0.0f;
+        for (int qc = 0; qc < nq; qc += 32) {
+            const uint32_t mk = qc + lane < QS ? qm[qc + lane] : 0u;
             const int lim = min(32, nq - qc);
             for (int qq = 0; qq < lim; ++qq) {
                 const uint32_t kk = __shfl_sync(PB_FULL, mk, qq);
                 if (kk) score = __fadd_rn(score, key_to_score(kk));
             }
-            __syncwarp();
         }
         if (lane == 0) {
             approx[(size_t)b * cand_cap + i] = score;
             keys[(size_t)b * cand_cap + i] = ((u64)(~score_key_asc(score)) << 32) | (d + doc_id_base);
         }
+        __syncwarp();
     }
     if (lane == 0 && my_tokens) atomicAdd(tok_counter, my_tokens);
 }
