@@ -87,7 +87,7 @@ PB_DEV uint4 gather16(const char *p) { return *reinterpret_cast<const uint4 *>(p
 // LPR = lanes per row: 4 (rows up to 64 bytes: nq <= 32, eight rows per load instruction) or 8 (up to 128 bytes:
 // nq <= 64 in ONE pass over the codes, four rows per instruction).  Longer queries loop over 8*LPR-token column blocks.
 template <int LPR>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, LPR == 4 ? 4 : 2)
 k_approx16(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
            const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off,
            const uint32_t *__restrict__ cand, long long cand_cap, const int *__restrict__ n_cand,

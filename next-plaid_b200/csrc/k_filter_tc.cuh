@@ -309,6 +309,47 @@ k_exact_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, c
 // + 8e-6 (filter_eps_unit2 in engine.cu).  Flagged queries (no valid table) publish nothing -> no estimate -> every
 // kept doc survives.  Same grid / block / TMEM layout as k_exact_tc.
 // ------------------------------------------------------------------------------------------
+// the global loads of one token of k_exact_tc2: packed residual row (HBM), the score-table row of its centroid (L2), 1/|v|
+template <int PACKED, int SW>
+PB_DEV void tc2_load_token(const TokMeta &m, const uint8_t *__restrict__ residuals, const char *__restrict__ STb, unsigned rowb,
+                           int QS, const float *__restrict__ inv_norm, uint32_t (&pw)[PACKED / 4], uint32_t (&sw)[SW], float &inv) {
+    constexpr int NW = PACKED / 4;
+    constexpr bool PIECES = PACKED % 16 == 0;
+    inv = 0.0f;
+    if (m.r >= 0) {
+        const uint8_t *src = residuals + (size_t)m.g * PACKED;
+        if (PIECES) {
+#pragma unroll
+            for (int pc = 0; pc < PACKED / 16; ++pc) {
+                const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(src) + pc);
+                pw[4 * pc] = t4.x;
+                pw[4 * pc + 1] = t4.y;
+                pw[4 * pc + 2] = t4.z;
+                pw[4 * pc + 3] = t4.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) pw[i] = __ldg(reinterpret_cast<const uint32_t *>(src) + i);
+        }
+        const uint4 *srow = reinterpret_cast<const uint4 *>(STb + (size_t)m.code * rowb);  // 16-byte aligned (QS % 8 == 0)
+#pragma unroll
+        for (int i = 0; i < SW / 4; ++i) {
+            uint4 t4 = make_uint4(0, 0, 0, 0);
+            if (8 * i < QS) t4 = srow[i];
+            sw[4 * i] = t4.x;
+            sw[4 * i + 1] = t4.y;
+            sw[4 * i + 2] = t4.z;
+            sw[4 * i + 3] = t4.w;
+        }
+        inv = inv_norm[m.g];
+    } else {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) pw[i] = 0u;
+#pragma unroll
+        for (int i = 0; i < SW; ++i) sw[i] = 0u;
+    }
+}
+
 template <int DIM, int NBITS, int NQT>
 __global__ void __launch_bounds__(128, NQT == 32 ? 4 : 3)
 k_exact_tc2(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, const unsigned short *__restrict__ ST16,
@@ -323,8 +364,6 @@ k_exact_tc2(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
     constexpr uint32_t LBO_B = (NQT / 8) * 128, SBO = 128;
     constexpr int PACKED = DIM * NBITS / 8, NW = PACKED / 4;
     static_assert(PACKED % 4 == 0, "k_exact_tc2: packed rows are read in 32-bit words");
-    constexpr bool PIECES = PACKED % 16 == 0;
-    constexpr int P = PIECES ? PACKED / 16 : 1;
     constexpr int VB = 8 / NBITS;
     unsigned char *As = smem_x;                        // [128 tokens] fp16 residual tile: element (r, kc) at kc*LBO + 16 r
     unsigned char *Qb = As + A_BYTES;                  // [NQT query rows] fp16 operand tile
@@ -375,43 +414,13 @@ k_exact_tc2(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
     uint32_t phase = 0;
     const int row = threadIdx.x;  // one thread per token (= TMEM lane in the epilogue)
     TokMeta cur = locate_token<false>(c_lo * 128 + threadIdx.x, T, 0, nk, tp, kp, doc_off, codes);
+    uint32_t pw[NW], sw[SW];
+    float inv;
+    tc2_load_token<PACKED, SW>(cur, residuals, STb, rowb, QS, inv_norm, pw, sw, inv);
     for (long long chunk = c_lo; chunk < c_hi; ++chunk) {
         __syncthreads();  // previous chunk: TMEM read out, operand tile free
-        // ---- loads: the token's packed residual row (HBM), its centroid's score row (L2), 1/|v| ----
-        uint32_t pw[NW], sw[SW];
-        float inv = 0.0f;
-        if (cur.r >= 0) {
-            const uint8_t *src = residuals + (size_t)cur.g * PACKED;
-            if (PIECES) {
-#pragma unroll
-                for (int pc = 0; pc < P; ++pc) {
-                    const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(src) + pc);
-                    pw[4 * pc] = t4.x;
-                    pw[4 * pc + 1] = t4.y;
-                    pw[4 * pc + 2] = t4.z;
-                    pw[4 * pc + 3] = t4.w;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NW; ++i) pw[i] = __ldg(reinterpret_cast<const uint32_t *>(src) + i);
-            }
-            const uint4 *srow = reinterpret_cast<const uint4 *>(STb + (size_t)cur.code * rowb);  // rows are 16-byte aligned (QS % 8 == 0)
-#pragma unroll
-            for (int i = 0; i < SW / 4; ++i) {
-                uint4 t4 = make_uint4(0, 0, 0, 0);
-                if (8 * i < QS) t4 = srow[i];
-                sw[4 * i] = t4.x;
-                sw[4 * i + 1] = t4.y;
-                sw[4 * i + 2] = t4.z;
-                sw[4 * i + 3] = t4.w;
-            }
-            inv = inv_norm[cur.g];
-        } else {
-#pragma unroll
-            for (int i = 0; i < NW; ++i) pw[i] = 0u;
-#pragma unroll
-            for (int i = 0; i < SW; ++i) sw[i] = 0u;
-        }
+        // the next chunk's metadata and global loads go out first: they are in flight under this chunk's tile build,
+        // MMA and epilogue (software pipeline, one chunk deep)
         TokMeta nxt;
         nxt.r = -1;
         nxt.g = 0;
@@ -420,6 +429,9 @@ k_exact_tc2(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
             const int r_lo = max(__shfl_sync(PB_FULL, cur.r, 0), 0);
             nxt = locate_token<false>((chunk + 1) * 128 + threadIdx.x, T, r_lo, nk, tp, kp, doc_off, codes);
         }
+        uint32_t pwn[NW], swn[SW];
+        float invn;
+        tc2_load_token<PACKED, SW>(nxt, residuals, STb, rowb, QS, inv_norm, pwn, swn, invn);
         // ---- residual part of the token as fp16, straight into the operand tile: one table read per packed byte ----
 #pragma unroll
         for (int kc = 0; kc < KC; ++kc) {
@@ -508,6 +520,11 @@ k_exact_tc2(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
         }
         tc_fence_before();
         cur = nxt;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) pw[i] = pwn[i];
+#pragma unroll
+        for (int i = 0; i < SW; ++i) sw[i] = swn[i];
+        inv = invn;
     }
     __syncthreads();
     if (w == 0) {

@@ -478,7 +478,7 @@ PB_DEV void recheck_flush(const float *__restrict__ Qs, int qld, const float *__
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 2)
 k_approx_recheck(const unsigned short *__restrict__ ST16, const float *__restrict__ Q, const int *__restrict__ q_off,
                  const float *__restrict__ C, int dim, long long K, int QS, const uint32_t *__restrict__ ucodes,
                  const long long *__restrict__ udoc_off, const uint32_t *__restrict__ cand, long long cand_cap,
@@ -535,9 +535,8 @@ k_approx_recheck(const unsigned short *__restrict__ ST16, const float *__restric
                 if (pass == 0) {  // column maxima: lane = query token, one 2*32-byte smem wavefront per row
 #pragma unroll
                     for (int qc = 0; qc < 8; ++qc) {
-                        if (qc >= n_qc) break;
                         const int q = 32 * qc + lane;
-                        if (q < QS) {
+                        if (qc < n_qc && q < QS) {
                             uint32_t mm = m[qc];
                             const unsigned short *col = reinterpret_cast<const unsigned short *>(tile) + q;
                             for (int r = 0; r < rows; ++r) mm = max(mm, (uint32_t)col[(size_t)r * QS]);
@@ -547,7 +546,7 @@ k_approx_recheck(const unsigned short *__restrict__ ST16, const float *__restric
                 } else {  // pairs within the margin of the maximum
 #pragma unroll
                     for (int qc = 0; qc < 8; ++qc) {
-                        if (qc >= n_qc) break;
+                        if (qc >= n_qc) continue;  // warp-uniform
                         const int q = 32 * qc + lane;
                         const bool live = q < nq;
                         const uint32_t lo = m[qc] > (uint32_t)code_margin ? m[qc] - (uint32_t)code_margin : 0u;
