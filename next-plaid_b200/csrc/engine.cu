@@ -241,7 +241,7 @@ struct Workspace {
     cudaEvent_t call_ev[2] = {};                // around a whole search call
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2,  cellbits,
-        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc, mslot, slicecnt;
+        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc, mslot, slicecnt, rcmax, rcpairs, rcn;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -253,6 +253,7 @@ struct Workspace {
         subset_bits.zero_on_grow = true;
         elig.zero_on_grow = true;
         cellbits.zero_on_grow = true;
+        rcmax.zero_on_grow = true;
         return PB_OK;
     }
     ~Workspace() {
@@ -853,7 +854,8 @@ static pb_status run_k1_tc(pb_index *ix, Workspace &ws, const pb_search_params *
         ws.sel.as<u64>(), ws.k1rows.as<float>(), ws.ulist.as<uint32_t>(), ws.nulist.as<int>(), ws.qoff.as<int>(), ix->K, QS, n,
         cells_cap, p->has_centroid_score_threshold, p->centroid_score_threshold, batched ? 1 : 0,
         batched ? (long long)p->centroid_batch_size : ix->K, ws.cells.as<uint32_t>(), ws.ncells.as<int>(),
-        ws.ST16.as<unsigned short>(), ws.qrange.as<float2>(), cm, ws.Q.as<float>(), ix->centroids.as<float>(), ix->dim);
+        ws.ST16.as<unsigned short>(), ws.qrange.as<float2>(), cm, ws.Q.as<float>(), ix->centroids.as<float>(), ix->dim,
+        ws.cmax16.as<unsigned short>(), n_chunks, chunk_rows);
     CK(cudaGetLastError());
     L[PB_STAGE_PROBE] += 7;
     *cells_cap_out = cells_cap;
@@ -1326,7 +1328,9 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             k_cells<<<B, 256, sm2, ws.stream>>>(ws.sel.as<u64>(), ws.ST.as<float>(), ws.qoff.as<int>(), ix->K, QS, n,
                                                 cells_cap, p->has_centroid_score_threshold, p->centroid_score_threshold,
                                                 batched ? 1 : 0, batched ? (long long)p->centroid_batch_size : ix->K,
-                                                ws.cells.as<uint32_t>(), ws.ncells.as<int>());
+                                                ws.cells.as<uint32_t>(), ws.ncells.as<int>(),
+                                                thr_path ? ws.cmax16.as<unsigned short>() : nullptr, t_chunks, t_rows,
+                                                ws.qrange.as<float2>(), d_fallback);
             CK(cudaGetLastError());
             L[PB_STAGE_PROBE] += 3;
         }
@@ -1382,14 +1386,24 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             cand_n = ws.ncand2.as<int>();
         }
         if (tc) {  // the exact approximate score of the docs around the cut from pinned-order dots (no dense fp32 S)
-            const size_t smr = (size_t)4 * PB_RECHECK_TILE + (size_t)nq_max * (ix->dim + 4) * 4 +
-                               (size_t)4 * (2 * (PB_RECHECK_LIST + 32) + QS) * 4;
-            CKS(set_smem(k_approx_recheck, smr));
-            const int gx = std::max(1, (8 * ix->sm_count + B - 1) / B);
-            k_approx_recheck<<<dim3(gx, B), 128, smr, ws.stream>>>(
-                ws.ST16.as<unsigned short>(), ws.Q.as<float>(), ws.qoff.as<int>(), ix->centroids.as<float>(), ix->dim, ix->K, QS,
-                ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(), cand_list, ix->D, cand_n, 2 * ix->k1_margin + 1,
-                ws.approx.as<float>(), ws.keys.as<u64>(), ws.counters.as<unsigned long long>() + B + 1, (uint32_t)ix->doc_id_base);
+            const int rc_cap = 2 * Mcap + 1024, pair_cap = 64 * rc_cap;
+            CKS(ws.rcmax.ensure((size_t)B * rc_cap * QS * 4));
+            CKS(ws.rcpairs.ensure((size_t)B * pair_cap * 8));
+            CKS(ws.rcn.ensure((size_t)B * 4 + 16));
+            CK(cudaMemsetAsync(ws.rcn.p, 0, (size_t)B * 4, ws.stream));
+            int *d_fb = const_cast<int *>(d_probe_fallback);
+            k_recheck_pairs<<<dim3(ix->sm_count * 2, B), 256, 0, ws.stream>>>(
+                ws.ST16.as<unsigned short>(), ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(),
+                cand_list, ix->D, cand_n, 2 * ix->k1_margin + 1, rc_cap, pair_cap, ws.rcpairs.as<u64>(), ws.rcn.as<int>(), d_fb,
+                ws.counters.as<unsigned long long>() + B + 1);
+            k_recheck_dots<<<dim3(ix->sm_count * 2, B), 128, 0, ws.stream>>>(ws.rcpairs.as<u64>(), ws.rcn.as<int>(), pair_cap,
+                                                                             ws.Q.as<float>(), ws.qoff.as<int>(),
+                                                                             ix->centroids.as<float>(), ix->dim, rc_cap, QS,
+                                                                             ws.rcmax.as<uint32_t>());
+            k_recheck_sum<<<dim3(ix->sm_count, B), 256, 0, ws.stream>>>(ws.rcmax.as<uint32_t>(), ws.qoff.as<int>(), QS, cand_list,
+                                                                        ix->D, cand_n, rc_cap, ws.approx.as<float>(),
+                                                                        ws.keys.as<u64>(), (uint32_t)ix->doc_id_base);
+            L[PB_STAGE_APPROX] += 2;
         }
         else
             k_approx<<<dim3(ix->sm_count * 8, B), 256, 0, ws.stream>>>(

@@ -212,14 +212,9 @@ k_select_u32(const uint32_t *__restrict__ sel_keys, const int *__restrict__ sel_
             for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
             __syncthreads();
             const uint32_t prefix = prefix_s, mask = mask_s;
-            // the sums of a query crowd into a few digits: one atomic per distinct digit of a warp, not per element
-            for (int i0 = 0; i0 < ns; i0 += blockDim.x) {
-                const int i = i0 + threadIdx.x;
-                const uint32_t k = i < ns ? ~L[i] : 0u;
-                const bool in = i < ns && (k & mask) == prefix;
-                const uint32_t digit = in ? ((k >> shift) & 255u) : 256u + (threadIdx.x & 31);
-                const unsigned peers = __match_any_sync(PB_FULL, digit);
-                if (in && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
+            for (int i = threadIdx.x; i < ns; i += blockDim.x) {  // (warp-aggregated via match.any measured 2x slower)
+                const uint32_t k = ~L[i];
+                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
             }
             __syncthreads();
             if (threadIdx.x == 0) {

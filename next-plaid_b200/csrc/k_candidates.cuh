@@ -280,13 +280,9 @@ k_cut(const u64 *__restrict__ keys, const float *__restrict__ approx_in, long lo
             for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
             __syncthreads();
             const u64 prefix = prefix_s, mask = mask_s;
-            for (int i0 = 0; i0 < n; i0 += blockDim.x) {  // warp-aggregated: one atomic per distinct digit of a warp
-                const int i = i0 + threadIdx.x;
-                const u64 k = i < n ? kb[i] : 0ull;
-                const bool in = i < n && (k & mask) == prefix;
-                const uint32_t digit = in ? (uint32_t)((k >> shift) & 255ull) : 256u + (threadIdx.x & 31);
-                const unsigned peers = __match_any_sync(PB_FULL, digit);
-                if (in && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                u64 k = kb[i];
+                if ((k & mask) == prefix) atomicAdd(&hist[(int)((k >> shift) & 255ull)], 1);
             }
             __syncthreads();
             if (threadIdx.x == 0) {

@@ -240,12 +240,17 @@ __global__ void k_topn_merge(const u64 *__restrict__ partial, const int *__restr
 __global__ void __launch_bounds__(256)
 k_cells(const u64 *__restrict__ sel, const float *__restrict__ ST, const int *__restrict__ q_off,
         long long K, int QS, int n, int cells_cap, int has_thr, float thr, int batched,
-        long long slab, uint32_t *__restrict__ cells, int *__restrict__ n_cells) {
+        long long slab, uint32_t *__restrict__ cells, int *__restrict__ n_cells,
+        const unsigned short *__restrict__ cmax16, int n_chunks, int chunk_rows, const float2 *__restrict__ qrange,
+        const int *__restrict__ gate) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     const int nq = q_off[b + 1] - q_off[b];
     const int total = nq * n;
     const int P = next_pow2(max(total, 1));
+    // chunk maxima of the 16-bit table (threshold-first probe) prune the slab-prefix scan below; not when the
+    // probe fell back (flagged query: no valid table)
+    const bool use_cmax = cmax16 != nullptr && !(gate && *gate);
     u64 *s = reinterpret_cast<u64 *>(smem_raw);  // [P] sort buffer, then unique list
     int *flags = reinterpret_cast<int *>(s + P);  // [P]
     __shared__ int scan_tmp[33];
@@ -316,8 +321,25 @@ k_cells(const u64 *__restrict__ sel, const float *__restrict__ ST, const int *__
                         if (!(kv != 0u && v >= thr)) continue;  // finite and over the threshold
                         // entered iff fewer than n earlier slab entries are "not worse" than v
                         int cnt = 0;
-                        for (long long c2 = s0 + lane; c2 < (long long)c; c2 += 32)
-                            cnt += (score_key_asc(STb[(size_t)c2 * QS + q]) >= kv) ? 1 : 0;
+                        if (use_cmax) {  // a chunk whose largest code is below code(v) holds no entry >= v
+                            const float2 rg = qrange[b];
+                            const int kv16 = (int)fminf(fmaxf(floorf(__fmaf_rn(v, rg.y, rg.x)), 0.0f), 65535.0f);
+                            const long long ch_lo = s0 / chunk_rows, ch_hi = ((long long)c + chunk_rows - 1) / chunk_rows;
+                            for (long long ch0 = ch_lo; ch0 < ch_hi; ch0 += 32) {
+                                const long long chl = ch0 + lane;
+                                const bool need = chl < ch_hi && (int)cmax16[((size_t)b * n_chunks + chl) * QS + q] >= kv16;
+                                unsigned todo = __ballot_sync(PB_FULL, need);
+                                while (todo) {
+                                    const long long ch = ch0 + (__ffs(todo) - 1);
+                                    todo &= todo - 1;
+                                    const long long r_lo = max(s0, ch * chunk_rows), r_hi = min((long long)c, (ch + 1) * chunk_rows);
+                                    for (long long c2 = r_lo + lane; c2 < r_hi; c2 += 32)
+                                        cnt += (score_key_asc(STb[(size_t)c2 * QS + q]) >= kv) ? 1 : 0;
+                                }
+                            }
+                        } else
+                            for (long long c2 = s0 + lane; c2 < (long long)c; c2 += 32)
+                                cnt += (score_key_asc(STb[(size_t)c2 * QS + q]) >= kv) ? 1 : 0;
 #pragma unroll
                         for (int m = 16; m >= 1; m >>= 1) cnt += __shfl_xor_sync(PB_FULL, cnt, m);
                         if (cnt < n) keep = 1;

@@ -372,7 +372,8 @@ k_cells_thr(const u64 *__restrict__ sel, const float *__restrict__ rows, const u
             const int *__restrict__ n_u, const int *__restrict__ q_off, long long K, int QS, int n, int cap, int has_thr,
             float thr, int batched, long long slab, uint32_t *__restrict__ cells, int *__restrict__ n_cells,
             const unsigned short *__restrict__ ST16, const float2 *__restrict__ qrange, int code_margin,
-            const float *__restrict__ Q, const float *__restrict__ C, int dim) {
+            const float *__restrict__ Q, const float *__restrict__ C, int dim, const unsigned short *__restrict__ cmax16,
+            int n_chunks, int chunk_rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *flags = reinterpret_cast<int *>(smem_raw);  // [cap]
     __shared__ int scan_tmp[33];
@@ -417,12 +418,26 @@ k_cells_thr(const u64 *__restrict__ sel, const float *__restrict__ rows, const u
                         const int kv16 = (int)fminf(fmaxf(floorf(__fmaf_rn(v, rg.y, rg.x)), 0.0f), 65535.0f);
                         const unsigned short *col16 = ST16 + (size_t)b * K * QS + q;
                         const float *qrow = Q + (size_t)(q_off[b] + q) * dim;
+                        // the chunk maxima of the probe (k_chunkmax16) rule out almost every chunk of the slab prefix: a
+                        // chunk whose largest estimate code is <= kv16 - code_margin holds no entry that could reach v
                         int cnt = 0;
-                        for (long long c2 = s0 + lane; c2 < (long long)c; c2 += 32) {
-                            const int cd2 = (int)col16[(size_t)c2 * QS];
-                            if (cd2 >= kv16 + code_margin) ++cnt;
-                            else if (cd2 + code_margin > kv16)
-                                cnt += (score_key_asc(pinned_dot(qrow, C + (size_t)c2 * dim, dim)) >= kv) ? 1 : 0;
+                        const long long ch_lo = s0 / chunk_rows, ch_hi = ((long long)c + chunk_rows - 1) / chunk_rows;
+                        for (long long ch0 = ch_lo; ch0 < ch_hi; ch0 += 32) {
+                            const long long chl = ch0 + lane;
+                            const bool need = chl < ch_hi &&
+                                              (int)cmax16[((size_t)b * n_chunks + chl) * QS + q] + code_margin > kv16;
+                            unsigned todo = __ballot_sync(PB_FULL, need);
+                            while (todo) {
+                                const long long ch = ch0 + (__ffs(todo) - 1);
+                                todo &= todo - 1;
+                                const long long r_lo = max(s0, ch * chunk_rows), r_hi = min((long long)c, (ch + 1) * chunk_rows);
+                                for (long long c2 = r_lo + lane; c2 < r_hi; c2 += 32) {
+                                    const int cd2 = (int)col16[(size_t)c2 * QS];
+                                    if (cd2 >= kv16 + code_margin) ++cnt;
+                                    else if (cd2 + code_margin > kv16)
+                                        cnt += (score_key_asc(pinned_dot(qrow, C + (size_t)c2 * dim, dim)) >= kv) ? 1 : 0;
+                                }
+                            }
                         }
 #pragma unroll
                         for (int m = 16; m >= 1; m >>= 1) cnt += __shfl_xor_sync(PB_FULL, cnt, m);
@@ -451,137 +466,124 @@ k_cells_thr(const u64 *__restrict__ sel, const float *__restrict__ rows, const u
 // still make the cut, without a dense fp32 S.  For a doc and a query token q, m_q = the largest estimate code over
 // the doc's distinct codes; the code c* that attains the exact maximum satisfies code(c*) >= m_q - (2E + 1)
 // (e(c*) >= e(c^) for the estimate's argmax c^, so t(c*) >= t(c^) - 2 delta), so the exact per-token maximum is the
-// maximum of the pinned-order dots over the (typically one or two) codes within `code_margin` of m_q.
-// One warp per doc, 4 warps per CTA.  The doc's table rows (2*QS bytes per distinct code) are gathered ONCE, 16 bytes
-// per lane, into a 16 KB shared-memory tile of the warp; the column maxima and the margin test then read shared memory
-// (lane = query token), the (code, q) pairs inside the margin are queued, and the lanes work the queue off as
-// independent dots against the query rows staged in shared memory.  Docs with more distinct codes than a tile holds
-// take both passes tile by tile.  Emits what k_approx emits: approx[b][i] and the cut key.
-// grid = (CTAs, B), 128 threads, dynamic smem = recheck_smem_bytes(nq, dim).
+// maximum of the pinned-order dots over the (typically one or two) codes within `code_margin` of m_q.  Three kernels,
+// each with all the parallelism the work has (a one-kernel form -- warp per doc, dots in place -- ran at 8 warps per
+// SM and 1.6 ms):
+//   k_recheck_pairs  warp per doc, lane = query token: column maxima (gather_max), then the (doc slot, q, code) pairs
+//                    inside the margin appended to the query's pair list (warp-aggregated atomics)
+//   k_recheck_dots   thread per pair: the pinned-order dot, atomicMax of its score key into exactmax[b][slot][q]
+//   k_recheck_sum    warp per doc: the q-ordered fp32 sum of the maxima -> approx[b][i] and the cut key (what k_approx
+//                    emits); clears the doc's exactmax row for the next call
+// More docs than rc_cap or more pairs than pair_cap raise *fallback (the sub-batch is redone on the exact path).
 // ------------------------------------------------------------------------------------------
-#define PB_RECHECK_LIST 96
-#define PB_RECHECK_TILE 16384
-PB_DEV void recheck_flush(const float *__restrict__ Qs, int qld, const float *__restrict__ C, int dim, const uint32_t *pc,
-                          const uint32_t *pq, int cnt, uint32_t *qm, int lane) {
-    for (int j = lane; j < cnt; j += 32) {
-        const float *q = Qs + (size_t)pq[j] * qld, *c = C + (size_t)pc[j] * dim;
+__global__ void __launch_bounds__(256)
+k_recheck_pairs(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
+                const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off,
+                const uint32_t *__restrict__ cand, long long cand_cap, const int *__restrict__ n_cand, int code_margin,
+                int rc_cap, int pair_cap, u64 *__restrict__ pairs, int *__restrict__ n_pairs, int *__restrict__ fallback,
+                unsigned long long *__restrict__ tok_counter) {
+    const int b = blockIdx.y;
+    const int nq = q_off[b + 1] - q_off[b];
+    const int n = n_cand[b];
+    if (n > rc_cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(fallback, 1);
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    const unsigned short *STb = ST16 + (size_t)b * K * QS;
+    const unsigned rowb = (unsigned)QS * 2u;
+    u64 *plist = pairs + (size_t)b * pair_cap;
+    unsigned long long my_tokens = 0;
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps_per_grid) {
+        const uint32_t d = cand[(size_t)b * cand_cap + i];
+        const long long t0 = udoc_off[d], t1 = udoc_off[d + 1];
+        my_tokens += (unsigned long long)(t1 - t0);
+        for (int qc = 0; qc < nq; qc += 32) {
+            const int q = qc + lane;
+            const bool live = q < nq;
+            const char *col = reinterpret_cast<const char *>(STb + (live ? q : 0));
+            const uint32_t m = gather_max<GatherU16>(col, rowb, ucodes, t0, t1);
+            const uint32_t lo = m > (uint32_t)code_margin ? m - (uint32_t)code_margin : 0u;
+            uint32_t prev = 0xffffffffu;  // lists are padded to 8 with the last code: a repeat is not a new pair
+            for (long long t = t0; t < t1; t += 8) {
+                const uint4 ca = *reinterpret_cast<const uint4 *>(ucodes + t);
+                const uint4 cb = *reinterpret_cast<const uint4 *>(ucodes + t + 4);
+                const uint32_t cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+                uint32_t v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const unsigned short *>(col + (size_t)cs[e] * rowb);
+                unsigned mine = 0;  // this lane's hits of the block, one bit per code
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const bool rep = cs[e] == (e == 0 ? prev : cs[e - 1]);
+                    if (live && !rep && v[e] >= lo) mine |= 1u << e;
+                }
+                prev = cs[7];
+                if (!__any_sync(PB_FULL, mine != 0u)) continue;  // the common case
+                const int cnt = __popc(mine);
+                int incl = cnt;  // inclusive prefix of the hit counts over the lanes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(PB_FULL, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                const int total = __shfl_sync(PB_FULL, incl, 31);
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&n_pairs[b], total);
+                base = __shfl_sync(PB_FULL, base, 0);
+                int pos = base + incl - cnt;
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (mine & (1u << e)) {
+                        if (pos < pair_cap) plist[pos] = ((u64)i << 40) | ((u64)q << 32) | cs[e];
+                        else atomicOr(fallback, 1);
+                        ++pos;
+                    }
+            }
+        }
+    }
+    if (lane == 0 && my_tokens) atomicAdd(tok_counter, my_tokens);
+}
+
+__global__ void __launch_bounds__(128)
+k_recheck_dots(const u64 *__restrict__ pairs, const int *__restrict__ n_pairs, int pair_cap, const float *__restrict__ Q,
+               const int *__restrict__ q_off, const float *__restrict__ C, int dim, int rc_cap, int QS,
+               uint32_t *__restrict__ exactmax) {
+    const int b = blockIdx.y;
+    const int n = min(n_pairs[b], pair_cap);
+    const float *Qb = Q + (size_t)q_off[b] * dim;
+    const u64 *plist = pairs + (size_t)b * pair_cap;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const u64 pr = plist[j];
+        const uint32_t slot = (uint32_t)(pr >> 40), q = (uint32_t)(pr >> 32) & 255u, c = (uint32_t)pr;
+        const float *qr = Qb + (size_t)q * dim, *cr = C + (size_t)c * dim;
         float s = 0.0f;
 #pragma unroll 8
-        for (int d = 0; d < dim; d += 4) {
-            const float4 a = *reinterpret_cast<const float4 *>(q + d), v = __ldg(reinterpret_cast<const float4 *>(c + d));
+        for (int d0 = 0; d0 < dim; d0 += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(qr + d0)), v = __ldg(reinterpret_cast<const float4 *>(cr + d0));
             s = __fmaf_rn(a.x, v.x, s);
             s = __fmaf_rn(a.y, v.y, s);
             s = __fmaf_rn(a.z, v.z, s);
             s = __fmaf_rn(a.w, v.w, s);
         }
-        atomicMax(&qm[pq[j]], score_key_asc(s));
+        atomicMax(&exactmax[((size_t)b * rc_cap + slot) * QS + q], score_key_asc(s));
     }
 }
 
-__global__ void __launch_bounds__(128, 2)
-k_approx_recheck(const unsigned short *__restrict__ ST16, const float *__restrict__ Q, const int *__restrict__ q_off,
-                 const float *__restrict__ C, int dim, long long K, int QS, const uint32_t *__restrict__ ucodes,
-                 const long long *__restrict__ udoc_off, const uint32_t *__restrict__ cand, long long cand_cap,
-                 const int *__restrict__ n_cand, int code_margin, float *__restrict__ approx, u64 *__restrict__ keys,
-                 unsigned long long *__restrict__ tok_counter, uint32_t doc_id_base) {
-    extern __shared__ __align__(16) unsigned char smem_rc[];
-    const int b = blockIdx.y;
-    const int r0 = q_off[b], nq = q_off[b + 1] - r0;
-    const int n = n_cand[b];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int qld = dim + 4;
-    // layout: 4 row tiles | query rows [nq][dim + 4] | per warp: pair codes, pair tokens, per-token maxima [QS]
-    unsigned char *tile = smem_rc + (size_t)w * PB_RECHECK_TILE;
-    float *Qs = reinterpret_cast<float *>(smem_rc + 4 * PB_RECHECK_TILE);
-    uint32_t *wbase = reinterpret_cast<uint32_t *>(Qs + (size_t)nq * qld) + (size_t)w * (2 * (PB_RECHECK_LIST + 32) + QS);
-    uint32_t *pc = wbase, *pq = wbase + (PB_RECHECK_LIST + 32), *qm = pq + (PB_RECHECK_LIST + 32);
-    if (blockIdx.x * 4 >= n) return;
-    for (int idx = threadIdx.x; idx < nq * (dim / 4); idx += blockDim.x) {
-        const int r = idx / (dim / 4), g = idx - r * (dim / 4);
-        *reinterpret_cast<float4 *>(Qs + (size_t)r * qld + 4 * g) = reinterpret_cast<const float4 *>(Q + (size_t)(r0 + r) * dim)[g];
-    }
-    __syncthreads();
-    const char *STb = reinterpret_cast<const char *>(ST16 + (size_t)b * K * QS);
-    const int rowb = QS * 2;                     // bytes per table row (multiple of 16)
-    const int lpr = rowb / 16;                   // lanes per row when a row is copied 16 bytes per lane
-    const int rpi = lpr <= 32 ? 32 / lpr : 1;    // rows per copy instruction
-    const int cap_rows = PB_RECHECK_TILE / rowb; // rows a tile holds
-    const int n_qc = (nq + 31) / 32;             // 32-token column chunks (QS <= 256)
-    unsigned long long my_tokens = 0;
-    for (int i = blockIdx.x * 4 + w; i < n; i += gridDim.x * 4) {
-        const uint32_t d = cand[(size_t)b * cand_cap + i];
-        const long long t0 = udoc_off[d], t1 = udoc_off[d + 1];
-        const int n_codes = (int)(t1 - t0);
-        my_tokens += (unsigned long long)n_codes;
-        const int n_tiles = (n_codes + cap_rows - 1) / cap_rows;
-        for (int q = lane; q < QS; q += 32) qm[q] = 0u;  // exact maxima as score keys (0 = none)
-        uint32_t m[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-        int cnt = 0;
-        for (int pass = 0; pass < 2; ++pass) {
-            for (int tl = 0; tl < n_tiles; ++tl) {
-                const int base = tl * cap_rows, rows = min(cap_rows, n_codes - base);
-                if (pass == 0 || n_tiles > 1) {  // a single-tile doc stays resident for the second pass
-                    __syncwarp();
-                    if (lpr <= 32) {
-                        const int rl = lane / lpr, piece = lane - rl * lpr;
-                        for (int r = rl; r < rows && rl < rpi; r += rpi) {
-                            const uint32_t c = ucodes[t0 + base + r];
-                            *reinterpret_cast<uint4 *>(tile + (size_t)r * rowb + 16 * piece) =
-                                *reinterpret_cast<const uint4 *>(STb + (size_t)c * rowb + 16 * piece);
-                        }
-                    }
-                    __syncwarp();
-                }
-                if (pass == 0) {  // column maxima: lane = query token, one 2*32-byte smem wavefront per row
-#pragma unroll
-                    for (int qc = 0; qc < 8; ++qc) {
-                        const int q = 32 * qc + lane;
-                        if (qc < n_qc && q < QS) {
-                            uint32_t mm = m[qc];
-                            const unsigned short *col = reinterpret_cast<const unsigned short *>(tile) + q;
-                            for (int r = 0; r < rows; ++r) mm = max(mm, (uint32_t)col[(size_t)r * QS]);
-                            m[qc] = mm;
-                        }
-                    }
-                } else {  // pairs within the margin of the maximum
-#pragma unroll
-                    for (int qc = 0; qc < 8; ++qc) {
-                        if (qc >= n_qc) continue;  // warp-uniform
-                        const int q = 32 * qc + lane;
-                        const bool live = q < nq;
-                        const uint32_t lo = m[qc] > (uint32_t)code_margin ? m[qc] - (uint32_t)code_margin : 0u;
-                        const unsigned short *col = reinterpret_cast<const unsigned short *>(tile) + (q < QS ? q : 0);
-                        for (int r = 0; r < rows; ++r) {
-                            const uint32_t c = ucodes[t0 + base + r];  // warp-uniform
-                            // lists are padded to 8 with the last code: a code equal to its predecessor is a repeat
-                            const bool rep = base + r > 0 && c == ucodes[t0 + base + r - 1];
-                            const bool hit = live && !rep && (uint32_t)col[(size_t)r * QS] >= lo;
-                            const unsigned bal = __ballot_sync(PB_FULL, hit);
-                            if (bal == 0u) continue;
-                            if (hit) {
-                                const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
-                                pc[pos] = c;
-                                pq[pos] = (uint32_t)q;
-                            }
-                            cnt += __popc(bal);
-                            if (cnt > PB_RECHECK_LIST) {
-                                __syncwarp();
-                                recheck_flush(Qs, qld, C, dim, pc, pq, cnt, qm, lane);
-                                __syncwarp();
-                                cnt = 0;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (cnt > 0) recheck_flush(Qs, qld, C, dim, pc, pq, cnt, qm, lane);
-        __syncwarp();
-        // score += max for q ascending, skipping rows without a finite maximum (search.rs:318-320)
-        float score = 0.0f;
-        for (int qc = 0; qc < nq; qc += 32) {
-            const uint32_t mk = qc + lane < QS ? qm[qc + lane] : 0u;
+__global__ void __launch_bounds__(256)
+k_recheck_sum(uint32_t *__restrict__ exactmax, const int *__restrict__ q_off, int QS, const uint32_t *__restrict__ cand,
+              long long cand_cap, const int *__restrict__ n_cand, int rc_cap, float *__restrict__ approx,
+              u64 *__restrict__ keys, uint32_t doc_id_base) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int nq = q_off[b + 1] - q_off[b];
+    const int n = min(n_cand[b], rc_cap);
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
+        uint32_t *row = exactmax + ((size_t)b * rc_cap + i) * QS;
+        float score = 0.0f;  // score += max for q ascending, skipping rows without a finite maximum (search.rs:318-320)
+        for (int qc = 0; qc < QS; qc += 32) {
+            const uint32_t mk = qc + lane < QS ? row[qc + lane] : 0u;
+            if (qc + lane < QS) row[qc + lane] = 0u;
             const int lim = min(32, nq - qc);
             for (int qq = 0; qq < lim; ++qq) {
                 const uint32_t kk = __shfl_sync(PB_FULL, mk, qq);
@@ -589,10 +591,9 @@ k_approx_recheck(const unsigned short *__restrict__ ST16, const float *__restric
             }
         }
         if (lane == 0) {
+            const uint32_t d = cand[(size_t)b * cand_cap + i];
             approx[(size_t)b * cand_cap + i] = score;
             keys[(size_t)b * cand_cap + i] = ((u64)(~score_key_asc(score)) << 32) | (d + doc_id_base);
         }
-        __syncwarp();
     }
-    if (lane == 0 && my_tokens) atomicAdd(tok_counter, my_tokens);
 }
