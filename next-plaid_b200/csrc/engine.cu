@@ -241,7 +241,7 @@ struct Workspace {
     cudaEvent_t call_ev[2] = {};                // around a whole search call
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2,  cellbits,
-        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc, mslot, slicecnt, rcmax, rcpairs, rcn;
+        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc, mslot, slicecnt, rcmax, rcpairs, rcn, cellflags;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -341,6 +341,13 @@ struct pb_index {
         case 256: { constexpr int DIM = 256; __VA_ARGS__; } break;                                 \
         default: return pb_fail(PB_ERR_UNSUPPORTED, "embedding_dim %d not built (32/64/96/128/256)", dim); \
     }
+
+// QS: query tokens per score-table row.  Up to 32 tokens: rounded up to 8 (rows of at most 64 bytes); beyond: to a
+// multiple of 64, so that a row is whole 128-byte lines (a 96-byte row straddles lines and costs the first approximate
+// pass 2.5x instead of 1.5-2x: profiles/r02_summary.md)
+static int query_row_tokens(int nq_max) {
+    return nq_max <= 32 ? std::max(8, (nq_max + 7) & ~7) : ((nq_max + 63) & ~63);
+}
 
 static bool dim_supported(int d) { return d == 32 || d == 64 || d == 96 || d == 128 || d == 256; }
 
@@ -849,15 +856,17 @@ static pb_status run_k1_tc(pb_index *ix, Workspace &ws, const pb_search_params *
             ws.Qi.as<float>(), ws.qoff.as<int>(), QS, ix->centroids.as<float>(), ws.ulist.as<uint32_t>(), ws.nulist.as<int>(),
             cells_cap, ws.k1rows.as<float>());
     });
-    CKS(set_smem(k_cells_thr, (size_t)cells_cap * 4));
-    k_cells_thr<<<B, 256, (size_t)cells_cap * 4, ws.stream>>>(
+    CKS(ws.cellflags.ensure((size_t)B * cells_cap * 4));
+    k_cells_thr<<<dim3(8, B), 256, 0, ws.stream>>>(
         ws.sel.as<u64>(), ws.k1rows.as<float>(), ws.ulist.as<uint32_t>(), ws.nulist.as<int>(), ws.qoff.as<int>(), ix->K, QS, n,
         cells_cap, p->has_centroid_score_threshold, p->centroid_score_threshold, batched ? 1 : 0,
-        batched ? (long long)p->centroid_batch_size : ix->K, ws.cells.as<uint32_t>(), ws.ncells.as<int>(),
-        ws.ST16.as<unsigned short>(), ws.qrange.as<float2>(), cm, ws.Q.as<float>(), ix->centroids.as<float>(), ix->dim,
-        ws.cmax16.as<unsigned short>(), n_chunks, chunk_rows);
+        batched ? (long long)p->centroid_batch_size : ix->K, ws.cellflags.as<int>(), ws.ST16.as<unsigned short>(),
+        ws.qrange.as<float2>(), cm, ws.Q.as<float>(), ix->centroids.as<float>(), ix->dim, ws.cmax16.as<unsigned short>(),
+        n_chunks, chunk_rows);
+    k_cells_emit<<<B, 256, 0, ws.stream>>>(ws.ulist.as<uint32_t>(), ws.nulist.as<int>(), ws.cellflags.as<int>(), cells_cap,
+                                           ws.cells.as<uint32_t>(), ws.ncells.as<int>());
     CK(cudaGetLastError());
-    L[PB_STAGE_PROBE] += 7;
+    L[PB_STAGE_PROBE] += 8;
     *cells_cap_out = cells_cap;
     *d_fallback_out = d_fallback;
     return PB_OK;
@@ -1171,7 +1180,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
     // ---- sub-batching: bound the transposed score matrix ----
     int nq_max_all = 0;
     for (int64_t b = 0; b < Bt; ++b) nq_max_all = std::max<int>(nq_max_all, (int)(io.q_off[b + 1] - io.q_off[b]));
-    const int QS_all = std::max(8, (nq_max_all + 7) & ~7);
+    const int QS_all = query_row_tokens(nq_max_all);
     if (!all_eligible && !big_probe && (long long)QS_all * n_probe > 8192)
         return pb_fail(PB_ERR_UNSUPPORTED, "query tokens x n_ivf_probe = %lld exceeds 8192", (long long)QS_all * n_probe);
     size_t per_q = (size_t)ix->K * QS_all * sizeof(float);
@@ -1194,7 +1203,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         std::vector<int> qoff(B + 1);
         for (int b = 0; b <= B; ++b) qoff[b] = (int)(io.q_off[b0 + b] - r0);
         for (int b = 0; b < B; ++b) nq_max = std::max(nq_max, qoff[b + 1] - qoff[b]);
-        const int QS = std::max(8, (nq_max + 7) & ~7);
+        const int QS = query_row_tokens(nq_max);
         int *L = g_stats.launches;
         const bool fast = ix->fast_approx && !io.trace;  // trace wants every candidate's exact approx score
         // the score table comes from the tensor cores unless something needs the dense fp32 S (an eligibility filter,

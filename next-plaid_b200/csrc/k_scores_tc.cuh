@@ -366,22 +366,20 @@ k_cells_unique(const u64 *__restrict__ sel, const int *__restrict__ q_off, int Q
 // rows[b][u][QS] = S[.][ulist[b][u]].  The batched variant's slab-prefix scan ("did c enter token q's slab heap?")
 // ranks the earlier centroids of the slab on the 16-bit estimate table: with kv16 = the code of the exact value v,
 // an estimate code >= kv16 + code_margin is certainly not below v, one <= kv16 - code_margin certainly below,
-// anything between is settled by a pinned-order dot.  grid = B, 256 threads.
+// anything between is settled by a pinned-order dot.  grid = (slices, B), 256 threads: a warp per selected centroid, the
+// keep flags go to global memory and k_cells_emit compacts them in order.
 __global__ void __launch_bounds__(256)
 k_cells_thr(const u64 *__restrict__ sel, const float *__restrict__ rows, const uint32_t *__restrict__ ulist,
             const int *__restrict__ n_u, const int *__restrict__ q_off, long long K, int QS, int n, int cap, int has_thr,
-            float thr, int batched, long long slab, uint32_t *__restrict__ cells, int *__restrict__ n_cells,
+            float thr, int batched, long long slab, int *__restrict__ flags,
             const unsigned short *__restrict__ ST16, const float2 *__restrict__ qrange, int code_margin,
             const float *__restrict__ Q, const float *__restrict__ C, int dim, const unsigned short *__restrict__ cmax16,
             int n_chunks, int chunk_rows) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    int *flags = reinterpret_cast<int *>(smem_raw);  // [cap]
-    __shared__ int scan_tmp[33];
-    const int b = blockIdx.x;
+    const int b = blockIdx.y;
     const int nq = q_off[b + 1] - q_off[b];
     const int nu = n_u[b];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int u = w; u < nu; u += nwarps) {
+    for (int u = blockIdx.x * nwarps + w; u < nu; u += gridDim.x * nwarps) {
         const uint32_t c = ulist[(size_t)b * cap + u];
         int keep = 1;
         if (has_thr) {
@@ -431,11 +429,16 @@ k_cells_thr(const u64 *__restrict__ sel, const float *__restrict__ rows, const u
                                 const long long ch = ch0 + (__ffs(todo) - 1);
                                 todo &= todo - 1;
                                 const long long r_lo = max(s0, ch * chunk_rows), r_hi = min((long long)c, (ch + 1) * chunk_rows);
-                                for (long long c2 = r_lo + lane; c2 < r_hi; c2 += 32) {
-                                    const int cd2 = (int)col16[(size_t)c2 * QS];
-                                    if (cd2 >= kv16 + code_margin) ++cnt;
-                                    else if (cd2 + code_margin > kv16)
-                                        cnt += (score_key_asc(pinned_dot(qrow, C + (size_t)c2 * dim, dim)) >= kv) ? 1 : 0;
+                                for (long long c2 = r_lo + lane; c2 < r_hi; c2 += 128) {  // four strided loads in flight
+                                    int cd[4];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) cd[e] = c2 + 32 * e < r_hi ? (int)col16[(size_t)(c2 + 32 * e) * QS] : -1000000;
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        if (cd[e] >= kv16 + code_margin) ++cnt;
+                                        else if (cd[e] + code_margin > kv16)
+                                            cnt += (score_key_asc(pinned_dot(qrow, C + (size_t)(c2 + 32 * e) * dim, dim)) >= kv) ? 1 : 0;
+                                    }
                                 }
                             }
                         }
@@ -446,13 +449,21 @@ k_cells_thr(const u64 *__restrict__ sel, const float *__restrict__ rows, const u
                 }
             }
         }
-        if (lane == 0) flags[u] = keep;
+        if (lane == 0) flags[(size_t)b * cap + u] = keep;
     }
-    __syncthreads();
+}
+
+// ordered compaction of the kept cells.  grid = B, 256 threads.
+__global__ void __launch_bounds__(256)
+k_cells_emit(const uint32_t *__restrict__ ulist, const int *__restrict__ n_u, const int *__restrict__ flags, int cap,
+             uint32_t *__restrict__ cells, int *__restrict__ n_cells) {
+    __shared__ int scan_tmp[33];
+    const int b = blockIdx.x;
+    const int nu = n_u[b];
     int outn = 0;
     for (int base = 0; base < nu; base += blockDim.x) {
         const int i = base + threadIdx.x;
-        const int f = (i < nu) ? flags[i] : 0;
+        const int f = (i < nu) ? flags[(size_t)b * cap + i] : 0;
         int tot;
         const int pos = block_exclusive_scan(f, scan_tmp, &tot);
         if (f && outn + pos < cap) cells[(size_t)b * cap + outn + pos] = ulist[(size_t)b * cap + i];
@@ -476,6 +487,23 @@ k_cells_thr(const u64 *__restrict__ sel, const float *__restrict__ rows, const u
 //                    emits); clears the doc's exactmax row for the next call
 // More docs than rc_cap or more pairs than pair_cap raise *fallback (the sub-batch is redone on the exact path).
 // ------------------------------------------------------------------------------------------
+// One pass over the doc's codes: every lane (= query token) tracks its three largest estimate codes with their
+// centroids; at the end the entries within the margin of the largest are the pairs.  Only when the third is still inside
+// the margin could a fourth have been dropped: that (rare) lane re-walks the list and emits every code in the margin.
+PB_DEV void top3_insert(uint32_t v, uint32_t c, uint32_t (&tv)[3], uint32_t (&tc)[3]) {
+    if (v <= tv[2] || c == tc[0] || c == tc[1] || c == tc[2]) return;  // ties keep the earlier code; repeats are not new
+    if (v > tv[0]) {
+        tv[2] = tv[1]; tc[2] = tc[1];
+        tv[1] = tv[0]; tc[1] = tc[0];
+        tv[0] = v; tc[0] = c;
+    } else if (v > tv[1]) {
+        tv[2] = tv[1]; tc[2] = tc[1];
+        tv[1] = v; tc[1] = c;
+    } else {
+        tv[2] = v; tc[2] = c;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_recheck_pairs(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
                 const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off,
@@ -503,43 +531,65 @@ k_recheck_pairs(const unsigned short *__restrict__ ST16, const int *__restrict__
             const int q = qc + lane;
             const bool live = q < nq;
             const char *col = reinterpret_cast<const char *>(STb + (live ? q : 0));
-            const uint32_t m = gather_max<GatherU16>(col, rowb, ucodes, t0, t1);
-            const uint32_t lo = m > (uint32_t)code_margin ? m - (uint32_t)code_margin : 0u;
-            uint32_t prev = 0xffffffffu;  // lists are padded to 8 with the last code: a repeat is not a new pair
-            for (long long t = t0; t < t1; t += 8) {
-                const uint4 ca = *reinterpret_cast<const uint4 *>(ucodes + t);
-                const uint4 cb = *reinterpret_cast<const uint4 *>(ucodes + t + 4);
-                const uint32_t cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-                uint32_t v[8];
+            // values are stored + 1 so that 0 means "empty slot" (a code can be 0)
+            uint32_t tv[3] = {0u, 0u, 0u}, tc[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+            for (long long t = t0; t < t1; t += 16) {  // lists are padded to 8: 16 row loads in flight, the tail has 8
+                const bool two = t + 16 <= t1;
+                const uint4 ca = *reinterpret_cast<const uint4 *>(ucodes + t), cb = *reinterpret_cast<const uint4 *>(ucodes + t + 4);
+                const uint4 cc = two ? *reinterpret_cast<const uint4 *>(ucodes + t + 8) : cb;
+                const uint4 cd = two ? *reinterpret_cast<const uint4 *>(ucodes + t + 12) : cb;
+                const uint32_t cs[16] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w, cc.x, cc.y, cc.z, cc.w, cd.x, cd.y, cd.z, cd.w};
+                uint32_t v[16];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const unsigned short *>(col + (size_t)cs[e] * rowb);
-                unsigned mine = 0;  // this lane's hits of the block, one bit per code
+                for (int e = 0; e < 16; ++e) v[e] = *reinterpret_cast<const unsigned short *>(col + (size_t)cs[e] * rowb);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const bool rep = cs[e] == (e == 0 ? prev : cs[e - 1]);
-                    if (live && !rep && v[e] >= lo) mine |= 1u << e;
-                }
-                prev = cs[7];
-                if (!__any_sync(PB_FULL, mine != 0u)) continue;  // the common case
-                const int cnt = __popc(mine);
-                int incl = cnt;  // inclusive prefix of the hit counts over the lanes
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int y = __shfl_up_sync(PB_FULL, incl, o);
-                    if (lane >= o) incl += y;
-                }
-                const int total = __shfl_sync(PB_FULL, incl, 31);
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&n_pairs[b], total);
-                base = __shfl_sync(PB_FULL, base, 0);
-                int pos = base + incl - cnt;
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    if (mine & (1u << e)) {
-                        if (pos < pair_cap) plist[pos] = ((u64)i << 40) | ((u64)q << 32) | cs[e];
-                        else atomicOr(fallback, 1);
-                        ++pos;
+                for (int e = 0; e < 16; ++e)
+                    if (live) top3_insert(v[e] + 1u, cs[e], tv, tc);
+            }
+            const uint32_t lo = tv[0] > (uint32_t)code_margin ? tv[0] - (uint32_t)code_margin : 1u;
+            int cnt = 0;
+            if (live && tv[0]) cnt = 1 + (tv[1] >= lo ? 1 : 0) + (tv[2] >= lo ? 1 : 0);
+            const bool deep = live && tv[2] != 0u && tv[2] >= lo;  // a fourth code may sit in the margin as well
+            if (__any_sync(PB_FULL, deep)) {
+                // rare: this warp re-walks the list; the `deep` lanes count / emit every distinct code in their margin
+                if (deep) {
+                    cnt = 0;
+                    uint32_t prev = 0xffffffffu;
+                    for (long long t = t0; t < t1; ++t) {
+                        const uint32_t c = ucodes[t];
+                        if (c != prev && (uint32_t)*reinterpret_cast<const unsigned short *>(col + (size_t)c * rowb) + 1u >= lo) ++cnt;
+                        prev = c;
                     }
+                }
+            }
+            int incl = cnt;  // inclusive prefix of the pair counts over the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(PB_FULL, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const int total = __shfl_sync(PB_FULL, incl, 31);
+            if (total == 0) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&n_pairs[b], total);
+            base = __shfl_sync(PB_FULL, base, 0);
+            int pos = base + incl - cnt;
+            if (pos + cnt > pair_cap) {
+                if (cnt) atomicOr(fallback, 1);
+                continue;
+            }
+            const u64 head = ((u64)i << 40) | ((u64)q << 32);
+            if (deep) {
+                uint32_t prev = 0xffffffffu;
+                for (long long t = t0; t < t1; ++t) {
+                    const uint32_t c = ucodes[t];
+                    if (c != prev && (uint32_t)*reinterpret_cast<const unsigned short *>(col + (size_t)c * rowb) + 1u >= lo) plist[pos++] = head | c;
+                    prev = c;
+                }
+            } else if (cnt) {
+                plist[pos] = head | tc[0];
+                if (tv[1] >= lo) plist[++pos] = head | tc[1];
+                if (tv[2] >= lo) plist[++pos] = head | tc[2];
             }
         }
     }
