@@ -667,6 +667,10 @@ def run_reference(args):
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: native libraries that print to fd 1 (NCCL's version banner) go to stderr
+    _out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _out
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

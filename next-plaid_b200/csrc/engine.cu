@@ -241,7 +241,7 @@ struct Workspace {
     cudaEvent_t call_ev[2] = {};                // around a whole search call
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2,  cellbits,
-        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc, mslot, slicecnt, rcmax, rcpairs, rcn, cellflags;
+        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc, mslot, slicecnt, rcmax, rcpairs, rcn, cellflags, estkey, srcrank, xpairs, xnpairs, needexact;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -303,6 +303,9 @@ struct pb_index {
     DevBuf centroids_f16;      // [K][dim] fp16 copy for the filter (k_exact_tc, the variant without a score table)
     DevBuf tok_inv_norm;       // [N] 1 / |c + w| for the linear filter (k_exact_tc2)
     bool filter_v1 = false;    // PB_FILTER_V1=1: always the decompressing filter k_exact_tc (A/B measurement)
+    bool filter_ws = true;     // the linear filter as the warp-specialised pipeline k_maxsim_tc (PB_FILTER_WS=0: k_exact_tc2)
+    bool pair_exact = true;    // exact stage on the (token, query token) pairs that can hold a maximum (PB_PAIR_EXACT=0: k_exact)
+    int ws_grid = 8;           // k_maxsim_tc CTAs per SM across the batch (PB_WS_GRID)
     bool profiling = false;
     size_t st_budget = (size_t)8 << 30;  // workspace budget of one search call (PB_WS_BUDGET_MB)
     ncclComm_t comm = nullptr;  // doc-sharded deployment: one rank per GPU
@@ -581,6 +584,9 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_FAST_APPROX")) ix->fast_approx = atoi(e) != 0;
         if (const char *e = getenv("PB_FAST_EXACT")) ix->fast_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_FILTER_V1")) ix->filter_v1 = atoi(e) != 0;
+        if (const char *e = getenv("PB_FILTER_WS")) ix->filter_ws = atoi(e) != 0;
+        if (const char *e = getenv("PB_PAIR_EXACT")) ix->pair_exact = atoi(e) != 0;
+        if (const char *e = getenv("PB_WS_GRID")) ix->ws_grid = std::max(1, atoi(e));
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC_DIAG")) ix->k1_diag = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC")) ix->k1_tc = atoi(e) != 0;
@@ -937,7 +943,7 @@ struct KeptView {  // the docs the exact stage scores: the cut's output, or the 
 };
 
 static pb_status launch_exact(pb_index *ix, Workspace &ws, const KeptView &kv, int B, int QS, int Mcap, int kept_shared,
-                              long long max_tokens, int *launches) {
+                              long long max_tokens, int *launches, const int *only_flagged = nullptr, bool timed = true) {
     // each CTA owns a contiguous range of chunks; aim for 8 waves of 2 CTAs/SM over the whole grid
     long long chunks = (max_tokens + PB_TOK_TILE - 1) / PB_TOK_TILE;
     long long want = std::max<long long>(1, ((long long)ix->sm_count * 16 + B - 1) / B);
@@ -945,12 +951,12 @@ static pb_status launch_exact(pb_index *ix, Workspace &ws, const KeptView &kv, i
     PB_DIM_SWITCH(ix->dim, {
         auto kern = k_exact<DIM, false>;
         CKS(set_smem(kern, smem_exact(DIM, ix->packed)));
-        KEV_BEGIN(PB_KERNEL_EXACT);
+        if (timed) KEV_BEGIN(PB_KERNEL_EXACT);
         kern<<<dim3(gx, B), 128, smem_exact(DIM, ix->packed), ws.stream>>>(
             ws.Q.as<float>(), ws.qoff.as<int>(), QS, ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits,
             ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(), ix->doc_off.as<long long>(), nullptr,
-            kv.kept, kv.nkept, kv.tokp, Mcap, kept_shared, ws.maxkey.as<uint32_t>());
-        KEV_END(PB_KERNEL_EXACT);
+            kv.kept, kv.nkept, kv.tokp, Mcap, kept_shared, ws.maxkey.as<uint32_t>(), only_flagged);
+        if (timed) KEV_END(PB_KERNEL_EXACT);
     });
     CK(cudaGetLastError());
     if (launches) ++*launches;
@@ -984,14 +990,78 @@ static float filter_eps_unit2(const pb_index *ix, int E) {
     return eps < 0.05f ? eps : 0.0f;
 }
 
+static size_t smem_maxsim_tc(int dim, int packed, int nqt) {
+    const int nbits = packed * 8 / dim;
+    return (size_t)2 * (dim / 8) * PB_XTC_LBO + (size_t)nqt * dim * 2 + (size_t)256 * (8 / nbits) * 2 + 4 * 128 * sizeof(MsMeta) +
+           12 * 8 + 16;
+}
+
+// the warp-specialised linear estimate over the docs of `in`: pass 1 (pairs == nullptr) leaves per (doc, q) maxima in
+// `keys`; pass 2 lists the (token, q) pairs within the certified band of the maxima `keys` holds at src_rank
+static pb_status launch_maxsim_tc(pb_index *ix, Workspace &ws, const KeptView &in, int B, int QS, int Mcap, long long max_tokens,
+                                  int nq_max, uint32_t *keys, const uint32_t *src_rank, float band_unit, u64 *pairs,
+                                  int *n_pairs, int pair_cap, int kev) {
+    long long chunks = (max_tokens + 127) / 128;
+    long long want = std::max<long long>(1, ((long long)ix->sm_count * ix->ws_grid + B - 1) / B);
+    int gx = (int)std::max<long long>(1, std::min<long long>(chunks, want));
+    const int nqt = nq_max <= 32 ? 32 : 64;
+    const size_t sm = smem_maxsim_tc(ix->dim, ix->packed, nqt);
+    const bool emit = pairs != nullptr;
+#define PB_MS_GO(DV, NB, NQ, EM)                                                                                       \
+    {                                                                                                                  \
+        auto kern = k_maxsim_tc<DV, NB, NQ, EM>;                                                                       \
+        CKS(set_smem(kern, sm));                                                                                       \
+        if (kev >= 0) KEV_BEGIN(kev);                                                                                  \
+        kern<<<dim3(gx, B), 288, sm, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS, ws.ST16.as<unsigned short>(), \
+                                                  ix->K, ws.qrange.as<float2>(), ws.qflag.as<int>(), ix->w_rev.as<float>(), \
+                                                  ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(),               \
+                                                  ix->tok_inv_norm.as<float>(), ix->doc_off.as<long long>(), in.kept,  \
+                                                  in.nkept, in.tokp, Mcap, keys, src_rank, ws.qnmax.as<float>(),       \
+                                                  band_unit, pairs, n_pairs, pair_cap);                                \
+        if (kev >= 0) KEV_END(kev);                                                                                    \
+    }
+#define PB_MS_LAUNCH(DV, NB)                                                                                           \
+    if (emit) {                                                                                                        \
+        if (nqt == 32) PB_MS_GO(DV, NB, 32, true) else PB_MS_GO(DV, NB, 64, true)                                      \
+    } else {                                                                                                           \
+        if (nqt == 32) PB_MS_GO(DV, NB, 32, false) else PB_MS_GO(DV, NB, 64, false)                                    \
+    }
+#define PB_MS_NBITS(DV)                                                                                                \
+    switch (ix->nbits) {                                                                                               \
+        case 1: PB_MS_LAUNCH(DV, 1) break;                                                                             \
+        case 2: PB_MS_LAUNCH(DV, 2) break;                                                                             \
+        case 4: PB_MS_LAUNCH(DV, 4) break;                                                                             \
+        default: PB_MS_LAUNCH(DV, 8) break;                                                                            \
+    }
+    switch (ix->dim) {
+        case 64: PB_MS_NBITS(64) break;
+        case 96: PB_MS_NBITS(96) break;
+        case 128: PB_MS_NBITS(128) break;
+        default: return pb_fail(PB_ERR_UNSUPPORTED, "filter: unsupported dim");
+    }
+#undef PB_MS_NBITS
+#undef PB_MS_LAUNCH
+#undef PB_MS_GO
+    CK(cudaGetLastError());
+    return PB_OK;
+}
+
 // a7': tensor-core estimate of every kept doc, then the survivors that can still reach the top_k
 static pb_status launch_filter(pb_index *ix, Workspace &ws, const KeptView &in, const KeptView &out, int B, int QS, int Mcap,
-                               int top_k, long long max_tokens, float eps_unit, int nq_max, bool linear, int *launches) {
+                               int top_k, long long max_tokens, float eps_unit, int nq_max, bool linear, bool keep_keys,
+                               int *launches) {
     long long chunks = (max_tokens + 127) / 128;
     long long want = std::max<long long>(1, ((long long)ix->sm_count * ix->xtc_grid + B - 1) / B);
     int gx = (int)std::max<long long>(1, std::min<long long>(chunks, want));
     const int nqt = nq_max <= 32 ? 32 : 64;
     const size_t sm = smem_exact_tc(ix->dim, ix->packed, nqt);
+    // keep_keys: the per (doc, q) maxima go to their own buffer and stay there for the pair pass of the exact stage
+    uint32_t *keys = keep_keys ? ws.estkey.as<uint32_t>() : ws.maxkey.as<uint32_t>();
+    if (keep_keys) CK(cudaMemsetAsync(keys, 0, (size_t)B * Mcap * QS * 4, ws.stream));
+    if (linear && ix->filter_ws) {
+        CKS(launch_maxsim_tc(ix, ws, in, B, QS, Mcap, max_tokens, nq_max, keys, nullptr, 0.0f, nullptr, nullptr, 0,
+                             PB_KERNEL_FILTER));
+    } else {
 #define PB_TC_LAUNCH(DV, NB)                                                                                           \
     if (linear) {                                                                                                      \
         auto kern = nqt == 32 ? k_exact_tc2<DV, NB, 32> : k_exact_tc2<DV, NB, 64>;                                     \
@@ -1001,7 +1071,7 @@ static pb_status launch_filter(pb_index *ix, Workspace &ws, const KeptView &in, 
                                                   ix->K, ws.qrange.as<float2>(), ws.qflag.as<int>(), ix->w_rev.as<float>(), \
                                                   ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(),               \
                                                   ix->tok_inv_norm.as<float>(), ix->doc_off.as<long long>(), in.kept,  \
-                                                  in.nkept, in.tokp, Mcap, ws.maxkey.as<uint32_t>());                  \
+                                                  in.nkept, in.tokp, Mcap, keys);                                      \
         KEV_END(PB_KERNEL_FILTER);                                                                                     \
     } else {                                                                                                           \
         auto kern = nqt == 32 ? k_exact_tc<DV, NB, 32> : k_exact_tc<DV, NB, 64>;                                       \
@@ -1010,8 +1080,7 @@ static pb_status launch_filter(pb_index *ix, Workspace &ws, const KeptView &in, 
         kern<<<dim3(gx, B), 128, sm, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS,                             \
                                                   ix->centroids_f16.as<__half>(), ix->w_rev.as<float>(),               \
                                                   ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(),               \
-                                                  ix->doc_off.as<long long>(), in.kept, in.nkept, in.tokp, Mcap,       \
-                                                  ws.maxkey.as<uint32_t>());                                           \
+                                                  ix->doc_off.as<long long>(), in.kept, in.nkept, in.tokp, Mcap, keys); \
         KEV_END(PB_KERNEL_FILTER);                                                                                     \
     }
 #define PB_TC_NBITS(DV)                                                                                                \
@@ -1021,17 +1090,18 @@ static pb_status launch_filter(pb_index *ix, Workspace &ws, const KeptView &in, 
         case 4: PB_TC_LAUNCH(DV, 4) break;                                                                             \
         default: PB_TC_LAUNCH(DV, 8) break;                                                                            \
     }
-    switch (ix->dim) {
-        case 64: PB_TC_NBITS(64) break;
-        case 96: PB_TC_NBITS(96) break;
-        case 128: PB_TC_NBITS(128) break;
-        default: return pb_fail(PB_ERR_UNSUPPORTED, "filter: unsupported dim");
-    }
+        switch (ix->dim) {
+            case 64: PB_TC_NBITS(64) break;
+            case 96: PB_TC_NBITS(96) break;
+            case 128: PB_TC_NBITS(128) break;
+            default: return pb_fail(PB_ERR_UNSUPPORTED, "filter: unsupported dim");
+        }
 #undef PB_TC_NBITS
 #undef PB_TC_LAUNCH
-    CK(cudaGetLastError());
-    k_tc_finalize<<<dim3((Mcap + 7) / 8, B), 256, 0, ws.stream>>>(ws.maxkey.as<uint32_t>(), ws.qoff.as<int>(), QS, in.nkept,
-                                                                  Mcap, in.tokp, ws.est.as<float>());
+        CK(cudaGetLastError());
+    }
+    k_tc_finalize<<<dim3((Mcap + 7) / 8, B), 256, 0, ws.stream>>>(keys, ws.qoff.as<int>(), QS, in.nkept, Mcap, in.tokp,
+                                                                  ws.est.as<float>(), keep_keys ? 0 : 1);
     CK(cudaGetLastError());
     int Pm = 1;
     while (Pm < Mcap) Pm <<= 1;
@@ -1039,9 +1109,10 @@ static pb_status launch_filter(pb_index *ix, Workspace &ws, const KeptView &in, 
     k_tc_select<<<B, 1024, (size_t)Pm * 8, ws.stream>>>(ws.est.as<float>(), in.kept, in.krank, in.nkept, Mcap, top_k,
                                                         ws.qoff.as<int>(), ws.qnmax.as<float>(), eps_unit,
                                                         ix->doc_off.as<long long>(), out.kept, out.krank, out.nkept,
-                                                        out.tokp, ws.ktok2.as<long long>());
+                                                        out.tokp, ws.ktok2.as<long long>(),
+                                                        keep_keys ? ws.srcrank.as<uint32_t>() : nullptr);
     CK(cudaGetLastError());
-    if (launches) *launches += 3;
+    if (launches) *launches += 3 + (keep_keys ? 1 : 0);
     return PB_OK;
 }
 
@@ -1405,10 +1476,12 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
                 ws.ST16.as<unsigned short>(), ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(),
                 cand_list, ix->D, cand_n, 2 * ix->k1_margin + 1, rc_cap, pair_cap, ws.rcpairs.as<u64>(), ws.rcn.as<int>(), d_fb,
                 ws.counters.as<unsigned long long>() + B + 1);
-            k_recheck_dots<<<dim3(ix->sm_count * 2, B), 128, 0, ws.stream>>>(ws.rcpairs.as<u64>(), ws.rcn.as<int>(), pair_cap,
-                                                                             ws.Q.as<float>(), ws.qoff.as<int>(),
-                                                                             ix->centroids.as<float>(), ix->dim, rc_cap, QS,
-                                                                             ws.rcmax.as<uint32_t>());
+            const size_t smd = (size_t)(nq_max + 128) * (ix->dim + 1) * 4;
+            CKS(set_smem(k_recheck_dots, smd));
+            k_recheck_dots<<<dim3(ix->sm_count * 2, B), 128, smd, ws.stream>>>(ws.rcpairs.as<u64>(), ws.rcn.as<int>(), pair_cap,
+                                                                               ws.Q.as<float>(), ws.qoff.as<int>(),
+                                                                               ix->centroids.as<float>(), ix->dim, rc_cap, QS,
+                                                                               ws.rcmax.as<uint32_t>());
             k_recheck_sum<<<dim3(ix->sm_count, B), 256, 0, ws.stream>>>(ws.rcmax.as<uint32_t>(), ws.qoff.as<int>(), QS, cand_list,
                                                                         ix->D, cand_n, rc_cap, ws.approx.as<float>(),
                                                                         ws.keys.as<u64>(), (uint32_t)ix->doc_id_base);
@@ -1467,6 +1540,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         const float eps_unit = linear ? filter_eps_unit2(ix, tc ? ix->k1_margin : 0) : filter_eps_unit(ix);
         const bool filt = ix->fast_exact && !io.trace && ix->centroids_f16.p && eps_unit > 0.0f && nq_max <= 64 &&
                           top_k < Mcap && ix->packed % 4 == 0;
+        bool pairs = false;
         if (filt) {
             CKS(ws.est.ensure((size_t)B * Mcap * 4));
             CKS(ws.kept2.ensure((size_t)B * Mcap * 4));
@@ -1482,12 +1556,54 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
                 L[PB_STAGE_EXACT] += 1;
             }
             KeptView kv2{ws.kept2.as<uint32_t>(), ws.nkept2.as<int>(), ws.tokp2.as<long long>(), ws.krank2.as<uint32_t>()};
+            // pair form of the exact stage: pass 2 of the estimate over the survivors lists the (token, q) pairs that can
+            // hold a per-token maximum, k_pair_exact evaluates them in the pinned order; a query whose list overflows
+            // (or that published no estimate) goes through k_exact
+            pairs = linear && ix->filter_ws && ix->pair_exact && Mcap <= 65535 && QS <= 256;
+            if (pairs) {
+                CKS(ws.estkey.ensure((size_t)B * Mcap * QS * 4));
+                CKS(ws.srcrank.ensure((size_t)B * Mcap * 4));
+            }
             CKS(launch_filter(ix, ws, kv, kv2, B, QS, Mcap, top_k, (long long)Mcap * std::max(ix->max_doclen, 1), eps_unit,
-                              nq_max, linear, &L[PB_STAGE_EXACT]));
+                              nq_max, linear, pairs, &L[PB_STAGE_EXACT]));
             kv = kv2;
             if (!sharded) kv.krank = nullptr;  // survivors keep their order, so position breaks ties the same way
         }
-        CKS(launch_exact(ix, ws, kv, B, QS, Mcap, 0, (long long)Mcap * std::max(ix->max_doclen, 1), &L[PB_STAGE_EXACT]));
+        if (pairs) {
+            const int pair_cap = 16 * Mcap + 4096;  // ~ (top_k + ties) * nq * (1 + a few) pairs per query in practice
+            CKS(ws.xpairs.ensure((size_t)B * pair_cap * 8));
+            CKS(ws.xnpairs.ensure((size_t)B * 4 + 16));
+            CKS(ws.needexact.ensure((size_t)B * 4 + 16));
+            CK(cudaMemsetAsync(ws.xnpairs.p, 0, (size_t)B * 4, ws.stream));
+            KEV_BEGIN(PB_KERNEL_EXACT);  // pass 2 + pair evaluation + the (normally empty) k_exact of flagged queries
+            CKS(launch_maxsim_tc(ix, ws, kv, B, QS, Mcap, (long long)Mcap * std::max(ix->max_doclen, 1), nq_max,
+                                 ws.estkey.as<uint32_t>(), ws.srcrank.as<uint32_t>(), eps_unit, ws.xpairs.as<u64>(),
+                                 ws.xnpairs.as<int>(), pair_cap, -1));
+            k_pair_overflow<<<(B + 255) / 256, 256, 0, ws.stream>>>(ws.xnpairs.as<int>(), pair_cap, ws.qflag.as<int>(), B,
+                                                                    ws.needexact.as<int>());
+            CK(cudaGetLastError());
+            const size_t smp = ((size_t)(nq_max + 128) * (ix->dim + 1) + 256) * 4;
+            switch (ix->dim) {
+#define PB_PE(DV)                                                                                                      \
+    case DV: {                                                                                                         \
+        CKS(set_smem(k_pair_exact<DV>, smp));                                                                          \
+        k_pair_exact<DV><<<dim3(ix->sm_count, B), 128, smp, ws.stream>>>(                                              \
+            ws.xpairs.as<u64>(), ws.xnpairs.as<int>(), pair_cap, ws.Q.as<float>(), ws.qoff.as<int>(), QS,              \
+            ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(),                     \
+            ix->residuals.as<uint8_t>(), Mcap, ws.maxkey.as<uint32_t>());                                              \
+    } break;
+                PB_PE(64) PB_PE(96) PB_PE(128)
+#undef PB_PE
+                default: return pb_fail(PB_ERR_UNSUPPORTED, "pair exact: unsupported dim");
+            }
+            CK(cudaGetLastError());
+            L[PB_STAGE_EXACT] += 4;
+            CKS(launch_exact(ix, ws, kv, B, QS, Mcap, 0, (long long)Mcap * std::max(ix->max_doclen, 1), &L[PB_STAGE_EXACT],
+                             ws.needexact.as<int>(), false));
+            KEV_END(PB_KERNEL_EXACT);
+        } else {
+            CKS(launch_exact(ix, ws, kv, B, QS, Mcap, 0, (long long)Mcap * std::max(ix->max_doclen, 1), &L[PB_STAGE_EXACT]));
+        }
         if (sharded) {
             CKS(ws.payload.ensure((size_t)B * Mcap * 8));
             CK(cudaMemsetAsync(ws.fkeys.p, 0xff, (size_t)B * Mcap * 8, ws.stream));  // ~0 = no entry
@@ -1821,7 +1937,7 @@ extern "C" pb_status pb_maxsim_scores(int32_t device, const float *query, int32_
         CKS(set_smem(kern, smem_exact(DV, 0)));                                                                  \
         kern<<<dim3(gx, 1), 128, smem_exact(DV, 0)>>>(dQ.as<float>(), dqoff.as<int>(), QS, nullptr, nullptr, 8, nullptr, \
                                                    nullptr, nullptr, dtok.as<float>(), dkept.as<uint32_t>(),    \
-                                                   dnk.as<int>(), dtp.as<long long>(), Mcap, 0, dmax.as<uint32_t>()); \
+                                                   dnk.as<int>(), dtp.as<long long>(), Mcap, 0, dmax.as<uint32_t>(), nullptr); \
     } break;
         PB_CASE(32) PB_CASE(64) PB_CASE(96) PB_CASE(128) PB_CASE(256)
 #undef PB_CASE

@@ -536,7 +536,7 @@ k_exact_tc2(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
 // estimate[b][r] = sum over q of the per-token maxima (any order); resets maxkey.  one warp per kept doc.
 __global__ void __launch_bounds__(256)
 k_tc_finalize(uint32_t *__restrict__ maxkey, const int *__restrict__ q_off, int QS, const int *__restrict__ n_kept, int Mcap,
-              const long long *__restrict__ tok_prefix, float *__restrict__ est) {
+              const long long *__restrict__ tok_prefix, float *__restrict__ est, int reset) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n_kept[b]) return;
@@ -546,7 +546,7 @@ k_tc_finalize(uint32_t *__restrict__ maxkey, const int *__restrict__ q_off, int 
     bool bad = false;
     for (int q = lane; q < nq; q += 32) {
         const uint32_t k = row[q];
-        row[q] = 0u;
+        if (reset) row[q] = 0u;
         if (k) tot += key_to_score(k);
         else bad = true;  // no finite similarity for this query token: do not trust the estimate
     }
@@ -566,7 +566,7 @@ k_tc_select(const float *__restrict__ est, const uint32_t *__restrict__ kept, co
             const int *__restrict__ n_kept, int Mcap, int top_k, const int *__restrict__ q_off,
             const float *__restrict__ qnmax, float eps_unit, const long long *__restrict__ doc_off,
             uint32_t *__restrict__ kept2, uint32_t *__restrict__ krank2, int *__restrict__ n_kept2,
-            long long *__restrict__ tok_prefix2, long long *__restrict__ kept_tokens2) {
+            long long *__restrict__ tok_prefix2, long long *__restrict__ kept_tokens2, uint32_t *__restrict__ src_rank2) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *sk = reinterpret_cast<u64 *>(smem_raw);
     __shared__ int scan_tmp[33];
@@ -615,6 +615,7 @@ k_tc_select(const float *__restrict__ est, const uint32_t *__restrict__ kept, co
             kept2[(size_t)b * Mcap + outn + pos] = d;
             krank2[(size_t)b * Mcap + outn + pos] = krank ? krank[(size_t)b * Mcap + i] : (uint32_t)i;
             tok_prefix2[(size_t)b * (Mcap + 1) + outn + pos] = run + tpos;
+            if (src_rank2) src_rank2[(size_t)b * Mcap + outn + pos] = (uint32_t)i;
         }
         outn += tot;
         run += ttot;

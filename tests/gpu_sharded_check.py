@@ -40,6 +40,7 @@ def main():
         for q, r in zip(qs, res):
             w = oracle.search_one(ix, q, po, subset=subset)
             if r.passage_ids.tolist() != w.passage_ids.tolist() or not np.array_equal(r.scores, w.scores):
+                print(f"rank {rank}: search mismatch cbs={cbs} subset={subset is not None}", file=sys.stderr)
                 bad += 1
     # data-parallel k-means over NCCL (pb_kmeans_fit_dp): every rank must end with the same unit-norm centroids
     rng = np.random.default_rng(3)
@@ -53,8 +54,14 @@ def main():
     cent = npb.kmeans_fit_dp([pts], 32, niters=6, seed=5, device=local, nccl=(uid2[0], rank, world))
     allc = [None] * world
     dist.all_gather_object(allc, cent.tobytes())
-    if any(c != allc[0] for c in allc) or np.abs(np.linalg.norm(cent, axis=1) - 1.0).max() > 1e-5 or \
-            ((centers @ cent.T).max(1) > 0.98).mean() < 0.75:
+    # (Lloyd from a random start need not find every blob: the single-GPU fit of the same seed is the yardstick)
+    solo = npb.kmeans_fit(pts, 32, niters=6, seed=5, device=local)
+    found = lambda c: ((centers @ c.T).max(1) > 0.98).mean()   # noqa: E731
+    km_bad = any(c != allc[0] for c in allc) or np.abs(np.linalg.norm(cent, axis=1) - 1.0).max() > 1e-5 or \
+        found(cent) < found(solo) - 0.2
+    if km_bad:
+        print(f"rank {rank}: k-means check failed: identical={all(c == allc[0] for c in allc)} found={found(cent):.2f} "
+              f"solo={found(solo):.2f}", file=sys.stderr)
         bad += 1
     t = torch.tensor([bad], device="cuda")
     dist.all_reduce(t)
