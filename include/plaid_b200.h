@@ -268,6 +268,8 @@ typedef struct pb_work_counters {
     int64_t n_k1_tc;             /* sub-batches whose score table came from the tcgen05 kernel (k_scores16_tc) */
     int64_t n_recheck_docs;      /* docs that got the exact fp32 approximate score (a5 second pass) */
     int64_t n_k1_tc_redo;        /* sub-batches the tensor-core pass handed back to the exact path (flagged query, list overflow) */
+    int64_t n_exact_pairs;       /* (token, query token) similarities the pair form of the exact stage evaluated */
+    int64_t n_pair_fallback_queries; /* queries whose pair list overflowed (or that had no estimate): scored by k_exact */
 } pb_work_counters;
 PB_API pb_status pb_last_work_counters(pb_index *ix, pb_work_counters *out);
 

@@ -1301,7 +1301,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
                 CK(cudaMemcpyAsync(ws.Q.p, ws.hq.p, (size_t)R * ix->dim * 4, cudaMemcpyHostToDevice, ws.stream));
             }
         }
-        CKS(ws.hcounts.ensure((size_t)(B + 1) * 4 + 16 + (size_t)(B + 2) * 8 + (size_t)B * 8 + (size_t)B * 5 * 4 + 64));
+        CKS(ws.hcounts.ensure((size_t)(B + 1) * 4 + 16 + (size_t)(B + 2) * 8 + (size_t)B * 8 + (size_t)B * 7 * 4 + 192));
         memcpy(ws.hcounts.p, qoff.data(), (size_t)(B + 1) * 4);
         CK(cudaMemcpyAsync(ws.qoff.p, ws.hcounts.p, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ws.stream));
         if (prof) CK(cudaEventRecord(ws.ev[1], ws.stream));
@@ -1660,7 +1660,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         unsigned long long *hcnt = reinterpret_cast<unsigned long long *>(hbase);
         long long *hsurv_tok = reinterpret_cast<long long *>(hcnt + (B + 2));
         int *hc = reinterpret_cast<int *>(hsurv_tok + B);
-        int *hsurv = hc + 3 * B, *hrecheck = hc + 4 * B, *hfell = hc + 5 * B;
+        int *hsurv = hc + 3 * B, *hrecheck = hc + 4 * B, *hfell = hc + 5 * B, *hpairs = hc + 5 * B + 16, *hneed = hc + 6 * B + 16;
         *hfell = 0;
         CK(cudaMemcpyAsync(hc, ws.ncells.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
         CK(cudaMemcpyAsync(hc + B, ws.ncand.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
@@ -1671,6 +1671,10 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             CK(cudaMemcpyAsync(hsurv, ws.nkept2.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
         }
         if (fast) CK(cudaMemcpyAsync(hrecheck, ws.ncand2.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
+        if (pairs) {
+            CK(cudaMemcpyAsync(hpairs, ws.xnpairs.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
+            CK(cudaMemcpyAsync(hneed, ws.needexact.p, (size_t)B * 4, cudaMemcpyDeviceToHost, ws.stream));
+        }
         if (d_probe_fallback) CK(cudaMemcpyAsync(hfell, d_probe_fallback, 4, cudaMemcpyDeviceToHost, ws.stream));
         if (!io.out_on_device) {
             size_t bytes = (size_t)B * top_k * 12 + (size_t)B * 4;
@@ -1719,6 +1723,11 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         else if (probe_list_only) g_stats.work.n_probe_list += 1;
         if (fast)
             for (int b = 0; b < B; ++b) g_stats.work.n_recheck_docs += hrecheck[b];
+        if (pairs)
+            for (int b = 0; b < B; ++b) {
+                if (hneed[b]) g_stats.work.n_pair_fallback_queries += 1;
+                else g_stats.work.n_exact_pairs += hpairs[b];
+            }
         g_stats.work.n_candidate_tokens += (long long)hcnt[0];
         for (int b = 0; b < B; ++b) {
             g_stats.work.n_cells += hc[b];

@@ -69,7 +69,6 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
     const long long per = (n_chunks + gridDim.x - 1) / gridDim.x;
     const long long c_lo = (long long)blockIdx.x * per, c_hi = min(n_chunks, c_lo + per);
     if (c_lo >= c_hi || nq == 0 || qflag[b]) return;
-    if (EMIT && n_pairs[b] > pair_cap) return;  // (never true on entry; keeps the contract local)
     const int n = (int)(c_hi - c_lo);
     for (int i = threadIdx.x; i < 256 * VB; i += blockDim.x) {
         const int byte = i / VB, j = i - byte * VB;
@@ -105,7 +104,7 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
     if (w >= 4 && w < 8) {
         // ================= producers =================
         const int t = threadIdx.x - 128;
-        auto load_packed = [&](const TokMeta &m, uint32_t (&pw)[NW]) {
+        auto load_packed = [&](const TokMeta &m, uint32_t (&pw)[NW]) __attribute__((always_inline)) {
             if (m.r >= 0) {
                 const uint8_t *src = residuals + (size_t)m.g * PACKED;
                 if (PACKED % 16 == 0) {
@@ -126,7 +125,8 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
                 for (int i = 0; i < NW; ++i) pw[i] = 0u;
             }
         };
-        auto step = [&](int i, const TokMeta &cur, const uint32_t (&pw)[NW], TokMeta &nxt, uint32_t (&pwn)[NW]) {
+        auto step = [&](int i, const TokMeta &cur, const uint32_t (&pw)[NW], TokMeta &nxt, uint32_t (&pwn)[NW])
+                        __attribute__((always_inline)) {
             const int s = i & 1, ms = i & 3;
             MsMeta mm;
             mm.g = cur.g;
@@ -208,6 +208,8 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
             }
             __syncwarp();
         }
+        // both commits of the last chunks must have landed before the CTA's shared memory is released
+        for (int i = max(n - 2, 0); i < n; ++i) mbar_wait(&a_empty[i & 1], (uint32_t)(i >> 1) & 1u);
     } else {
         // ================= epilogue =================
         const int t = threadIdx.x;
@@ -216,7 +218,7 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
         const char *STb = reinterpret_cast<const char *>(ST16 + (size_t)b * K * QS);
         const unsigned rowb = (unsigned)QS * 2u;
         const float band = EMIT ? 2.0f * band_unit * qnmax[b] + 1e-6f : 0.0f;
-        auto load_side = [&](const MsMeta &m, uint32_t (&sw)[SW], float &inv) {
+        auto load_side = [&](const MsMeta &m, uint32_t (&sw)[SW], float &inv) __attribute__((always_inline)) {
             inv = 0.0f;
             if (m.r >= 0) {
                 const uint4 *srow = reinterpret_cast<const uint4 *>(STb + (size_t)m.code * rowb);  // 16-byte aligned (QS % 8 == 0)
@@ -235,7 +237,8 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
                 for (int i = 0; i < SW; ++i) sw[i] = 0u;
             }
         };
-        auto step = [&](int i, const MsMeta &cur, const uint32_t (&sw)[SW], float inv, MsMeta &nxt, uint32_t (&swn)[SW], float &invn) {
+        auto step = [&](int i, const MsMeta &cur, const uint32_t (&sw)[SW], float inv, MsMeta &nxt, uint32_t (&swn)[SW],
+                        float &invn) __attribute__((always_inline)) {
             nxt.r = -1;
             nxt.g = 0;
             nxt.code = 0;
@@ -252,13 +255,19 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
             const unsigned grp = __match_any_sync(PB_FULL, rank);
 #pragma unroll
             for (int h = 0; h < NQT / 32; ++h) {
+                if (32 * h >= nq) {  // (uniform) nothing to read in this half
+                    if (h == NQT / 32 - 1) {
+                        tc_fence_before();
+                        ms_arrive(&t_empty[s]);
+                    }
+                    continue;
+                }
                 uint32_t rr[32];
-                if (32 * h < nq) tc_ld32(tmem_base + ((uint32_t)(32 * w) << 16) + s * NQT + 32 * h, rr);
+                tc_ld32(tmem_base + ((uint32_t)(32 * w) << 16) + s * NQT + 32 * h, rr);
                 if (h == NQT / 32 - 1) {  // the accumulator is in registers: hand it back to the MMA warp
                     tc_fence_before();
                     ms_arrive(&t_empty[s]);
                 }
-                if (32 * h >= nq) continue;
                 if (EMIT) {
                     // thresholds of the warp's doc: lane = query token (a warp that straddles docs reads per token)
                     const bool uni = grp == PB_FULL;

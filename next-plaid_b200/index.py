@@ -67,7 +67,8 @@ class _Work(C.Structure):
                                          "n_candidate_tokens", "n_exact_docs", "n_exact_tokens",
                                          "n_filter_docs", "n_filter_tokens", "k1_tc_max_code_diff",
                                          "k1_rows_mismatch", "n_probe_threshold", "n_probe_list", "n_k1_tc",
-                                         "n_recheck_docs", "n_k1_tc_redo")]
+                                         "n_recheck_docs", "n_k1_tc_redo", "n_exact_pairs",
+                                         "n_pair_fallback_queries")]
 
 
 EXPORTS = [

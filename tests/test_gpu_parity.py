@@ -423,11 +423,14 @@ def test_long_queries_keep_the_fast_paths(oracle, npb, corpus, nq):
             assert np.array_equal(r.scores, w.scores), (kw, nq)
 
 
-@pytest.mark.parametrize("env", [{"PB_FILTER_V1": "1"}, {"PB_FAST_APPROX": "0"}, {"PB_K1_TC": "0"}, {}])
+@pytest.mark.parametrize("env", [{"PB_FILTER_V1": "1"}, {"PB_FAST_APPROX": "0"}, {"PB_K1_TC": "0"}, {"PB_FILTER_WS": "0"},
+                                 {"PB_PAIR_EXACT": "0"}, {}])
 def test_both_filter_kernels_and_their_score_tables(oracle, npb, corpus, monkeypatch, env):
     # the linear filter (k_exact_tc2: centroid score from the 16-bit table + residual part on the tensor cores) on the
     # tensor-core table (default) and on the exact table (PB_K1_TC=0); the decompressing filter (k_exact_tc) when
-    # forced (PB_FILTER_V1=1) or when there is no table (PB_FAST_APPROX=0)
+    # forced (PB_FILTER_V1=1) or when there is no table (PB_FAST_APPROX=0); the linear filter as one CTA-wide loop
+    # (k_exact_tc2, PB_FILTER_WS=0) or as the warp-specialised pipeline (k_maxsim_tc, default), the exact stage on the
+    # (token, q) pairs inside the certified band (default) or on every token of the survivors (PB_PAIR_EXACT=0)
     docs, ix, qs, src, _ = corpus
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -442,12 +445,45 @@ def test_both_filter_kernels_and_their_score_tables(oracle, npb, corpus, monkeyp
             res = gpu.search_batch(batch, pg)
             w = gpu.last_work_counters()
             assert 0 < w["n_exact_docs"] < w["n_filter_docs"], (env, kw, w)
+            pair_form = not env or set(env) == {"PB_K1_TC"}
+            assert (w["n_exact_pairs"] > 0) == pair_form, (env, kw, w)
+            if pair_form:   # a little over one pair per (survivor, query token), never every token
+                assert w["n_pair_fallback_queries"] == 0, (env, kw, w)
+                assert w["n_exact_pairs"] < 0.25 * 48 * w["n_exact_tokens"], (env, kw, w)
             for q, r in zip(batch, res):
                 want = oracle.search_one(ix, q, po)
                 assert r.passage_ids.tolist() == want.passage_ids.tolist(), (env, kw)
                 assert np.array_equal(r.scores, want.scores), (env, kw)
     finally:
         gpu.close()
+
+
+def test_pair_lists_that_overflow_fall_back_to_the_token_kernel(oracle, npb):
+    # docs made of one repeated token: every token of a doc holds every per-token maximum, so the (token, q) list of
+    # the exact stage grows to doclen * nq per survivor and overflows -- those queries are scored by k_exact instead;
+    # a second corpus mixes repeated-token docs with ordinary ones (several pairs per (doc, q), no overflow)
+    rng = np.random.default_rng(5)
+    base = oracle.synthetic_corpus(300, 30, dim=128, seed=23)
+    rep = [np.repeat(d[:1], 200, axis=0) for d in base]
+    mixed = [np.repeat(d[:6], 2, axis=0) if i % 2 else d for i, d in enumerate(base)]
+    for docs, expect_overflow in ((rep, True), (mixed, False)):
+        ix = oracle.create_index(docs, nbits=4, seed=2, num_partitions=64)
+        qs, _ = oracle.synthetic_queries(docs, 6, nq=32, seed=9)
+        gpu = _gpu_index(npb, ix)
+        try:
+            for kw in (dict(top_k=20, n_full_scores=256, centroid_score_threshold=None, n_ivf_probe=16),
+                       dict(top_k=5, n_full_scores=1024, centroid_score_threshold=None, n_ivf_probe=32)):
+                pg, po = _params(npb, oracle, **kw)
+                res = gpu.search_batch(qs, pg)
+                w = gpu.last_work_counters()
+                if w["n_filter_docs"] > 0:
+                    assert (w["n_pair_fallback_queries"] > 0) == expect_overflow, (kw, w)
+                for q, r in zip(qs, res):
+                    want = oracle.search_one(ix, q, po)
+                    assert r.passage_ids.tolist() == want.passage_ids.tolist(), (kw, expect_overflow)
+                    assert np.array_equal(r.scores, want.scores), (kw, expect_overflow)
+        finally:
+            gpu.close()
 
 
 def test_fast_plaid_directory_serves_the_same_results(oracle, npb, corpus, tmp_path):

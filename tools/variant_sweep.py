@@ -17,6 +17,11 @@ VARIANTS = [
     ("filter off", {"PB_FAST_EXACT": "0"}),
     ("list-scan probe (exact a2)", {"PB_PROBE16": "0", "PB_K1_TC": "0"}),
     ("decompressing filter (PB_FILTER_V1)", {"PB_FILTER_V1": "1"}),
+    ("one-loop filter k_exact_tc2 (PB_FILTER_WS=0)", {"PB_FILTER_WS": "0"}),
+    ("token-form exact stage (PB_PAIR_EXACT=0)", {"PB_PAIR_EXACT": "0"}),
+    ("ws grid 4", {"PB_WS_GRID": "4"}),
+    ("ws grid 16", {"PB_WS_GRID": "16"}),
+    ("ws grid 32", {"PB_WS_GRID": "32"}),
     ("nq=48 queries", {"__args__": "--nq 48"}),
 ]
 
@@ -50,6 +55,7 @@ def main():
         par = d.get("self_parity") or {}
         print(f"{name:34s} {d['value']:8.0f} q/s  " + "  ".join(f"{k}={st[k]:.3f}" for k in
               ("centroid_scores", "probe", "approx", "exact")) +
+              "  " + "  ".join(f"k.{k}={v:.3f}" for k, v in d.get("kernel_ms_per_step", {}).items()) +
               f"  parity {par.get('ids_identical')}/{par.get('queries')} dmax={par.get('max_abs_score_diff')}"
               f"  k1_code_diff={d.get('work_per_step', {}).get('k1_tc_max_code_diff')}"
               f"  tc/redo={d.get('work_per_step', {}).get('n_k1_tc')}/{d.get('work_per_step', {}).get('n_k1_tc_redo')}"
