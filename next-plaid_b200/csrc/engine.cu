@@ -241,7 +241,7 @@ struct Workspace {
     cudaEvent_t call_ev[2] = {};                // around a whole search call
     DevBuf Q, qoff, ST, partial, sel, cells, ncells, bitmap, cand, ncand, approx, keys, kept, nkept, tokp, maxkey,
         exact, fkeys, oids, oscores, ocounts, subset, subset_bits, elig, misc, list, counters, lkeys, ST16, qrange, qflag, lsum, cand2, ncand2,  cellbits,
-        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc, mslot, slicecnt, rcmax, rcpairs, rcn, cellflags, estkey, srcrank, xpairs, xnpairs, needexact;
+        gkeys, krank, payload, gfkeys, gpayload, cmax16, tau16, plist, pcount, Qi, Qh16t, Ql16t, ST16b, k1diag, k1rows, ulist, nulist, est, kept2, krank2, nkept2, tokp2, ktok2, qnmax, qexp, qrange_tc, mslot, slicecnt, rcmax, rcpairs, rcn, cellflags, estkey, srcrank, xpairs, xnpairs, needexact, gbase;
     HostBuf hq, hres, hcounts;
     pb_status init() {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -986,7 +986,10 @@ static float filter_eps_unit2(const pb_index *ix, int E) {
     if (!(vmin > 0.0f) || !(ix->cmax < 3.0e4f) || !(wmax < 3.0e4f)) return 0.0f;
     const float ds = ((float)E + 1.01f) * 2.0f * ix->cmax * 1.0001f / 65535.0f;
     const float dw = wmax * (2.0f * u + u * u + 3.0517578e-5f);
-    const float eps = (ds + dw) / vmin + 8e-6f;
+    // k_maxsim_tc decodes a code with one FFMA whose folded constant (|.| <= 257 R, R = |q| cmax) is rounded once:
+    // <= 257 R 2^-24 = 0.503 code units
+    const float dfold = 0.53f * 2.0f * ix->cmax * 1.0001f / 65535.0f;
+    const float eps = (ds + dw + dfold) / vmin + 8e-6f;
     return eps < 0.05f ? eps : 0.0f;
 }
 
@@ -1007,6 +1010,10 @@ static pb_status launch_maxsim_tc(pb_index *ix, Workspace &ws, const KeptView &i
     const int nqt = nq_max <= 32 ? 32 : 64;
     const size_t sm = smem_maxsim_tc(ix->dim, ix->packed, nqt);
     const bool emit = pairs != nullptr;
+    CKS(ws.gbase.ensure((size_t)B * Mcap * 8));
+    k_doc_gbase<<<dim3((Mcap + 255) / 256, B), 256, 0, ws.stream>>>(in.kept, in.nkept, in.tokp, ix->doc_off.as<long long>(), Mcap,
+                                                                    ws.gbase.as<long long>());
+    CK(cudaGetLastError());
 #define PB_MS_GO(DV, NB, NQ, EM)                                                                                       \
     {                                                                                                                  \
         auto kern = k_maxsim_tc<DV, NB, NQ, EM>;                                                                       \
@@ -1015,7 +1022,7 @@ static pb_status launch_maxsim_tc(pb_index *ix, Workspace &ws, const KeptView &i
         kern<<<dim3(gx, B), 288, sm, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS, ws.ST16.as<unsigned short>(), \
                                                   ix->K, ws.qrange.as<float2>(), ws.qflag.as<int>(), ix->w_rev.as<float>(), \
                                                   ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(),               \
-                                                  ix->tok_inv_norm.as<float>(), ix->doc_off.as<long long>(), in.kept,  \
+                                                  ix->tok_inv_norm.as<float>(), ws.gbase.as<long long>(),              \
                                                   in.nkept, in.tokp, Mcap, keys, src_rank, ws.qnmax.as<float>(),       \
                                                   band_unit, pairs, n_pairs, pair_cap);                                \
         if (kev >= 0) KEV_END(kev);                                                                                    \
@@ -1476,12 +1483,10 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
                 ws.ST16.as<unsigned short>(), ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(),
                 cand_list, ix->D, cand_n, 2 * ix->k1_margin + 1, rc_cap, pair_cap, ws.rcpairs.as<u64>(), ws.rcn.as<int>(), d_fb,
                 ws.counters.as<unsigned long long>() + B + 1);
-            const size_t smd = (size_t)(nq_max + 128) * (ix->dim + 1) * 4;
-            CKS(set_smem(k_recheck_dots, smd));
-            k_recheck_dots<<<dim3(ix->sm_count * 2, B), 128, smd, ws.stream>>>(ws.rcpairs.as<u64>(), ws.rcn.as<int>(), pair_cap,
-                                                                               ws.Q.as<float>(), ws.qoff.as<int>(),
-                                                                               ix->centroids.as<float>(), ix->dim, rc_cap, QS,
-                                                                               ws.rcmax.as<uint32_t>());
+            k_recheck_dots<<<dim3(ix->sm_count * 2, B), 128, 0, ws.stream>>>(ws.rcpairs.as<u64>(), ws.rcn.as<int>(), pair_cap,
+                                                                             ws.Q.as<float>(), ws.qoff.as<int>(),
+                                                                             ix->centroids.as<float>(), ix->dim, rc_cap, QS,
+                                                                             ws.rcmax.as<uint32_t>());
             k_recheck_sum<<<dim3(ix->sm_count, B), 256, 0, ws.stream>>>(ws.rcmax.as<uint32_t>(), ws.qoff.as<int>(), QS, cand_list,
                                                                         ix->D, cand_n, rc_cap, ws.approx.as<float>(),
                                                                         ws.keys.as<u64>(), (uint32_t)ix->doc_id_base);
@@ -1582,12 +1587,13 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             k_pair_overflow<<<(B + 255) / 256, 256, 0, ws.stream>>>(ws.xnpairs.as<int>(), pair_cap, ws.qflag.as<int>(), B,
                                                                     ws.needexact.as<int>());
             CK(cudaGetLastError());
-            const size_t smp = ((size_t)(nq_max + 128) * (ix->dim + 1) + 256) * 4;
+            const size_t smp = ((size_t)(nq_max + 256) * (ix->dim + 1) + 256) * 4;
+            const int pe_ctas = std::max(1, std::min(16, (2 * ix->sm_count + B - 1) / B));  // about one wave over the batch
             switch (ix->dim) {
 #define PB_PE(DV)                                                                                                      \
     case DV: {                                                                                                         \
         CKS(set_smem(k_pair_exact<DV>, smp));                                                                          \
-        k_pair_exact<DV><<<dim3(ix->sm_count, B), 128, smp, ws.stream>>>(                                              \
+        k_pair_exact<DV><<<dim3(pe_ctas, B), 256, smp, ws.stream>>>(                                                   \
             ws.xpairs.as<u64>(), ws.xnpairs.as<int>(), pair_cap, ws.Q.as<float>(), ws.qoff.as<int>(), QS,              \
             ix->centroids.as<float>(), ix->w_rev.as<float>(), ix->nbits, ix->codes.as<uint32_t>(),                     \
             ix->residuals.as<uint8_t>(), Mcap, ws.maxkey.as<uint32_t>());                                              \
@@ -1597,7 +1603,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
                 default: return pb_fail(PB_ERR_UNSUPPORTED, "pair exact: unsupported dim");
             }
             CK(cudaGetLastError());
-            L[PB_STAGE_EXACT] += 4;
+            L[PB_STAGE_EXACT] += 5;
             CKS(launch_exact(ix, ws, kv, B, QS, Mcap, 0, (long long)Mcap * std::max(ix->max_doclen, 1), &L[PB_STAGE_EXACT],
                              ws.needexact.as<int>(), false));
             KEV_END(PB_KERNEL_EXACT);

@@ -32,12 +32,48 @@ struct MsMeta {
 
 PB_DEV void ms_arrive(uint64_t *bar) { mbar_arrive(bar); }
 
+// gbase[b][r] = first token of kept doc r minus its offset in the query's kept-token stream: token s of the stream is
+// index token gbase[r] + s (one dependent load after the prefix search instead of kept -> doc_off)
+__global__ void k_doc_gbase(const uint32_t *__restrict__ kept, const int *__restrict__ n_kept, const long long *__restrict__ tok_prefix,
+                            const long long *__restrict__ doc_off, int Mcap, long long *__restrict__ gbase) {
+    const int b = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_kept[b]) gbase[(size_t)b * Mcap + r] = doc_off[kept[(size_t)b * Mcap + r]] - tok_prefix[(size_t)b * (Mcap + 1) + r];
+}
+
+// locate_token without the code: (rank, index token) of stream position s
+PB_DEV TokMeta ms_locate(long long s, long long T, int r_lo, int nk, const long long *__restrict__ tp,
+                         const long long *__restrict__ gb) {
+    TokMeta m;
+    m.r = -1;
+    m.g = 0;
+    m.code = 0;
+    if (s < T) {
+        int lo = r_lo, hi = nk, step = 1;
+        while (lo + step < nk) {
+            if (tp[lo + step] <= s) {
+                lo += step;
+                step <<= 1;
+            } else {
+                hi = lo + step;
+                break;
+            }
+        }
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (tp[mid] <= s) lo = mid; else hi = mid;
+        }
+        m.r = lo;
+        m.g = gb[lo] + s;
+    }
+    return m;
+}
+
 template <int DIM, int NBITS, int NQT, bool EMIT>
 __global__ void __launch_bounds__(288, 2)
 k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, const unsigned short *__restrict__ ST16,
             long long K, const float2 *__restrict__ qrange, const int *__restrict__ qflag, const float *__restrict__ w_rev,
             const uint32_t *__restrict__ codes, const uint8_t *__restrict__ residuals, const float *__restrict__ inv_norm,
-            const long long *__restrict__ doc_off, const uint32_t *__restrict__ kept, const int *__restrict__ n_kept,
+            const long long *__restrict__ gbase, const int *__restrict__ n_kept,
             const long long *__restrict__ tok_prefix, int Mcap, uint32_t *__restrict__ maxkey,
             const uint32_t *__restrict__ src_rank, const float *__restrict__ qnmax, float band_unit,
             u64 *__restrict__ pairs, int *__restrict__ n_pairs, int pair_cap) {
@@ -61,7 +97,7 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
     const int b = blockIdx.y;
     const int nk = n_kept[b];
     const long long *tp = tok_prefix + (size_t)b * (Mcap + 1);
-    const uint32_t *kp = kept + (size_t)b * Mcap;
+    const long long *gb = gbase + (size_t)b * Mcap;
     const long long T = tp[nk];
     const int r0q = q_off[b], nq = q_off[b + 1] - r0q;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,7 +167,7 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
             MsMeta mm;
             mm.g = cur.g;
             mm.r = cur.r;
-            mm.code = cur.code;
+            mm.code = 0u;
             meta[ms * 128 + t] = mm;
             ms_arrive(&m_full[ms]);
             nxt.r = -1;
@@ -139,7 +175,7 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
             nxt.code = 0;
             if (i + 1 < n) {
                 const int r_lo = max(__shfl_sync(PB_FULL, cur.r, 0), 0);
-                nxt = locate_token<false>((c_lo + i + 1) * 128 + t, T, r_lo, nk, tp, kp, doc_off, codes);
+                nxt = ms_locate((c_lo + i + 1) * 128 + t, T, r_lo, nk, tp, gb);
             }
             load_packed(nxt, pwn);
             mbar_wait(&a_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);
@@ -180,7 +216,7 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             ms_arrive(&a_full[s]);
         };
-        TokMeta mA = locate_token<false>(c_lo * 128 + t, T, 0, nk, tp, kp, doc_off, codes), mB;
+        TokMeta mA = ms_locate(c_lo * 128 + t, T, 0, nk, tp, gb), mB;
         uint32_t pA[NW], pB[NW];
         load_packed(mA, pA);
         for (int i = 0; i < n; i += 2) {
@@ -215,13 +251,18 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
         const int t = threadIdx.x;
         const float2 rg = qrange[b];
         const float inv_scale = 1.0f / rg.y, s_bias = (0.5f - rg.x) / rg.y;
+        // code -> score without an int-to-float conversion: PRMT puts the 16-bit code under the exponent of 2^23
+        // (float 2^23 + code, exact) and one FFMA applies scale and bias; 2^23 * inv_scale is exact, the folded
+        // constant is rounded once (<= half an ulp of ~2^8: 1.6e-5, a per-query constant that filter_eps_unit2 carries)
+        const float s_bias23 = s_bias - 8388608.0f * inv_scale;
         const char *STb = reinterpret_cast<const char *>(ST16 + (size_t)b * K * QS);
         const unsigned rowb = (unsigned)QS * 2u;
         const float band = EMIT ? 2.0f * band_unit * qnmax[b] + 1e-6f : 0.0f;
         auto load_side = [&](const MsMeta &m, uint32_t (&sw)[SW], float &inv) __attribute__((always_inline)) {
             inv = 0.0f;
             if (m.r >= 0) {
-                const uint4 *srow = reinterpret_cast<const uint4 *>(STb + (size_t)m.code * rowb);  // 16-byte aligned (QS % 8 == 0)
+                const uint32_t code = __ldg(codes + m.g);
+                const uint4 *srow = reinterpret_cast<const uint4 *>(STb + (size_t)code * rowb);  // 16-byte aligned (QS % 8 == 0)
 #pragma unroll
                 for (int i = 0; i < SW / 4; ++i) {
                     uint4 t4 = make_uint4(0, 0, 0, 0);
@@ -280,8 +321,8 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
                     if (!uni && rank >= 0) trow = maxkey + ((size_t)b * Mcap + src_rank[(size_t)b * Mcap + rank]) * QS + 32 * h;
 #pragma unroll
                     for (int q = 0; q < 32; ++q) {
-                        const uint32_t cd = (sw[16 * h + (q >> 1)] >> (16 * (q & 1))) & 0xffffu;
-                        const float sim = (__uint_as_float(rr[q]) + __fmaf_rn((float)cd, inv_scale, s_bias)) * inv;
+                        const uint32_t f = __byte_perm(sw[16 * h + (q >> 1)], 0x4B000000u, (q & 1) ? 0x7632 : 0x7610);
+                        const float sim = (__uint_as_float(rr[q]) + __fmaf_rn(__uint_as_float(f), inv_scale, s_bias23)) * inv;
                         float thr = __shfl_sync(PB_FULL, thr_l, q);
                         if (!uni && rank >= 0 && 32 * h + q < nq) {
                             const uint32_t k = trow[q];
@@ -295,16 +336,16 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
                     }
                 } else if (grp == PB_FULL) {
                     if (rank >= 0) {  // the warp's 32 tokens belong to one doc: one 32-lane atomic (lane = query token)
-                        int mine = 0;
+                        float mine = 0.0f;
 #pragma unroll
                         for (int q = 0; q < 32; ++q) {
-                            const uint32_t cd = (sw[16 * h + (q >> 1)] >> (16 * (q & 1))) & 0xffffu;
-                            const float sim = (__uint_as_float(rr[q]) + __fmaf_rn((float)cd, inv_scale, s_bias)) * inv;
-                            const int x = __float_as_int(sim);
-                            const int m = __reduce_max_sync(PB_FULL, x ^ ((x >> 31) & 0x7fffffff));
+                            const uint32_t f = __byte_perm(sw[16 * h + (q >> 1)], 0x4B000000u, (q & 1) ? 0x7632 : 0x7610);
+                            const float sim = (__uint_as_float(rr[q]) + __fmaf_rn(__uint_as_float(f), inv_scale, s_bias23)) * inv;
+                            float m;
+                            asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(m) : "f"(sim), "r"(PB_FULL));
                             if (lane == q) mine = m;
                         }
-                        const uint32_t key = score_key_asc(__int_as_float(mine ^ ((mine >> 31) & 0x7fffffff)));
+                        const uint32_t key = score_key_asc(mine);
                         if (32 * h + lane < nq && key) atomicMax(&maxkey[((size_t)b * Mcap + rank) * QS + 32 * h + lane], key);
                     }
                 } else if (rank >= 0) {  // doc boundary inside the warp: reduce per group, the group's first lane publishes
@@ -312,8 +353,8 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
                     uint32_t *mrow = &maxkey[((size_t)b * Mcap + rank) * QS + 32 * h];
 #pragma unroll
                     for (int q = 0; q < 32; ++q) {
-                        const uint32_t cd = (sw[16 * h + (q >> 1)] >> (16 * (q & 1))) & 0xffffu;
-                        const float sim = (__uint_as_float(rr[q]) + __fmaf_rn((float)cd, inv_scale, s_bias)) * inv;
+                        const uint32_t f = __byte_perm(sw[16 * h + (q >> 1)], 0x4B000000u, (q & 1) ? 0x7632 : 0x7610);
+                        const float sim = (__uint_as_float(rr[q]) + __fmaf_rn(__uint_as_float(f), inv_scale, s_bias23)) * inv;
                         const int x = __float_as_int(sim);
                         const int m = __reduce_max_sync(grp, x ^ ((x >> 31) & 0x7fffffff));
                         const uint32_t key = score_key_asc(__int_as_float(m ^ ((m >> 31) & 0x7fffffff)));
@@ -342,14 +383,14 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
 }
 
 // ------------------------------------------------------------------------------------------
-// exact similarity of the listed (token, query token) pairs.  grid = (CTAs, B), 128 threads, dynamic smem =
-// ((nq + 128) * (DIM + 1) + 256) floats.  A warp takes 32 pairs at a time: the 32 tokens are decompressed by the whole
+// exact similarity of the listed (token, query token) pairs.  grid = (a few CTAs, B), 256 threads, dynamic smem =
+// ((nq + 256) * (DIM + 1) + 256) floats (staging the query is the fixed cost of a CTA: few CTAs, each loops).  A warp takes 32 pairs at a time: the 32 tokens are decompressed by the whole
 // warp exactly as decompress_token does (lane = float4 group, pinned sum-of-squares butterfly, IEEE division) into
 // a padded shared-memory tile, then every lane runs its own pair's sequential FMA chain.
 // pair = token index << 24 | query token << 16 | rank among the kept docs.
 // ------------------------------------------------------------------------------------------
 template <int DIM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_pair_exact(const u64 *__restrict__ pairs, const int *__restrict__ n_pairs, int pair_cap, const float *__restrict__ Q,
              const int *__restrict__ q_off, int QS, const float *__restrict__ C, const float *__restrict__ w_rev, int nbits,
              const uint32_t *__restrict__ codes, const uint8_t *__restrict__ residuals, int Mcap,
@@ -359,19 +400,19 @@ k_pair_exact(const u64 *__restrict__ pairs, const int *__restrict__ n_pairs, int
     constexpr int LD = DIM + 1, G = DIM / 4;
     const int b = blockIdx.y;
     const int n = n_pairs[b];
-    if (n > pair_cap || (long long)blockIdx.x * 128 >= n) return;  // overflow: k_exact scores this query
+    if (n > pair_cap || (long long)blockIdx.x * 256 >= n) return;  // overflow: k_exact scores this query
     const int nq = q_off[b + 1] - q_off[b];
     const int packed = DIM * nbits / 8;
     float *Qs = smem_pe;                                             // [nq][LD]
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *rows = smem_pe + (size_t)nq * LD + (size_t)w * 32 * LD;   // [32][LD] of this warp
-    float *wr = smem_pe + (size_t)(nq + 128) * LD;                   // [256]
+    float *wr = smem_pe + (size_t)(nq + 256) * LD;                   // [256]
     for (int i = threadIdx.x; i < (1 << nbits); i += blockDim.x) wr[i] = w_rev[i];
     const float *Qb = Q + (size_t)q_off[b] * DIM;
     for (int idx = threadIdx.x; idx < nq * DIM; idx += blockDim.x) Qs[(idx / DIM) * LD + idx % DIM] = Qb[idx];
     __syncthreads();
     const u64 *plist = pairs + (size_t)b * pair_cap;
-    for (int j0 = (blockIdx.x * 4 + w) * 32; j0 < n; j0 += gridDim.x * 128) {
+    for (int j0 = (blockIdx.x * 8 + w) * 32; j0 < n; j0 += gridDim.x * 256) {
         const int j = j0 + lane;
         const u64 pr = j < n ? plist[j] : 0ull;
         const long long g = (long long)(pr >> 24);

@@ -170,20 +170,22 @@ k_scores16_tc(const __half *__restrict__ Ch, const __half *__restrict__ Cl, long
                 tc_ld32(tmem_base + ((uint32_t)(32 * lg) << 16) + acc * 128 + cb * 32, rr);
 #pragma unroll
                 for (int sub = 0; sub < 4; ++sub) {
-                    const long long row0 = (long long)g * 128 + cb * 32 + sub * 8;  // 8 query rows of one query (QS % 8 == 0)
-                    const int b = (int)(row0 / QS), q = (int)(row0 - (long long)b * QS);
+                    const int row0 = g * 128 + cb * 32 + sub * 8;  // 8 query rows of one query (QS % 8 == 0)
+                    const int b = row0 / QS, q = row0 - b * QS;
                     if (b >= B || c >= K) continue;
-                    const int nq = q_off[b + 1] - q_off[b];
                     const float2 rg = qrange_tc[b];  // (R*scale, scale / 2^(kq+kc))
                     uint32_t cd[8];
-                    bool real_bad = false;
+                    bool ok = true;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float t = floorf(__fmaf_rn(__uint_as_float(rr[sub * 8 + i]), rg.y, rg.x));
-                        real_bad |= (q + i < nq) && !(t >= 0.0f && t <= 65535.0f);
-                        cd[i] = (uint32_t)fminf(fmaxf(t, 0.0f), 65535.0f);
+                        // code = floor(x) clamped to [0, 65535]; x outside [+0, 65536) (NaN, -0 included) raises the
+                        // query's flag and the sub-batch is redone on the exact path, so only in-range codes matter.
+                        // Padding rows hold a zero accumulator: x = R*scale, in range.
+                        const float x = __fmaf_rn(__uint_as_float(rr[sub * 8 + i]), rg.y, rg.x);
+                        ok &= __float_as_uint(x) < 0x47800000u;
+                        cd[i] = min(__float2uint_rd(x), 65535u);
                     }
-                    if (real_bad) atomicOr(&qflag[b], 1);
+                    if (!ok) atomicOr(&qflag[b], 1);
                     *reinterpret_cast<uint4 *>(ST16 + ((size_t)b * K + c) * QS + q) =
                         make_uint4(cd[0] | (cd[1] << 16), cd[2] | (cd[3] << 16), cd[4] | (cd[5] << 16), cd[6] | (cd[7] << 16));
                 }
@@ -596,65 +598,33 @@ k_recheck_pairs(const unsigned short *__restrict__ ST16, const int *__restrict__
     if (lane == 0 && my_tokens) atomicAdd(tok_counter, my_tokens);
 }
 
-// grid = (CTAs, B), 128 threads, dynamic smem = (nq + 128) * (dim + 1) floats.  A warp takes 32 pairs at a time: the 32
-// centroid rows are loaded cooperatively (one coalesced 16-byte-per-lane load per row -- a thread reading its own row
-// touches 32 rows per instruction and uses half of every sector) into a padded shared-memory tile, then every lane
-// runs its own pair's FMA chain out of shared memory (row pitch dim + 1 floats: conflict-free).
+// thread per pair.  (A warp-cooperative form -- rows staged coalesced into a padded shared-memory tile, then a chain per
+// lane -- was measured: 0.37 ms against 0.25 ms; staging the query per CTA costs more than the half-used sectors.)
 __global__ void __launch_bounds__(128)
 k_recheck_dots(const u64 *__restrict__ pairs, const int *__restrict__ n_pairs, int pair_cap, const float *__restrict__ Q,
                const int *__restrict__ q_off, const float *__restrict__ C, int dim, int rc_cap, int QS,
                uint32_t *__restrict__ exactmax) {
-    extern __shared__ __align__(16) float smem_rd[];
     const int b = blockIdx.y;
     const int n = min(n_pairs[b], pair_cap);
-    const int nq = q_off[b + 1] - q_off[b];
-    const int ld = dim + 1;
-    float *Qs = smem_rd;                                             // [nq][ld]
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *rows = smem_rd + (size_t)nq * ld + (size_t)w * 32 * ld;   // [32][ld] of this warp
-    if ((long long)blockIdx.x * 128 >= n) return;
     const float *Qb = Q + (size_t)q_off[b] * dim;
-    for (int idx = threadIdx.x; idx < nq * dim; idx += blockDim.x) Qs[(idx / dim) * ld + idx % dim] = Qb[idx];
-    __syncthreads();
     const u64 *plist = pairs + (size_t)b * pair_cap;
-    const int g4 = dim / 4;  // float4 groups per row (<= 32 for dim <= 128; 64 for dim 256: two rounds)
-    for (int j0 = (blockIdx.x * 4 + w) * 32; j0 < n; j0 += gridDim.x * 128) {
-        const int j = j0 + lane;
-        const u64 pr = j < n ? plist[j] : 0ull;
-        const uint32_t c = (uint32_t)pr;
-        __syncwarp();
-        for (int r0 = 0; r0 < 32; r0 += 8) {  // 8 rows in flight
-            float4 v[8][2];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const uint32_t cr = __shfl_sync(PB_FULL, c, r0 + e);
-                const float4 *src = reinterpret_cast<const float4 *>(C + (size_t)cr * dim);
-                v[e][0] = lane < g4 ? __ldg(src + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-                v[e][1] = lane + 32 < g4 ? __ldg(src + lane + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float *dst = rows + (size_t)(r0 + e) * ld;
-                if (lane < g4) {
-                    dst[4 * lane] = v[e][0].x; dst[4 * lane + 1] = v[e][0].y; dst[4 * lane + 2] = v[e][0].z; dst[4 * lane + 3] = v[e][0].w;
-                }
-                if (lane + 32 < g4) {
-                    dst[4 * (lane + 32)] = v[e][1].x; dst[4 * (lane + 32) + 1] = v[e][1].y;
-                    dst[4 * (lane + 32) + 2] = v[e][1].z; dst[4 * (lane + 32) + 3] = v[e][1].w;
-                }
-            }
-        }
-        __syncwarp();
-        if (j < n) {
-            const uint32_t slot = (uint32_t)(pr >> 40), q = (uint32_t)(pr >> 32) & 255u;
-            const float *qr = Qs + (size_t)q * ld, *cr = rows + (size_t)lane * ld;
-            float s = 0.0f;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const u64 pr = plist[j];
+        const uint32_t slot = (uint32_t)(pr >> 40), q = (uint32_t)(pr >> 32) & 255u, c = (uint32_t)pr;
+        const float *qr = Qb + (size_t)q * dim, *cr = C + (size_t)c * dim;
+        float s = 0.0f;
 #pragma unroll 8
-            for (int d0 = 0; d0 < dim; ++d0) s = __fmaf_rn(qr[d0], cr[d0], s);
-            atomicMax(&exactmax[((size_t)b * rc_cap + slot) * QS + q], score_key_asc(s));
+        for (int d0 = 0; d0 < dim; d0 += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(qr + d0)), v = __ldg(reinterpret_cast<const float4 *>(cr + d0));
+            s = __fmaf_rn(a.x, v.x, s);
+            s = __fmaf_rn(a.y, v.y, s);
+            s = __fmaf_rn(a.z, v.z, s);
+            s = __fmaf_rn(a.w, v.w, s);
         }
+        atomicMax(&exactmax[((size_t)b * rc_cap + slot) * QS + q], score_key_asc(s));
     }
 }
+
 
 __global__ void __launch_bounds__(256)
 k_recheck_sum(uint32_t *__restrict__ exactmax, const int *__restrict__ q_off, int QS, const uint32_t *__restrict__ cand,
