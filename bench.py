@@ -79,6 +79,7 @@ def parse_args():
     ap.add_argument("--parity-queries", type=int, default=-1, help="oracle-checked queries; -1 = 64 at N=1, 16 at N>1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle (parity + cpu_baseline)")
     ap.add_argument("--threads", type=int, default=2, help="host threads for the extra concurrent-callers measurement")
+    ap.add_argument("--lanes", type=int, default=0, help="pb_set_lanes (0 = the library's default, 2)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--docs-per-topic", type=int, default=1024)
     ap.add_argument("--pool", type=int, default=256, help="centroids per topic pool")
@@ -391,6 +392,8 @@ def run_b200(args):
     d_ids = torch.empty((args.batch, args.top_k), dtype=torch.int64, device=dev)
     d_sc = torch.empty((args.batch, args.top_k), dtype=torch.float32, device=dev)
     d_cn = torch.empty((args.batch,), dtype=torch.int32, device=dev)
+    if args.lanes > 0:
+        gpu.set_lanes(args.lanes)
     gpu.set_profiling(True)
     sampler = ClockSampler(local if on_gpu else -1)       # spans warm-up + both timed regions (nvidia-smi needs ~0.2 s to start)
     for i in range(args.warmup):
@@ -399,23 +402,37 @@ def run_b200(args):
     sync()
     if world > 1:
         dist.barrier()
-    stage_ms, kern_ms, work = {}, {}, {}
-    launches, dev_ms = 0, 0.0
-    tw = time.perf_counter()
-    for i in range(args.steps):
-        gpu.search_batch_device(d_q[(args.warmup + i) % n_batches].data_ptr(), offs, params, d_ids.data_ptr(),
-                                d_sc.data_ptr(), d_cn.data_ptr())
-        dev_ms += gpu.last_call_ms()
-        ms, ln = gpu.last_stage_stats()
-        for k, v in ms.items():
-            stage_ms[k] = stage_ms.get(k, 0.0) + v
-        for k, v in gpu.last_kernel_ms().items():
-            kern_ms[k] = kern_ms.get(k, 0.0) + v
-        launches += sum(ln.values())
-        for k, v in gpu.last_work_counters().items():
-            work[k] = work.get(k, 0) + v
-    sync()
-    wall_ms = 1e3 * (time.perf_counter() - tw)
+    def timed_region():
+        stage_ms, kern_ms, work = {}, {}, {}
+        launches, dev_ms = 0, 0.0
+        tw = time.perf_counter()
+        for i in range(args.steps):
+            gpu.search_batch_device(d_q[(args.warmup + i) % n_batches].data_ptr(), offs, params, d_ids.data_ptr(),
+                                    d_sc.data_ptr(), d_cn.data_ptr())
+            dev_ms += gpu.last_call_ms()
+            ms, ln = gpu.last_stage_stats()
+            for k, v in ms.items():
+                stage_ms[k] = stage_ms.get(k, 0.0) + v
+            for k, v in gpu.last_kernel_ms().items():
+                kern_ms[k] = kern_ms.get(k, 0.0) + v
+            launches += sum(ln.values())
+            for k, v in gpu.last_work_counters().items():
+                work[k] = work.get(k, 0) + v
+        sync()
+        return stage_ms, kern_ms, work, launches, dev_ms, 1e3 * (time.perf_counter() - tw)
+
+    stage_ms, kern_ms, work, launches, dev_ms, wall_ms = timed_region()
+    # the same steps with the batch searched as one slice (pb_set_lanes(1)): kernels run alone, so these are the
+    # per-kernel times that are not stretched by a co-running slice
+    one_lane = None
+    if world == 1 and args.lanes != 1 and args.batch >= 16:
+        gpu.set_lanes(1)
+        gpu.search_batch_device(d_q[0].data_ptr(), offs, params, d_ids.data_ptr(), d_sc.data_ptr(), d_cn.data_ptr())
+        st1, km1, _, ln1, dm1, _ = timed_region()
+        gpu.set_lanes(args.lanes if args.lanes > 0 else 2)
+        one_lane = {"value": args.batch * args.steps / (dm1 * 1e-3), "unit": "queries/s", "ms_per_step": dm1 / args.steps,
+                    "gpu_launches": ln1, "stage_ms_per_step": {k: v / args.steps for k, v in st1.items()},
+                    "kernel_ms_per_step": {k: v / args.steps for k, v in km1.items()}}
     if world > 1:
         dist.barrier()
     gpu.set_profiling(False)
@@ -609,6 +626,10 @@ def run_b200(args):
         "e2e": {"value": args.batch * args.steps / e2e_s, "unit": "queries/s",
                 "h2d_bytes_per_step": int(flat[0].nbytes + offs.nbytes),
                 "d2h_bytes_per_step": int(h_ids.nbytes + h_sc.nbytes + h_cn.nbytes), "ms_per_step": 1e3 * e2e_s / args.steps},
+        "lanes": {"count": (args.lanes if args.lanes > 0 else 2) if world == 1 and args.batch >= 16 else 1,
+                  "what": "slices of a batch searched concurrently inside one call, each on its own stream "
+                          "(pb_set_lanes); stage / kernel times of the timed region are sums over the slices",
+                  "one_lane": one_lane},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_all": per_kernel, "maxsim": maxsim,
         "cpu_baseline": cpu, "parity": parity, "self_parity": self_parity, "concurrent": concurrent,
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},

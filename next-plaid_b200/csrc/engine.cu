@@ -12,6 +12,8 @@
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -276,6 +278,52 @@ struct Stats {
     pb_work_counters work = {};
 };
 static thread_local Stats g_stats;
+static thread_local int g_budget_div = 1;  // lanes of the current call share the workspace budget
+
+// One helper thread of a laned search call (search_impl): runs the pipeline of a slice of the batch on its own workspace
+// and stream while the caller runs another slice, so that one slice's latency-bound kernels overlap the other's
+// bandwidth-bound ones.
+struct LaneWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, done = false, quit = false;
+    LaneWorker() {
+        th = std::thread([this] {
+            std::unique_lock<std::mutex> lk(m);
+            for (;;) {
+                cv.wait(lk, [this] { return has_job || quit; });
+                if (quit) return;
+                lk.unlock();
+                job();
+                lk.lock();
+                has_job = false;
+                done = true;
+                cv.notify_all();
+            }
+        });
+    }
+    void submit(std::function<void()> f) {
+        std::lock_guard<std::mutex> lk(m);
+        job = std::move(f);
+        has_job = true;
+        done = false;
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [this] { return done; });
+    }
+    ~LaneWorker() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            quit = true;
+            cv.notify_all();
+        }
+        if (th.joinable()) th.join();
+    }
+};
 
 struct pb_index {
     int device = 0;
@@ -306,6 +354,9 @@ struct pb_index {
     bool filter_ws = true;     // the linear filter as the warp-specialised pipeline k_maxsim_tc (PB_FILTER_WS=0: k_exact_tc2)
     bool pair_exact = true;    // exact stage on the (token, query token) pairs that can hold a maximum (PB_PAIR_EXACT=0: k_exact)
     int ws_grid = 8;           // k_maxsim_tc CTAs per SM across the batch (PB_WS_GRID)
+    int lanes = 2;             // slices of a batch searched concurrently, each on its own stream (PB_LANES; 1 = off)
+    std::mutex lane_mu;        // one laned call at a time per handle (a second concurrent caller runs un-laned)
+    std::vector<std::unique_ptr<LaneWorker>> lane_workers;
     bool profiling = false;
     size_t st_budget = (size_t)8 << 30;  // workspace budget of one search call (PB_WS_BUDGET_MB)
     ncclComm_t comm = nullptr;  // doc-sharded deployment: one rank per GPU
@@ -587,6 +638,7 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_FILTER_WS")) ix->filter_ws = atoi(e) != 0;
         if (const char *e = getenv("PB_PAIR_EXACT")) ix->pair_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_WS_GRID")) ix->ws_grid = std::max(1, atoi(e));
+        if (const char *e = getenv("PB_LANES")) ix->lanes = std::min(8, std::max(1, atoi(e)));
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC_DIAG")) ix->k1_diag = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC")) ix->k1_tc = atoi(e) != 0;
@@ -677,6 +729,7 @@ extern "C" pb_status pb_index_open(const pb_index_desc *d, pb_index **out) {
 extern "C" void pb_index_close(pb_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
+    ix->lane_workers.clear();  // joins the helper threads
     cudaDeviceSynchronize();
     if (ix->comm) g_nccl.CommDestroy(ix->comm);
     delete ix;
@@ -707,6 +760,9 @@ extern "C" void pb_set_fast_approx(pb_index *ix, int32_t enabled) {
 }
 extern "C" void pb_set_scores_tc(pb_index *ix, int32_t enabled) {
     if (ix) ix->k1_tc = enabled != 0;  // effective when the tensor-core operands were built at open (k1_tc_usable)
+}
+extern "C" void pb_set_lanes(pb_index *ix, int32_t lanes) {
+    if (ix) ix->lanes = std::min(8, std::max(1, (int)lanes));
 }
 extern "C" void pb_set_fast_exact(pb_index *ix, int32_t enabled) {
     if (ix) ix->fast_exact = enabled != 0;
@@ -1267,7 +1323,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
     // sub-batch size: the score tables (16-bit always, fp32 only on the exact path) and the per-(query, doc) scratch
     // (candidate lists, code sums, approximate scores, cut keys, bitmap: 24.2 bytes per document) share one budget
     const size_t per_q_all = (size_t)ix->K * QS_all * (k1_tc_usable(ix) ? 2 : 6) + (size_t)ix->D * 24 + (size_t)ix->D / 8 + 4096;
-    int QB = (int)std::max<size_t>(1, std::min<size_t>((size_t)Bt, ix->st_budget / per_q_all));
+    int QB = (int)std::max<size_t>(1, std::min<size_t>((size_t)Bt, ix->st_budget / std::max(g_budget_div, 1) / per_q_all));
     QB = std::min(QB, 256);
     QB = (int)((Bt + (Bt + QB - 1) / QB - 1) / ((Bt + QB - 1) / QB));  // equal sub-batches
 
@@ -1802,10 +1858,95 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
     return PB_OK;
 }
 
+static void merge_stats(Stats &a, const Stats &b) {
+    for (int i = 0; i < PB_STAGE_COUNT; ++i) {
+        a.ms[i] += b.ms[i];
+        a.launches[i] += b.launches[i];
+    }
+    for (int i = 0; i < PB_KERNEL_COUNT; ++i) a.kernel_ms[i] += b.kernel_ms[i];
+    const int64_t *src = reinterpret_cast<const int64_t *>(&b.work);
+    int64_t *dst = reinterpret_cast<int64_t *>(&a.work);
+    const size_t kdiff = offsetof(pb_work_counters, k1_tc_max_code_diff) / 8;
+    for (size_t i = 0; i < sizeof(pb_work_counters) / 8; ++i) dst[i] = i == kdiff ? std::max(dst[i], src[i]) : dst[i] + src[i];
+}
+
+// events of the calling thread around a laned call (the lanes' own call events live on different streams)
+struct LaneClock {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {};
+    int device = -1;
+};
+static thread_local LaneClock g_lane_clock;
+
 static pb_status search_impl(pb_index *ix, const pb_search_params *p, const SearchIO &io) {
-    const pb_status st = search_impl_inner(ix, p, io);
-    if (st != PB_OK && ix && ix->group) ix->group->fail();  // the peers must not wait for a rank that gave up
-    return st;
+    // Lanes: the queries of a batch are independent, so the batch is cut into `lanes` slices searched concurrently, each
+    // through the whole pipeline on its own workspace and stream (helper threads do the launching).  Not with a trace
+    // (per-stage dumps), not doc-sharded (the exchanges are collective calls in batch order), not for small batches.
+    int lanes = 1;
+    if (ix && p && ix->lanes > 1 && !io.trace && ix->world == 1 && io.n_queries >= 16)
+        lanes = (int)std::min<int64_t>(ix->lanes, io.n_queries / 8);
+    std::unique_lock<std::mutex> lane_lock;
+    if (lanes > 1) {
+        lane_lock = std::unique_lock<std::mutex>(ix->lane_mu, std::try_to_lock);
+        if (!lane_lock.owns_lock()) lanes = 1;  // another host thread is using the helpers: it already provides the overlap
+    }
+    if (lanes <= 1) {
+        const pb_status st = search_impl_inner(ix, p, io);
+        if (st != PB_OK && ix && ix->group) ix->group->fail();  // the peers must not wait for a rank that gave up
+        return st;
+    }
+    while ((int)ix->lane_workers.size() < lanes - 1) ix->lane_workers.emplace_back(new LaneWorker());
+    const bool prof = ix->profiling;
+    LaneClock &clk = g_lane_clock;
+    if (prof) {
+        CK(cudaSetDevice(ix->device));
+        if (clk.device != ix->device) {
+            CK(cudaStreamCreateWithFlags(&clk.stream, cudaStreamNonBlocking));
+            CK(cudaEventCreate(&clk.ev[0]));
+            CK(cudaEventCreate(&clk.ev[1]));
+            clk.device = ix->device;
+        }
+        CK(cudaEventRecord(clk.ev[0], clk.stream));
+    }
+    std::vector<SearchIO> ios(lanes, io);
+    std::vector<pb_status> sts(lanes, PB_OK);
+    std::vector<Stats> stats(lanes);
+    std::vector<std::string> errs(lanes);
+    const int64_t Bt = io.n_queries, top_k = p->top_k;
+    for (int l = 0; l < lanes; ++l) {
+        const int64_t b0 = Bt * l / lanes, b1 = Bt * (l + 1) / lanes;
+        ios[l].q_off = io.q_off + b0;
+        ios[l].n_queries = b1 - b0;
+        if (io.out_ids) ios[l].out_ids = io.out_ids + b0 * top_k;
+        if (io.out_scores) ios[l].out_scores = io.out_scores + b0 * top_k;
+        ios[l].out_counts = io.out_counts ? io.out_counts + b0 : nullptr;
+    }
+    auto run_lane = [&](int l) {
+        g_budget_div = lanes;
+        sts[l] = search_impl_inner(ix, p, ios[l]);
+        g_budget_div = 1;
+        stats[l] = g_stats;
+        if (sts[l] != PB_OK) errs[l] = g_err;
+    };
+    for (int l = 1; l < lanes; ++l) ix->lane_workers[l - 1]->submit([&, l] { run_lane(l); });
+    run_lane(0);
+    for (int l = 1; l < lanes; ++l) ix->lane_workers[l - 1]->wait();
+    Stats total = stats[0];
+    for (int l = 1; l < lanes; ++l) merge_stats(total, stats[l]);
+    total.call_ms = 0.f;
+    for (int l = 0; l < lanes; ++l) total.call_ms = std::max(total.call_ms, stats[l].call_ms);
+    if (prof) {
+        CK(cudaEventRecord(clk.ev[1], clk.stream));
+        CK(cudaEventSynchronize(clk.ev[1]));
+        CK(cudaEventElapsedTime(&total.call_ms, clk.ev[0], clk.ev[1]));
+    }
+    g_stats = total;
+    for (int l = 0; l < lanes; ++l)
+        if (sts[l] != PB_OK) {
+            g_err = errs[l];
+            return sts[l];
+        }
+    return PB_OK;
 }
 
 extern "C" pb_status pb_search_batch_traced(pb_index *ix, const float *queries, const int64_t *q_tok_offsets,

@@ -79,7 +79,7 @@ EXPORTS = [
     "pb_maxsim_scores", "pb_exhaustive_scores", "pb_set_profiling", "pb_last_stage_stats",
     "pb_last_work_counters", "pb_search_batch_device", "pb_last_error", "pb_version",
     "pb_device_count", "pb_comm_unique_id", "pb_index_comm_init", "pb_shard_group_create", "pb_shard_group_destroy",
-    "pb_index_group_join", "pb_index_export_ivf", "pb_last_call_ms", "pb_last_kernel_ms", "pb_set_fast_approx", "pb_set_fast_exact", "pb_set_scores_tc",
+    "pb_index_group_join", "pb_index_export_ivf", "pb_last_call_ms", "pb_last_kernel_ms", "pb_set_fast_approx", "pb_set_fast_exact", "pb_set_scores_tc", "pb_set_lanes",
     "pb_codec_open", "pb_codec_close", "pb_codec_compress_into_codes", "pb_codec_compress_and_residuals",
     "pb_codec_encode_chunk", "pb_kmeans_fit", "pb_codec_train", "pb_kmeans_num_sample_docs",
     "pb_kmeans_num_partitions", "pb_codec_num_sample_docs", "pb_codec_heldout_tokens", "pb_create_index",
@@ -117,6 +117,8 @@ def load_library():
         L.pb_set_fast_exact.restype = None
         L.pb_set_scores_tc.argtypes = [C.c_void_p, C.c_int32]
         L.pb_set_scores_tc.restype = None
+        L.pb_set_lanes.argtypes = [C.c_void_p, C.c_int32]
+        L.pb_set_lanes.restype = None
         L.pb_index_load.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
         L.pb_index_open.argtypes = [C.POINTER(_Desc), C.POINTER(C.c_void_p)]
         L.pb_search_batch_traced.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
@@ -458,6 +460,10 @@ class MmapIndex:
 
     def set_profiling(self, on: bool):
         load_library().pb_set_profiling(self._h, 1 if on else 0)
+
+    def set_lanes(self, lanes: int):
+        """Slices of a batch searched concurrently inside one call (pb_set_lanes); 1 = off."""
+        load_library().pb_set_lanes(self._h, int(lanes))
 
     def last_stage_stats(self):
         ms = np.zeros(len(STAGES), np.float32)

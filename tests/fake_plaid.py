@@ -89,6 +89,9 @@ class MmapIndex:
     def exhaustive_scores(self, queries):
         return np.stack([oracle.exhaustive_scores(self.ix, q) for q in queries])
 
+    def set_lanes(self, lanes):
+        pass
+
     def set_profiling(self, on):
         pass
 

@@ -525,3 +525,38 @@ def test_batched_variant_with_more_than_64_probes(oracle, npb, corpus):
     with pytest.raises(npb.PlaidError) as e:
         gpu.search_batch(qs[:2], npb.SearchParameters(top_k=10, n_ivf_probe=193, centroid_batch_size=128))
     assert e.value.status == 4
+
+
+def test_lanes_cut_a_batch_without_changing_a_bit(oracle, npb, corpus):
+    # pb_set_lanes: slices of a batch run the pipeline concurrently on their own streams; ids, scores and the summed work
+    # counters must not depend on the number of lanes, with host buffers, ragged queries and a subset alike
+    docs, ix, qs, src, gpu = corpus
+    long_q, _ = oracle.synthetic_queries(docs, 4, nq=48, seed=91)
+    batch = (qs + long_q + [qs[0][:5], qs[1] * 3.0]) * 3
+    assert len(batch) >= 40
+    try:
+        for kw, subset in ((dict(top_k=10, n_full_scores=1024), None),
+                           (dict(top_k=25, n_full_scores=512, centroid_batch_size=128), None),
+                           (dict(top_k=10, n_full_scores=256), list(range(0, len(docs), 2)))):
+            pg, po = _params(npb, oracle, **kw)
+            ref = None
+            for lanes in (1, 2, 3, 5):
+                gpu.set_lanes(lanes)
+                res = gpu.search_batch(batch, pg, subset=subset)
+                w = gpu.last_work_counters()
+                got = [(r.passage_ids.tolist(), r.scores.tobytes()) for r in res]
+                key = (w["n_queries"], w["n_query_tokens"], w["n_candidates"], w["n_exact_docs"])
+                if ref is None:
+                    ref = (got, key)
+                    for q, r in zip(batch[:12], res):
+                        want = oracle.search_one(ix, q, po, subset=subset)
+                        assert r.passage_ids.tolist() == want.passage_ids.tolist() and np.array_equal(r.scores, want.scores)
+                assert got == ref[0], (kw, lanes)
+                assert key == ref[1], (kw, lanes, key, ref[1])
+        # an error inside one lane is the call's error
+        gpu.set_lanes(2)
+        bad = _params(npb, oracle, top_k=10, n_full_scores=10 ** 6)[0]
+        with pytest.raises(Exception):
+            gpu.search_batch(batch, bad)
+    finally:
+        gpu.set_lanes(2)
