@@ -32,6 +32,16 @@ struct MsMeta {
 
 PB_DEV void ms_arrive(uint64_t *bar) { mbar_arrive(bar); }
 
+PB_DEV void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // gbase[b][r] = first token of kept doc r minus its offset in the query's kept-token stream: token s of the stream is
 // index token gbase[r] + s (one dependent load after the prefix search instead of kept -> doc_off)
 __global__ void k_doc_gbase(const uint32_t *__restrict__ kept, const int *__restrict__ n_kept, const long long *__restrict__ tok_prefix,
@@ -40,9 +50,10 @@ __global__ void k_doc_gbase(const uint32_t *__restrict__ kept, const int *__rest
     if (r < n_kept[b]) gbase[(size_t)b * Mcap + r] = doc_off[kept[(size_t)b * Mcap + r]] - tok_prefix[(size_t)b * (Mcap + 1) + r];
 }
 
-// locate_token without the code: (rank, index token) of stream position s
+// locate_token through gbase: (rank, index token, code) of stream position s; the code is loaded here but first used
+// one chunk later (when the producer publishes the chunk's metadata), so its latency is off the critical path
 PB_DEV TokMeta ms_locate(long long s, long long T, int r_lo, int nk, const long long *__restrict__ tp,
-                         const long long *__restrict__ gb) {
+                         const long long *__restrict__ gb, const uint32_t *__restrict__ codes) {
     TokMeta m;
     m.r = -1;
     m.g = 0;
@@ -64,6 +75,7 @@ PB_DEV TokMeta ms_locate(long long s, long long T, int r_lo, int nk, const long 
         }
         m.r = lo;
         m.g = gb[lo] + s;
+        m.code = __ldg(codes + m.g);
     }
     return m;
 }
@@ -167,7 +179,7 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
             MsMeta mm;
             mm.g = cur.g;
             mm.r = cur.r;
-            mm.code = 0u;
+            mm.code = cur.code;
             meta[ms * 128 + t] = mm;
             ms_arrive(&m_full[ms]);
             nxt.r = -1;
@@ -175,7 +187,7 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
             nxt.code = 0;
             if (i + 1 < n) {
                 const int r_lo = max(__shfl_sync(PB_FULL, cur.r, 0), 0);
-                nxt = ms_locate((c_lo + i + 1) * 128 + t, T, r_lo, nk, tp, gb);
+                nxt = ms_locate((c_lo + i + 1) * 128 + t, T, r_lo, nk, tp, gb, codes);
             }
             load_packed(nxt, pwn);
             mbar_wait(&a_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);
@@ -216,7 +228,7 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             ms_arrive(&a_full[s]);
         };
-        TokMeta mA = ms_locate(c_lo * 128 + t, T, 0, nk, tp, gb), mB;
+        TokMeta mA = ms_locate(c_lo * 128 + t, T, 0, nk, tp, gb, codes), mB;
         uint32_t pA[NW], pB[NW];
         load_packed(mA, pA);
         for (int i = 0; i < n; i += 2) {
@@ -259,10 +271,9 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
         const unsigned rowb = (unsigned)QS * 2u;
         const float band = EMIT ? 2.0f * band_unit * qnmax[b] + 1e-6f : 0.0f;
         auto load_side = [&](const MsMeta &m, uint32_t (&sw)[SW], float &inv) __attribute__((always_inline)) {
-            inv = 0.0f;
+            inv = 1.0f;  // (a token slot past the stream: its bias is -inf, the product must stay -inf)
             if (m.r >= 0) {
-                const uint32_t code = __ldg(codes + m.g);
-                const uint4 *srow = reinterpret_cast<const uint4 *>(STb + (size_t)code * rowb);  // 16-byte aligned (QS % 8 == 0)
+                const uint4 *srow = reinterpret_cast<const uint4 *>(STb + (size_t)m.code * rowb);  // 16-byte aligned (QS % 8 == 0)
 #pragma unroll
                 for (int i = 0; i < SW / 4; ++i) {
                     uint4 t4 = make_uint4(0, 0, 0, 0);
@@ -303,6 +314,43 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
                     }
                     continue;
                 }
+                if (!EMIT) {
+                    // per-doc maxima, 16 query tokens at a time (16 accumulator registers live): one pass per doc
+                    // present in the warp's 32 tokens (one, unless a doc boundary falls inside them).  Tokens outside
+                    // the doc take bias -inf, so they never win the warp maximum; lane q keeps the maximum of query
+                    // token q and publishes it (one atomic instruction per doc and half).
+                    const unsigned valid = __ballot_sync(PB_FULL, rank >= 0);
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t r16[16];
+                        tc_ld16(tmem_base + ((uint32_t)(32 * w) << 16) + s * NQT + 32 * h + 16 * hh, r16);
+                        if (h == NQT / 32 - 1 && hh == 1) {  // the accumulator is in registers: hand it back to the MMA warp
+                            tc_fence_before();
+                            ms_arrive(&t_empty[s]);
+                        }
+                        unsigned done = 0u;
+                        while (valid & ~done) {
+                            const int leader = __ffs(valid & ~done) - 1;
+                            const int segrank = __shfl_sync(PB_FULL, rank, leader);
+                            const bool inseg = rank == segrank;
+                            const float bias_l = inseg ? s_bias23 : -INFINITY;
+                            float mine = 0.0f;
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                const uint32_t f = __byte_perm(sw[16 * h + 8 * hh + (q >> 1)], 0x4B000000u, (q & 1) ? 0x7632 : 0x7610);
+                                const float sim = (__uint_as_float(r16[q]) + __fmaf_rn(__uint_as_float(f), inv_scale, bias_l)) * inv;
+                                float m;
+                                asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(m) : "f"(sim), "r"(PB_FULL));
+                                if (lane == 16 * hh + q) mine = m;
+                            }
+                            const uint32_t key = score_key_asc(mine);
+                            const int qq = 32 * h + lane;
+                            if ((lane >> 4) == hh && qq < nq && key) atomicMax(&maxkey[((size_t)b * Mcap + segrank) * QS + qq], key);
+                            done |= __ballot_sync(PB_FULL, inseg);
+                        }
+                    }
+                    continue;
+                }
                 uint32_t rr[32];
                 tc_ld32(tmem_base + ((uint32_t)(32 * w) << 16) + s * NQT + 32 * h, rr);
                 if (h == NQT / 32 - 1) {  // the accumulator is in registers: hand it back to the MMA warp
@@ -333,32 +381,6 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
                             if (at < pair_cap)
                                 pairs[(size_t)b * pair_cap + at] = ((u64)cur.g << 24) | ((u64)(32 * h + q) << 16) | (u64)rank;
                         }
-                    }
-                } else if (grp == PB_FULL) {
-                    if (rank >= 0) {  // the warp's 32 tokens belong to one doc: one 32-lane atomic (lane = query token)
-                        float mine = 0.0f;
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            const uint32_t f = __byte_perm(sw[16 * h + (q >> 1)], 0x4B000000u, (q & 1) ? 0x7632 : 0x7610);
-                            const float sim = (__uint_as_float(rr[q]) + __fmaf_rn(__uint_as_float(f), inv_scale, s_bias23)) * inv;
-                            float m;
-                            asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(m) : "f"(sim), "r"(PB_FULL));
-                            if (lane == q) mine = m;
-                        }
-                        const uint32_t key = score_key_asc(mine);
-                        if (32 * h + lane < nq && key) atomicMax(&maxkey[((size_t)b * Mcap + rank) * QS + 32 * h + lane], key);
-                    }
-                } else if (rank >= 0) {  // doc boundary inside the warp: reduce per group, the group's first lane publishes
-                    const int leader = __ffs(grp) - 1;
-                    uint32_t *mrow = &maxkey[((size_t)b * Mcap + rank) * QS + 32 * h];
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const uint32_t f = __byte_perm(sw[16 * h + (q >> 1)], 0x4B000000u, (q & 1) ? 0x7632 : 0x7610);
-                        const float sim = (__uint_as_float(rr[q]) + __fmaf_rn(__uint_as_float(f), inv_scale, s_bias23)) * inv;
-                        const int x = __float_as_int(sim);
-                        const int m = __reduce_max_sync(grp, x ^ ((x >> 31) & 0x7fffffff));
-                        const uint32_t key = score_key_asc(__int_as_float(m ^ ((m >> 31) & 0x7fffffff)));
-                        if (lane == leader && 32 * h + q < nq && key) atomicMax(mrow + q, key);
                     }
                 }
             }
