@@ -349,9 +349,8 @@ struct pb_index {
     float vmin = 0.0f;         // smallest pre-normalisation token norm |c + w| over the index (error bound of the filter)
     float wmax = 0.0f;         // largest residual norm |w| over the index (same)
     DevBuf centroids_f16;      // [K][dim] fp16 copy for the filter (k_exact_tc, the variant without a score table)
-    DevBuf tok_inv_norm;       // [N] 1 / |c + w| for the linear filter (k_exact_tc2)
+    DevBuf tok_inv_norm;       // [N] 1 / |c + w| for the linear estimate (k_maxsim_tc)
     bool filter_v1 = false;    // PB_FILTER_V1=1: always the decompressing filter k_exact_tc (A/B measurement)
-    bool filter_ws = true;     // the linear filter as the warp-specialised pipeline k_maxsim_tc (PB_FILTER_WS=0: k_exact_tc2)
     bool pair_exact = true;    // exact stage on the (token, query token) pairs that can hold a maximum (PB_PAIR_EXACT=0: k_exact)
     int ws_grid = 8;           // k_maxsim_tc CTAs per SM across the batch (PB_WS_GRID)
     int lanes = 2;             // slices of a batch searched concurrently, each on its own stream (PB_LANES; 1 = off)
@@ -635,7 +634,6 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_FAST_APPROX")) ix->fast_approx = atoi(e) != 0;
         if (const char *e = getenv("PB_FAST_EXACT")) ix->fast_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_FILTER_V1")) ix->filter_v1 = atoi(e) != 0;
-        if (const char *e = getenv("PB_FILTER_WS")) ix->filter_ws = atoi(e) != 0;
         if (const char *e = getenv("PB_PAIR_EXACT")) ix->pair_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_WS_GRID")) ix->ws_grid = std::max(1, atoi(e));
         if (const char *e = getenv("PB_LANES")) ix->lanes = std::min(8, std::max(1, atoi(e)));
@@ -654,7 +652,7 @@ pb_status pb_index_finalize(pb_index *ix) {
         CK(cudaGetLastError());
         DevBuf mn;
         CKS(mn.ensure(16));
-        CKS(ix->tok_inv_norm.ensure((size_t)ix->N * 4));  // 1 / |c + w| per token: operand of the linear filter (k_exact_tc2)
+        CKS(ix->tok_inv_norm.ensure((size_t)ix->N * 4));  // 1 / |c + w| per token: operand of the linear estimate (k_maxsim_tc)
         const float init[2] = {3.0e38f, 0.0f};
         CK(cudaMemcpy(mn.p, init, 8, cudaMemcpyHostToDevice));
         switch (ix->dim) {
@@ -1035,7 +1033,7 @@ static float filter_eps_unit(const pb_index *ix) {
     return u + (1.0f + u) * rho / (1.0f - 0.5f * rho) + sub + 4e-5f;
 }
 
-// the same for the linear filter (derivation above k_exact_tc2); E = code error of the score table (0 = exact table)
+// the same for the linear filter (derivation above k_maxsim_tc and in DESIGN.md 4c); E = code error of the score table (0 = exact table)
 static float filter_eps_unit2(const pb_index *ix, int E) {
     const float u = 1.0f / 2048.0f;
     const float vmin = ix->vmin * 0.9999f, wmax = ix->wmax * 1.0001f;
@@ -1121,22 +1119,12 @@ static pb_status launch_filter(pb_index *ix, Workspace &ws, const KeptView &in, 
     // keep_keys: the per (doc, q) maxima go to their own buffer and stay there for the pair pass of the exact stage
     uint32_t *keys = keep_keys ? ws.estkey.as<uint32_t>() : ws.maxkey.as<uint32_t>();
     if (keep_keys) CK(cudaMemsetAsync(keys, 0, (size_t)B * Mcap * QS * 4, ws.stream));
-    if (linear && ix->filter_ws) {
+    if (linear) {
         CKS(launch_maxsim_tc(ix, ws, in, B, QS, Mcap, max_tokens, nq_max, keys, nullptr, 0.0f, nullptr, nullptr, 0,
                              PB_KERNEL_FILTER));
     } else {
 #define PB_TC_LAUNCH(DV, NB)                                                                                           \
-    if (linear) {                                                                                                      \
-        auto kern = nqt == 32 ? k_exact_tc2<DV, NB, 32> : k_exact_tc2<DV, NB, 64>;                                     \
-        CKS(set_smem(kern, sm));                                                                                       \
-        KEV_BEGIN(PB_KERNEL_FILTER);                                                                                   \
-        kern<<<dim3(gx, B), 128, sm, ws.stream>>>(ws.Q.as<float>(), ws.qoff.as<int>(), QS, ws.ST16.as<unsigned short>(), \
-                                                  ix->K, ws.qrange.as<float2>(), ws.qflag.as<int>(), ix->w_rev.as<float>(), \
-                                                  ix->codes.as<uint32_t>(), ix->residuals.as<uint8_t>(),               \
-                                                  ix->tok_inv_norm.as<float>(), ix->doc_off.as<long long>(), in.kept,  \
-                                                  in.nkept, in.tokp, Mcap, keys);                                      \
-        KEV_END(PB_KERNEL_FILTER);                                                                                     \
-    } else {                                                                                                           \
+    {                                                                                                                  \
         auto kern = nqt == 32 ? k_exact_tc<DV, NB, 32> : k_exact_tc<DV, NB, 64>;                                       \
         CKS(set_smem(kern, sm));                                                                                       \
         KEV_BEGIN(PB_KERNEL_FILTER);                                                                                   \
@@ -1620,7 +1608,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             // pair form of the exact stage: pass 2 of the estimate over the survivors lists the (token, q) pairs that can
             // hold a per-token maximum, k_pair_exact evaluates them in the pinned order; a query whose list overflows
             // (or that published no estimate) goes through k_exact
-            pairs = linear && ix->filter_ws && ix->pair_exact && Mcap <= 65535 && QS <= 256;
+            pairs = linear && ix->pair_exact && Mcap <= 65535 && QS <= 256;
             if (pairs) {
                 CKS(ws.estkey.ensure((size_t)B * Mcap * QS * 4));
                 CKS(ws.srcrank.ensure((size_t)B * Mcap * 4));

@@ -61,7 +61,7 @@ k_min_vnorm(const float *__restrict__ C, const float *__restrict__ w_rev, int nb
             pw += __shfl_xor_sync(PB_FULL, pw, m);
         }
         const float nrm = sqrtf(p), wn = sqrtf(pw);
-        if (inv_norm && lane == 0) inv_norm[t] = 1.0f / fmaxf(nrm, 1e-12f);  // operand of k_exact_tc2
+        if (inv_norm && lane == 0) inv_norm[t] = 1.0f / fmaxf(nrm, 1e-12f);  // operand of k_maxsim_tc
         best = fminf(best, nrm == nrm ? nrm : 0.0f);
         wbest = fmaxf(wbest, wn == wn ? wn : 3.0e38f);
     }
@@ -309,230 +309,6 @@ k_exact_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, c
 // + 8e-6 (filter_eps_unit2 in engine.cu).  Flagged queries (no valid table) publish nothing -> no estimate -> every
 // kept doc survives.  Same grid / block / TMEM layout as k_exact_tc.
 // ------------------------------------------------------------------------------------------
-// the global loads of one token of k_exact_tc2: packed residual row (HBM), the score-table row of its centroid (L2), 1/|v|
-template <int PACKED, int SW>
-PB_DEV void tc2_load_token(const TokMeta &m, const uint8_t *__restrict__ residuals, const char *__restrict__ STb, unsigned rowb,
-                           int QS, const float *__restrict__ inv_norm, uint32_t (&pw)[PACKED / 4], uint32_t (&sw)[SW], float &inv) {
-    constexpr int NW = PACKED / 4;
-    constexpr bool PIECES = PACKED % 16 == 0;
-    inv = 0.0f;
-    if (m.r >= 0) {
-        const uint8_t *src = residuals + (size_t)m.g * PACKED;
-        if (PIECES) {
-#pragma unroll
-            for (int pc = 0; pc < PACKED / 16; ++pc) {
-                const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(src) + pc);
-                pw[4 * pc] = t4.x;
-                pw[4 * pc + 1] = t4.y;
-                pw[4 * pc + 2] = t4.z;
-                pw[4 * pc + 3] = t4.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < NW; ++i) pw[i] = __ldg(reinterpret_cast<const uint32_t *>(src) + i);
-        }
-        const uint4 *srow = reinterpret_cast<const uint4 *>(STb + (size_t)m.code * rowb);  // 16-byte aligned (QS % 8 == 0)
-#pragma unroll
-        for (int i = 0; i < SW / 4; ++i) {
-            uint4 t4 = make_uint4(0, 0, 0, 0);
-            if (8 * i < QS) t4 = srow[i];
-            sw[4 * i] = t4.x;
-            sw[4 * i + 1] = t4.y;
-            sw[4 * i + 2] = t4.z;
-            sw[4 * i + 3] = t4.w;
-        }
-        inv = inv_norm[m.g];
-    } else {
-#pragma unroll
-        for (int i = 0; i < NW; ++i) pw[i] = 0u;
-#pragma unroll
-        for (int i = 0; i < SW; ++i) sw[i] = 0u;
-    }
-}
-
-template <int DIM, int NBITS, int NQT>
-__global__ void __launch_bounds__(128, NQT == 32 ? 4 : 3)
-k_exact_tc2(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, const unsigned short *__restrict__ ST16,
-            long long K, const float2 *__restrict__ qrange, const int *__restrict__ qflag, const float *__restrict__ w_rev,
-            const uint32_t *__restrict__ codes, const uint8_t *__restrict__ residuals, const float *__restrict__ inv_norm,
-            const long long *__restrict__ doc_off, const uint32_t *__restrict__ kept, const int *__restrict__ n_kept,
-            const long long *__restrict__ tok_prefix, int Mcap, uint32_t *__restrict__ maxkey) {
-    extern __shared__ __align__(128) unsigned char smem_x[];
-    constexpr int KC = DIM / 8, KSTEPS = DIM / 16;
-    static_assert(NQT == 32 || NQT == 64, "k_exact_tc2: N = 32 or 64");
-    constexpr uint32_t LBO_A = PB_XTC_LBO, A_BYTES = KC * LBO_A, QB_BYTES = NQT * DIM * 2;
-    constexpr uint32_t LBO_B = (NQT / 8) * 128, SBO = 128;
-    constexpr int PACKED = DIM * NBITS / 8, NW = PACKED / 4;
-    static_assert(PACKED % 4 == 0, "k_exact_tc2: packed rows are read in 32-bit words");
-    constexpr int VB = 8 / NBITS;
-    unsigned char *As = smem_x;                        // [128 tokens] fp16 residual tile: element (r, kc) at kc*LBO + 16 r
-    unsigned char *Qb = As + A_BYTES;                  // [NQT query rows] fp16 operand tile
-    __half *Th = reinterpret_cast<__half *>(Qb + QB_BYTES);  // [256][VB]: fp16 bucket weights of the fields of a byte
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(Th + 256 * VB);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 1);
-    const int b = blockIdx.y;
-    const int nk = n_kept[b];
-    const long long *tp = tok_prefix + (size_t)b * (Mcap + 1);
-    const uint32_t *kp = kept + (size_t)b * Mcap;
-    const long long T = tp[nk];
-    const int r0q = q_off[b], nq = q_off[b + 1] - r0q;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long n_chunks = (T + 127) / 128;
-    const long long per = (n_chunks + gridDim.x - 1) / gridDim.x;
-    const long long c_lo = (long long)blockIdx.x * per, c_hi = min(n_chunks, c_lo + per);
-    if (c_lo >= c_hi || nq == 0 || qflag[b]) return;
-    for (int i = threadIdx.x; i < 256 * VB; i += blockDim.x) {
-        const int byte = i / VB, j = i - byte * VB;
-        Th[i] = __float2half_rn(w_rev[(byte >> (8 - NBITS * (j + 1))) & ((1 << NBITS) - 1)]);
-    }
-    for (int idx = threadIdx.x; idx < NQT * KC; idx += blockDim.x) {
-        const int r = idx / KC, kc = idx - r * KC;
-        __half v8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v8[e] = __float2half_rn(r < nq ? Q[(size_t)(r0q + r) * DIM + kc * 8 + e] : 0.0f);
-        *reinterpret_cast<uint4 *>(Qb + (kc * (NQT / 8) + (r >> 3)) * 128 + (r & 7) * 16) = *reinterpret_cast<uint4 *>(v8);
-    }
-    if (threadIdx.x == 0) {
-        mbar_init(mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (w == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(NQT) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(NQT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    // centroid score of a code: the centre of its 16-bit bucket, s~ = (code + 0.5) / scale - R
-    const float2 rg = qrange[b];
-    const float inv_scale = 1.0f / rg.y, s_bias = (0.5f - rg.x) / rg.y;
-    const char *STb = reinterpret_cast<const char *>(ST16 + (size_t)b * K * QS);
-    const unsigned rowb = (unsigned)QS * 2u;
-    constexpr int SW = NQT / 2;  // 32-bit words of a table row this kernel may need
-    uint32_t phase = 0;
-    const int row = threadIdx.x;  // one thread per token (= TMEM lane in the epilogue)
-    TokMeta cur = locate_token<false>(c_lo * 128 + threadIdx.x, T, 0, nk, tp, kp, doc_off, codes);
-    uint32_t pw[NW], sw[SW];
-    float inv;
-    tc2_load_token<PACKED, SW>(cur, residuals, STb, rowb, QS, inv_norm, pw, sw, inv);
-    for (long long chunk = c_lo; chunk < c_hi; ++chunk) {
-        __syncthreads();  // previous chunk: TMEM read out, operand tile free
-        // the next chunk's metadata and global loads go out first: they are in flight under this chunk's tile build,
-        // MMA and epilogue (software pipeline, one chunk deep)
-        TokMeta nxt;
-        nxt.r = -1;
-        nxt.g = 0;
-        nxt.code = 0;
-        if (chunk + 1 < c_hi) {
-            const int r_lo = max(__shfl_sync(PB_FULL, cur.r, 0), 0);
-            nxt = locate_token<false>((chunk + 1) * 128 + threadIdx.x, T, r_lo, nk, tp, kp, doc_off, codes);
-        }
-        uint32_t pwn[NW], swn[SW];
-        float invn;
-        tc2_load_token<PACKED, SW>(nxt, residuals, STb, rowb, QS, inv_norm, pwn, swn, invn);
-        // ---- residual part of the token as fp16, straight into the operand tile: one table read per packed byte ----
-#pragma unroll
-        for (int kc = 0; kc < KC; ++kc) {
-            uint32_t wv[4];
-            if (NBITS == 4) {
-                const uint32_t x = pw[kc];
-                const uint32_t *T32 = reinterpret_cast<const uint32_t *>(Th);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) wv[j] = T32[(x >> (8 * j)) & 255u];
-            } else if (NBITS == 2) {
-                const uint32_t x = pw[kc >> 1] >> (16 * (kc & 1));
-                const uint2 *T64 = reinterpret_cast<const uint2 *>(Th);
-                const uint2 a = T64[x & 255u], c = T64[(x >> 8) & 255u];
-                wv[0] = a.x;
-                wv[1] = a.y;
-                wv[2] = c.x;
-                wv[3] = c.y;
-            } else if (NBITS == 1) {
-                const uint4 a = reinterpret_cast<const uint4 *>(Th)[(pw[kc >> 2] >> (8 * (kc & 3))) & 255u];
-                wv[0] = a.x;
-                wv[1] = a.y;
-                wv[2] = a.z;
-                wv[3] = a.w;
-            } else {
-                const unsigned short *T16 = reinterpret_cast<const unsigned short *>(Th);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t x = pw[2 * kc + (j >> 1)] >> (16 * (j & 1));
-                    wv[j] = (uint32_t)T16[x & 255u] | ((uint32_t)T16[(x >> 8) & 255u] << 16);
-                }
-            }
-            if (cur.r < 0) wv[0] = wv[1] = wv[2] = wv[3] = 0u;
-            *reinterpret_cast<uint4 *>(As + kc * LBO_A + row * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_fence_before();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(As), b0 = smem_u32(Qb);
-#pragma unroll
-            for (int s = 0; s < KSTEPS; ++s)
-                tc_mma_bf16(tmem_base, tc_smem_desc(a0 + s * 2 * LBO_A, LBO_A, SBO), tc_smem_desc(b0 + s * 2 * LBO_B, LBO_B, SBO),
-                            idesc, s > 0 ? 1u : 0u);
-            tc_commit(mbar);
-        }
-        mbar_wait(mbar, phase);
-        phase ^= 1u;
-        tc_fence_after();
-        // ---- epilogue: sim = (q.w + s~(code)) / |v|; per-doc maxima on the order-preserving int image ----
-        const int rank = cur.r;
-        const unsigned grp = __match_any_sync(PB_FULL, rank);
-#pragma unroll
-        for (int h = 0; h < NQT / 32; ++h) {
-            if (32 * h < nq) {
-                uint32_t rr[32];
-                tc_ld32(tmem_base + ((uint32_t)(32 * w) << 16) + 32 * h, rr);
-                if (grp == PB_FULL) {
-                    if (rank >= 0) {  // the warp's 32 tokens belong to one doc: one 32-lane atomic (lane = query token)
-                        int mine = 0;
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            const uint32_t cd = (sw[16 * h + (q >> 1)] >> (16 * (q & 1))) & 0xffffu;
-                            const float sim = (__uint_as_float(rr[q]) + __fmaf_rn((float)cd, inv_scale, s_bias)) * inv;
-                            const int x = __float_as_int(sim);
-                            const int m = __reduce_max_sync(PB_FULL, x ^ ((x >> 31) & 0x7fffffff));
-                            if (lane == q) mine = m;
-                        }
-                        const uint32_t key = score_key_asc(__int_as_float(mine ^ ((mine >> 31) & 0x7fffffff)));
-                        if (32 * h + lane < nq && key) atomicMax(&maxkey[((size_t)b * Mcap + rank) * QS + 32 * h + lane], key);
-                    }
-                } else if (rank >= 0) {  // doc boundary inside the warp: reduce per group, the group's first lane publishes
-                    const int leader = __ffs(grp) - 1;
-                    uint32_t *mrow = &maxkey[((size_t)b * Mcap + rank) * QS + 32 * h];
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const uint32_t cd = (sw[16 * h + (q >> 1)] >> (16 * (q & 1))) & 0xffffu;
-                        const float sim = (__uint_as_float(rr[q]) + __fmaf_rn((float)cd, inv_scale, s_bias)) * inv;
-                        const int x = __float_as_int(sim);
-                        const int m = __reduce_max_sync(grp, x ^ ((x >> 31) & 0x7fffffff));
-                        const uint32_t key = score_key_asc(__int_as_float(m ^ ((m >> 31) & 0x7fffffff)));
-                        if (lane == leader && 32 * h + q < nq && key) atomicMax(mrow + q, key);
-                    }
-                }
-            }
-        }
-        tc_fence_before();
-        cur = nxt;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) pw[i] = pwn[i];
-#pragma unroll
-        for (int i = 0; i < SW; ++i) sw[i] = swn[i];
-        inv = invn;
-    }
-    __syncthreads();
-    if (w == 0) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NQT) : "memory");
-    }
-}
-
 // estimate[b][r] = sum over q of the per-token maxima (any order); resets maxkey.  one warp per kept doc.
 __global__ void __launch_bounds__(256)
 k_tc_finalize(uint32_t *__restrict__ maxkey, const int *__restrict__ q_off, int QS, const int *__restrict__ n_kept, int Mcap,

@@ -423,14 +423,12 @@ def test_long_queries_keep_the_fast_paths(oracle, npb, corpus, nq):
             assert np.array_equal(r.scores, w.scores), (kw, nq)
 
 
-@pytest.mark.parametrize("env", [{"PB_FILTER_V1": "1"}, {"PB_FAST_APPROX": "0"}, {"PB_K1_TC": "0"}, {"PB_FILTER_WS": "0"},
-                                 {"PB_PAIR_EXACT": "0"}, {}])
+@pytest.mark.parametrize("env", [{"PB_FILTER_V1": "1"}, {"PB_FAST_APPROX": "0"}, {"PB_K1_TC": "0"}, {"PB_PAIR_EXACT": "0"}, {}])
 def test_both_filter_kernels_and_their_score_tables(oracle, npb, corpus, monkeypatch, env):
-    # the linear filter (k_exact_tc2: centroid score from the 16-bit table + residual part on the tensor cores) on the
+    # the linear filter (k_maxsim_tc: centroid score from the 16-bit table + residual part on the tensor cores) on the
     # tensor-core table (default) and on the exact table (PB_K1_TC=0); the decompressing filter (k_exact_tc) when
-    # forced (PB_FILTER_V1=1) or when there is no table (PB_FAST_APPROX=0); the linear filter as one CTA-wide loop
-    # (k_exact_tc2, PB_FILTER_WS=0) or as the warp-specialised pipeline (k_maxsim_tc, default), the exact stage on the
-    # (token, q) pairs inside the certified band (default) or on every token of the survivors (PB_PAIR_EXACT=0)
+    # forced (PB_FILTER_V1=1) or when there is no table (PB_FAST_APPROX=0); the exact stage on the (token, q) pairs
+    # inside the certified band (default) or on every token of the survivors (PB_PAIR_EXACT=0)
     docs, ix, qs, src, _ = corpus
     for k, v in env.items():
         monkeypatch.setenv(k, v)

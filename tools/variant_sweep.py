@@ -17,7 +17,6 @@ VARIANTS = [
     ("filter off", {"PB_FAST_EXACT": "0"}),
     ("list-scan probe (exact a2)", {"PB_PROBE16": "0", "PB_K1_TC": "0"}),
     ("decompressing filter (PB_FILTER_V1)", {"PB_FILTER_V1": "1"}),
-    ("one-loop filter k_exact_tc2 (PB_FILTER_WS=0)", {"PB_FILTER_WS": "0"}),
     ("token-form exact stage (PB_PAIR_EXACT=0)", {"PB_PAIR_EXACT": "0"}),
     ("ws grid 4", {"PB_WS_GRID": "4"}),
     ("ws grid 16", {"PB_WS_GRID": "16"}),
