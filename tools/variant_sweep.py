@@ -22,6 +22,7 @@ VARIANTS = [
     ("ws grid 16", {"PB_WS_GRID": "16"}),
     ("ws grid 32", {"PB_WS_GRID": "32"}),
     ("lanes 1 (PB_LANES=1)", {"PB_LANES": "1"}),
+    ("lanes 2, no stagger", {"PB_LANE_STAGGER": "0"}),
     ("lanes 3", {"PB_LANES": "3"}),
     ("lanes 4", {"PB_LANES": "4"}),
     ("nq=48 queries", {"__args__": "--nq 48"}),
