@@ -79,7 +79,7 @@ def parse_args():
     ap.add_argument("--parity-queries", type=int, default=-1, help="oracle-checked queries; -1 = 64 at N=1, 16 at N>1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle (parity + cpu_baseline)")
     ap.add_argument("--threads", type=int, default=2, help="host threads for the extra concurrent-callers measurement")
-    ap.add_argument("--lanes", type=int, default=0, help="pb_set_lanes (0 = the library's default, 2)")
+    ap.add_argument("--lanes", type=int, default=0, help="pb_set_lanes (0 = the library's default, 1 = off)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--docs-per-topic", type=int, default=1024)
     ap.add_argument("--pool", type=int, default=256, help="centroids per topic pool")
@@ -425,11 +425,11 @@ def run_b200(args):
     # the same steps with the batch searched as one slice (pb_set_lanes(1)): kernels run alone, so these are the
     # per-kernel times that are not stretched by a co-running slice
     one_lane = None
-    if world == 1 and args.lanes != 1 and args.batch >= 16:
+    if world == 1 and args.lanes > 1 and args.batch >= 16:
         gpu.set_lanes(1)
         gpu.search_batch_device(d_q[0].data_ptr(), offs, params, d_ids.data_ptr(), d_sc.data_ptr(), d_cn.data_ptr())
         st1, km1, _, ln1, dm1, _ = timed_region()
-        gpu.set_lanes(args.lanes if args.lanes > 0 else 2)
+        gpu.set_lanes(args.lanes)
         one_lane = {"value": args.batch * args.steps / (dm1 * 1e-3), "unit": "queries/s", "ms_per_step": dm1 / args.steps,
                     "gpu_launches": ln1, "stage_ms_per_step": {k: v / args.steps for k, v in st1.items()},
                     "kernel_ms_per_step": {k: v / args.steps for k, v in km1.items()}}
@@ -626,7 +626,7 @@ def run_b200(args):
         "e2e": {"value": args.batch * args.steps / e2e_s, "unit": "queries/s",
                 "h2d_bytes_per_step": int(flat[0].nbytes + offs.nbytes),
                 "d2h_bytes_per_step": int(h_ids.nbytes + h_sc.nbytes + h_cn.nbytes), "ms_per_step": 1e3 * e2e_s / args.steps},
-        "lanes": {"count": (args.lanes if args.lanes > 0 else 2) if world == 1 and args.batch >= 16 else 1,
+        "lanes": {"count": args.lanes if args.lanes > 1 and world == 1 and args.batch >= 16 else 1,
                   "what": "slices of a batch searched concurrently inside one call, each on its own stream "
                           "(pb_set_lanes); stage / kernel times of the timed region are sums over the slices",
                   "one_lane": one_lane},

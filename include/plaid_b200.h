@@ -231,8 +231,9 @@ PB_API void pb_set_scores_tc(pb_index *ix, int32_t enabled);
 /* Lanes: a batch of >= 16 queries is cut into `lanes` slices that run the whole pipeline concurrently, each on its own
  * stream and workspace (helper threads inside the library do the launching), so that one slice's latency-bound kernels
  * overlap another's bandwidth-bound ones.  Results are independent of the setting (queries are independent; next-plaid
- * itself searches a batch query by query, search.rs:1136-1160).  Default 2 (env PB_LANES); 1 = off.  Doc-sharded
- * handles and traced calls always run one lane. */
+ * itself searches a batch query by query, search.rs:1136-1160).  Default 1 = off (env PB_LANES): measured on config B a
+ * single caller gains 2 % with 2 lanes, while several host threads calling one handle -- the reference's deployment
+ * model, which already overlaps whole batches -- lose 10 %.  Doc-sharded handles and traced calls always run one lane. */
 PB_API void pb_set_lanes(pb_index *ix, int32_t lanes);
 
 /* Enable per-stage CUDA-event timing for subsequent searches on this handle (adds event

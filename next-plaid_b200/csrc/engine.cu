@@ -9,7 +9,6 @@
 #include <cub/device/device_select.cuh>
 
 #include <algorithm>
-#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
@@ -326,19 +325,6 @@ struct LaneWorker {
     }
 };
 
-// Stagger of a laned call: the approximate stage (a5) sits on the L2 throughput cap, so two slices running it at the same
-// time gain nothing; slice l therefore starts its a5 when slice l-1 has finished its own (a stream wait on an event), and
-// runs under slice l-1's latency-bound back end (a6-a9) instead.  state[l]: 0 = not yet, 1 = event recorded, 2 = lane left
-// without recording (error, empty path).
-struct LaneSync {
-    std::atomic<int> state[8];
-    cudaEvent_t a5_done[8] = {};
-    bool created = false;
-};
-static thread_local LaneSync *g_lane_sync = nullptr;
-static thread_local int g_lane_id = 0;
-static thread_local bool g_lane_waited = false, g_lane_recorded = false;
-
 struct pb_index {
     int device = 0;
     int dim = 0, nbits = 0, packed = 0;
@@ -367,11 +353,10 @@ struct pb_index {
     bool filter_v1 = false;    // PB_FILTER_V1=1: always the decompressing filter k_exact_tc (A/B measurement)
     bool pair_exact = true;    // exact stage on the (token, query token) pairs that can hold a maximum (PB_PAIR_EXACT=0: k_exact)
     int ws_grid = 8;           // k_maxsim_tc CTAs per SM across the batch (PB_WS_GRID)
-    int lanes = 2;             // slices of a batch searched concurrently, each on its own stream (PB_LANES; 1 = off)
+    int lanes = 1;             // slices of a batch searched concurrently, each on its own stream (pb_set_lanes / PB_LANES; 1 = off)
     std::mutex lane_mu;        // one laned call at a time per handle (a second concurrent caller runs un-laned)
     std::vector<std::unique_ptr<LaneWorker>> lane_workers;
-    LaneSync lane_sync;
-    bool lane_stagger = true;  // PB_LANE_STAGGER=0: slices start every stage together
+    bool recheck_v1 = false;   // PB_RECHECK_V1=1: one-pass top-3 form of k_recheck_pairs (A/B)
     bool profiling = false;
     size_t st_budget = (size_t)8 << 30;  // workspace budget of one search call (PB_WS_BUDGET_MB)
     ncclComm_t comm = nullptr;  // doc-sharded deployment: one rank per GPU
@@ -653,7 +638,7 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_PAIR_EXACT")) ix->pair_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_WS_GRID")) ix->ws_grid = std::max(1, atoi(e));
         if (const char *e = getenv("PB_LANES")) ix->lanes = std::min(8, std::max(1, atoi(e)));
-        if (const char *e = getenv("PB_LANE_STAGGER")) ix->lane_stagger = atoi(e) != 0;
+        if (const char *e = getenv("PB_RECHECK_V1")) ix->recheck_v1 = atoi(e) != 0;
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC_DIAG")) ix->k1_diag = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC")) ix->k1_tc = atoi(e) != 0;
@@ -745,8 +730,6 @@ extern "C" void pb_index_close(pb_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     ix->lane_workers.clear();  // joins the helper threads
-    if (ix->lane_sync.created)
-        for (auto &e : ix->lane_sync.a5_done) cudaEventDestroy(e);
     cudaDeviceSynchronize();
     if (ix->comm) g_nccl.CommDestroy(ix->comm);
     delete ix;
@@ -1503,12 +1486,6 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
         if (prof) CK(cudaEventRecord(ws.ev[4], ws.stream));
 
         // ---- a5 approximate scores ----
-        if (g_lane_sync && g_lane_id > 0 && !g_lane_waited) {  // staggered lanes: after the previous slice's a5
-            g_lane_waited = true;
-            int st_prev;
-            while ((st_prev = g_lane_sync->state[g_lane_id - 1].load(std::memory_order_acquire)) == 0) std::this_thread::yield();
-            if (st_prev == 1) CK(cudaStreamWaitEvent(ws.stream, g_lane_sync->a5_done[g_lane_id - 1], 0));
-        }
         CKS(ws.counters.ensure((size_t)(B + 2) * 8));  // [0] candidate codes gathered, [1+b] kept-doc tokens, [B+1] re-check gathers
         CK(cudaMemsetAsync(ws.counters.p, 0, (size_t)(B + 2) * 8, ws.stream));
         CKS(ws.approx.ensure((size_t)B * ix->D * 4));
@@ -1529,11 +1506,6 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
                 st16, ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(), list, ix->D, list_n,
                 ws.lsum.as<uint32_t>(), cnt);
             KEV_END(PB_KERNEL_APPROX16);
-            if (g_lane_sync && !g_lane_recorded) {
-                g_lane_recorded = true;
-                CK(cudaEventRecord(g_lane_sync->a5_done[g_lane_id], ws.stream));
-                g_lane_sync->state[g_lane_id].store(1, std::memory_order_release);
-            }
             // band per query token in code units (W = band * nq + 8).  Exact table: +-1 code of rounding per token and side
             // plus the fp32 summation error -> 4.  Estimate table (k_scores_tc.cuh): W = nq (1.004 + 2 err) + nq^2/256 + 4
             // <= nq (ceil(1.004 + 2 err) + 1) + 8 for nq <= 256.
@@ -1553,7 +1525,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             CKS(ws.rcn.ensure((size_t)B * 4 + 16));
             CK(cudaMemsetAsync(ws.rcn.p, 0, (size_t)B * 4, ws.stream));
             int *d_fb = const_cast<int *>(d_probe_fallback);
-            k_recheck_pairs<<<dim3(ix->sm_count * 2, B), 256, 0, ws.stream>>>(
+            (ix->recheck_v1 ? k_recheck_pairs : (QS <= 32 ? k_recheck_pairs2<4> : k_recheck_pairs2<8>))<<<dim3(ix->sm_count * 2, B), 256, 0, ws.stream>>>(
                 ws.ST16.as<unsigned short>(), ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(),
                 cand_list, ix->D, cand_n, 2 * ix->k1_margin + 1, rc_cap, pair_cap, ws.rcpairs.as<u64>(), ws.rcn.as<int>(), d_fb,
                 ws.counters.as<unsigned long long>() + B + 1);
@@ -1939,24 +1911,9 @@ static pb_status search_impl(pb_index *ix, const pb_search_params *p, const Sear
         if (io.out_scores) ios[l].out_scores = io.out_scores + b0 * top_k;
         ios[l].out_counts = io.out_counts ? io.out_counts + b0 : nullptr;
     }
-    LaneSync *sync = nullptr;
-    if (ix->lane_stagger) {
-        sync = &ix->lane_sync;
-        if (!sync->created) {
-            CK(cudaSetDevice(ix->device));
-            for (auto &e : sync->a5_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            sync->created = true;
-        }
-        for (auto &st : sync->state) st.store(0);
-    }
     auto run_lane = [&](int l) {
         g_budget_div = lanes;
-        g_lane_sync = sync;
-        g_lane_id = l;
-        g_lane_waited = g_lane_recorded = false;
         sts[l] = search_impl_inner(ix, p, ios[l]);
-        if (sync && sync->state[l].load() == 0) sync->state[l].store(2, std::memory_order_release);  // left without an a5
-        g_lane_sync = nullptr;
         g_budget_div = 1;
         stats[l] = g_stats;
         if (sts[l] != PB_OK) errs[l] = g_err;

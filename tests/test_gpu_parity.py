@@ -557,4 +557,4 @@ def test_lanes_cut_a_batch_without_changing_a_bit(oracle, npb, corpus):
         with pytest.raises(Exception):
             gpu.search_batch(batch, bad)
     finally:
-        gpu.set_lanes(2)
+        gpu.set_lanes(1)
