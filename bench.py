@@ -582,7 +582,9 @@ def run_b200(args):
         traffic_cap = None
         if os.path.exists(cap):
             try:
-                traffic_cap = json.load(open(cap)).get(names[dom])
+                tr = json.load(open(cap))
+                hit = [k for k in tr if k.split("<")[0] == names[dom].split(" ")[0].split("<")[0]]
+                traffic_cap = dict(tr[hit[0]], capture_kernel=hit[0]) if hit else None
             except Exception:
                 traffic_cap = None
         roof = {"bound": "hbm", "kernel": d["kernel"], "achieved": d["achieved_gbs"], "peak": peaks["hbm"], "unit": "GB/s",

@@ -356,7 +356,6 @@ struct pb_index {
     int lanes = 1;             // slices of a batch searched concurrently, each on its own stream (pb_set_lanes / PB_LANES; 1 = off)
     std::mutex lane_mu;        // one laned call at a time per handle (a second concurrent caller runs un-laned)
     std::vector<std::unique_ptr<LaneWorker>> lane_workers;
-    bool recheck_v1 = false;   // PB_RECHECK_V1=1: one-pass top-3 form of k_recheck_pairs (A/B)
     bool profiling = false;
     size_t st_budget = (size_t)8 << 30;  // workspace budget of one search call (PB_WS_BUDGET_MB)
     ncclComm_t comm = nullptr;  // doc-sharded deployment: one rank per GPU
@@ -638,7 +637,6 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_PAIR_EXACT")) ix->pair_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_WS_GRID")) ix->ws_grid = std::max(1, atoi(e));
         if (const char *e = getenv("PB_LANES")) ix->lanes = std::min(8, std::max(1, atoi(e)));
-        if (const char *e = getenv("PB_RECHECK_V1")) ix->recheck_v1 = atoi(e) != 0;
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC_DIAG")) ix->k1_diag = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC")) ix->k1_tc = atoi(e) != 0;
@@ -1525,7 +1523,7 @@ static pb_status search_impl_inner(pb_index *ix, const pb_search_params *p, cons
             CKS(ws.rcn.ensure((size_t)B * 4 + 16));
             CK(cudaMemsetAsync(ws.rcn.p, 0, (size_t)B * 4, ws.stream));
             int *d_fb = const_cast<int *>(d_probe_fallback);
-            (ix->recheck_v1 ? k_recheck_pairs : (QS <= 32 ? k_recheck_pairs2<4> : k_recheck_pairs2<8>))<<<dim3(ix->sm_count * 2, B), 256, 0, ws.stream>>>(
+            (QS <= 32 ? k_recheck_pairs<4> : k_recheck_pairs<8>)<<<dim3(ix->sm_count * 2, B), 256, 0, ws.stream>>>(
                 ws.ST16.as<unsigned short>(), ws.qoff.as<int>(), ix->K, QS, ix->ucodes.as<uint32_t>(), ix->udoc_off.as<long long>(),
                 cand_list, ix->D, cand_n, 2 * ix->k1_margin + 1, rc_cap, pair_cap, ws.rcpairs.as<u64>(), ws.rcn.as<int>(), d_fb,
                 ws.counters.as<unsigned long long>() + B + 1);

@@ -482,132 +482,23 @@ k_cells_emit(const uint32_t *__restrict__ ulist, const int *__restrict__ n_u, co
 // maximum of the pinned-order dots over the (typically one or two) codes within `code_margin` of m_q.  Three kernels,
 // each with all the parallelism the work has (a one-kernel form -- warp per doc, dots in place -- ran at 8 warps per
 // SM and 1.6 ms):
-//   k_recheck_pairs  warp per doc, lane = query token: column maxima (gather_max), then the (doc slot, q, code) pairs
-//                    inside the margin appended to the query's pair list (warp-aggregated atomics)
+//   k_recheck_pairs  warp per doc: column maxima, then the (doc slot, q, code) pairs inside the margin appended to the
+//                    query's pair list (staged per warp: one atomic per doc and pass)
 //   k_recheck_dots   thread per pair: the pinned-order dot, atomicMax of its score key into exactmax[b][slot][q]
 //   k_recheck_sum    warp per doc: the q-ordered fp32 sum of the maxima -> approx[b][i] and the cut key (what k_approx
 //                    emits); clears the doc's exactmax row for the next call
 // More docs than rc_cap or more pairs than pair_cap raise *fallback (the sub-batch is redone on the exact path).
 // ------------------------------------------------------------------------------------------
-// One pass over the doc's codes: every lane (= query token) tracks its three largest estimate codes with their
-// centroids; at the end the entries within the margin of the largest are the pairs.  Only when the third is still inside
-// the margin could a fourth have been dropped: that (rare) lane re-walks the list and emits every code in the margin.
-PB_DEV void top3_insert(uint32_t v, uint32_t c, uint32_t (&tv)[3], uint32_t (&tc)[3]) {
-    if (v <= tv[2] || c == tc[0] || c == tc[1] || c == tc[2]) return;  // ties keep the earlier code; repeats are not new
-    if (v > tv[0]) {
-        tv[2] = tv[1]; tc[2] = tc[1];
-        tv[1] = tv[0]; tc[1] = tc[0];
-        tv[0] = v; tc[0] = c;
-    } else if (v > tv[1]) {
-        tv[2] = tv[1]; tc[2] = tc[1];
-        tv[1] = v; tc[1] = c;
-    } else {
-        tv[2] = v; tc[2] = c;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_recheck_pairs(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
-                const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off,
-                const uint32_t *__restrict__ cand, long long cand_cap, const int *__restrict__ n_cand, int code_margin,
-                int rc_cap, int pair_cap, u64 *__restrict__ pairs, int *__restrict__ n_pairs, int *__restrict__ fallback,
-                unsigned long long *__restrict__ tok_counter) {
-    const int b = blockIdx.y;
-    const int nq = q_off[b + 1] - q_off[b];
-    const int n = n_cand[b];
-    if (n > rc_cap) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(fallback, 1);
-        return;
-    }
-    const int lane = threadIdx.x & 31;
-    const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
-    const unsigned short *STb = ST16 + (size_t)b * K * QS;
-    const unsigned rowb = (unsigned)QS * 2u;
-    u64 *plist = pairs + (size_t)b * pair_cap;
-    unsigned long long my_tokens = 0;
-    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps_per_grid) {
-        const uint32_t d = cand[(size_t)b * cand_cap + i];
-        const long long t0 = udoc_off[d], t1 = udoc_off[d + 1];
-        my_tokens += (unsigned long long)(t1 - t0);
-        for (int qc = 0; qc < nq; qc += 32) {
-            const int q = qc + lane;
-            const bool live = q < nq;
-            const char *col = reinterpret_cast<const char *>(STb + (live ? q : 0));
-            // values are stored + 1 so that 0 means "empty slot" (a code can be 0)
-            uint32_t tv[3] = {0u, 0u, 0u}, tc[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
-            for (long long t = t0; t < t1; t += 16) {  // lists are padded to 8: 16 row loads in flight, the tail has 8
-                const bool two = t + 16 <= t1;
-                const uint4 ca = *reinterpret_cast<const uint4 *>(ucodes + t), cb = *reinterpret_cast<const uint4 *>(ucodes + t + 4);
-                const uint4 cc = two ? *reinterpret_cast<const uint4 *>(ucodes + t + 8) : cb;
-                const uint4 cd = two ? *reinterpret_cast<const uint4 *>(ucodes + t + 12) : cb;
-                const uint32_t cs[16] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w, cc.x, cc.y, cc.z, cc.w, cd.x, cd.y, cd.z, cd.w};
-                uint32_t v[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) v[e] = *reinterpret_cast<const unsigned short *>(col + (size_t)cs[e] * rowb);
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    if (live) top3_insert(v[e] + 1u, cs[e], tv, tc);
-            }
-            const uint32_t lo = tv[0] > (uint32_t)code_margin ? tv[0] - (uint32_t)code_margin : 1u;
-            int cnt = 0;
-            if (live && tv[0]) cnt = 1 + (tv[1] >= lo ? 1 : 0) + (tv[2] >= lo ? 1 : 0);
-            const bool deep = live && tv[2] != 0u && tv[2] >= lo;  // a fourth code may sit in the margin as well
-            if (__any_sync(PB_FULL, deep)) {
-                // rare: this warp re-walks the list; the `deep` lanes count / emit every distinct code in their margin
-                if (deep) {
-                    cnt = 0;
-                    uint32_t prev = 0xffffffffu;
-                    for (long long t = t0; t < t1; ++t) {
-                        const uint32_t c = ucodes[t];
-                        if (c != prev && (uint32_t)*reinterpret_cast<const unsigned short *>(col + (size_t)c * rowb) + 1u >= lo) ++cnt;
-                        prev = c;
-                    }
-                }
-            }
-            int incl = cnt;  // inclusive prefix of the pair counts over the lanes
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(PB_FULL, incl, o);
-                if (lane >= o) incl += y;
-            }
-            const int total = __shfl_sync(PB_FULL, incl, 31);
-            if (total == 0) continue;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&n_pairs[b], total);
-            base = __shfl_sync(PB_FULL, base, 0);
-            int pos = base + incl - cnt;
-            if (pos + cnt > pair_cap) {
-                if (cnt) atomicOr(fallback, 1);
-                continue;
-            }
-            const u64 head = ((u64)i << 40) | ((u64)q << 32);
-            if (deep) {
-                uint32_t prev = 0xffffffffu;
-                for (long long t = t0; t < t1; ++t) {
-                    const uint32_t c = ucodes[t];
-                    if (c != prev && (uint32_t)*reinterpret_cast<const unsigned short *>(col + (size_t)c * rowb) + 1u >= lo) plist[pos++] = head | c;
-                    prev = c;
-                }
-            } else if (cnt) {
-                plist[pos] = head | tc[0];
-                if (tv[1] >= lo) plist[++pos] = head | tc[1];
-                if (tv[2] >= lo) plist[++pos] = head | tc[2];
-            }
-        }
-    }
-    if (lane == 0 && my_tokens) atomicAdd(tok_counter, my_tokens);
-}
-
-// The same pairs from two passes over the doc's codes with the row-group gather of k_approx16 (16-byte loads of 8 query
-// tokens, packed vmaxu2 / vcmpgeu2): pass A the column maxima, pass B (rows now in L1) every (code, query token) whose
-// estimate code is within code_margin of its column maximum.  ~2 thread instructions per table entry against ~30 for the
-// one-pass top-3 form above (which was issue-bound: 0.33 ms for 1024 docs x 32 queries).  Hits go through a per-warp
+// Two passes over the doc's codes with the row-group gather of k_approx16 (16-byte loads of 8 query tokens, packed
+// vmaxu2 / vcmpgeu2): pass A the column maxima, pass B (rows now in L1) every (code, query token) whose estimate code is
+// within code_margin of its column maximum.  (A one-pass form -- lane = query token, 2-byte loads, the three largest codes
+// of every column tracked in registers -- was issue-bound: 0.33 ms against 0.24 ms for 1024 docs x 32 queries.)  Hits go through a per-warp
 // shared-memory stage so that the query's pair counter sees one atomic per (doc, pass); a stage overflow (a query token
 // whose maximum is inside the margin of zero lists every code) writes the surplus directly.  The padding entries of a
 // code list repeat its last code: such repeats are listed again, k_recheck_dots' atomicMax does not care.
 template <int LPR>
 __global__ void __launch_bounds__(256, LPR == 4 ? 3 : 2)
-k_recheck_pairs2(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
+k_recheck_pairs(const unsigned short *__restrict__ ST16, const int *__restrict__ q_off, long long K, int QS,
                  const uint32_t *__restrict__ ucodes, const long long *__restrict__ udoc_off,
                  const uint32_t *__restrict__ cand, long long cand_cap, const int *__restrict__ n_cand, int code_margin,
                  int rc_cap, int pair_cap, u64 *__restrict__ pairs, int *__restrict__ n_pairs, int *__restrict__ fallback,

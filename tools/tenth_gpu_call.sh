@@ -21,6 +21,6 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:
     --log-file gpurun_out/r02_launches.csv $B > gpurun_out/ncu_launches.log 2>&1
 tail -c 200 gpurun_out/ncu_launches.log
 timeout 500 ncu --set full --import-source on --clock-control none \
-    -k "regex:^k_(maxsim_tc|pair_exact|scores16_tc|recheck_pairs2|recheck_dots|approx16|select_u32)" -s 7 -c 8 -o gpurun_out/r02_final \
+    -k "regex:^k_(maxsim_tc|pair_exact|scores16_tc|recheck_pairs|recheck_dots|approx16|select_u32)" -s 7 -c 8 -o gpurun_out/r02_final \
     $B > gpurun_out/ncu_final.log 2>&1
 tail -c 300 gpurun_out/ncu_final.log

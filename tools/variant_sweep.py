@@ -22,7 +22,6 @@ VARIANTS = [
     ("ws grid 16", {"PB_WS_GRID": "16"}),
     ("ws grid 32", {"PB_WS_GRID": "32"}),
     ("lanes 2 (PB_LANES=2)", {"PB_LANES": "2"}),
-    ("one-pass re-check pairs (PB_RECHECK_V1=1)", {"PB_RECHECK_V1": "1"}),
     ("lanes 3", {"PB_LANES": "3"}),
     ("lanes 4", {"PB_LANES": "4"}),
     ("nq=48 queries", {"__args__": "--nq 48"}),
