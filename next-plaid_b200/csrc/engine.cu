@@ -1049,7 +1049,8 @@ static float filter_eps_unit2(const pb_index *ix, int E) {
 
 static size_t smem_maxsim_tc(int dim, int packed, int nqt) {
     const int nbits = packed * 8 / dim;
-    return (size_t)2 * (dim / 8) * PB_XTC_LBO + (size_t)nqt * dim * 2 + (size_t)256 * (8 / nbits) * 2 + 4 * 128 * sizeof(MsMeta) +
+    return (size_t)2 * (dim / 8) * PB_XTC_LBO + (size_t)nqt * dim * 2 + (size_t)256 * (8 / nbits) * 2 * (nbits == 4 ? 4 : 1) +
+           4 * 128 * sizeof(MsMeta) +
            12 * 8 + 16;
 }
 

@@ -99,11 +99,14 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
     static_assert(PACKED % 4 == 0, "k_maxsim_tc: packed rows are read in 32-bit words");
     static_assert(A_BYTES % 128 == 0, "k_maxsim_tc: stage alignment");
     constexpr int VB = 8 / NBITS;
+    // the 4-bit table (256 entries x 4 B) is kept in TR copies, lane l reads copy l % TR: 32 random lookups of one copy hit
+    // the worst bank ~3.5 times, 8 lookups spread over a copy's 8 banks ~2.3 times (the kernel sits on the LSU pipe)
+    constexpr int TR = NBITS == 4 ? 4 : 1;
     constexpr int SW = NQT / 2;  // 32-bit words of a score-table row
     unsigned char *As = smem_x;                                   // [2][A_BYTES] fp16 residual tiles
     unsigned char *Qb = As + 2 * A_BYTES;                         // [NQT query rows] fp16 operand tile
-    __half *Th = reinterpret_cast<__half *>(Qb + QB_BYTES);       // [256][VB]: fp16 bucket weights of the fields of a byte
-    MsMeta *meta = reinterpret_cast<MsMeta *>(Th + 256 * VB);     // [4][128]
+    __half *Th = reinterpret_cast<__half *>(Qb + QB_BYTES);       // [256][TR][VB]: fp16 bucket weights of the fields of a byte
+    MsMeta *meta = reinterpret_cast<MsMeta *>(Th + 256 * VB * TR); // [4][128]
     uint64_t *bars = reinterpret_cast<uint64_t *>(meta + 4 * 128);
     uint64_t *a_full = bars, *a_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6, *m_full = bars + 8;  // 2,2,2,2,4
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
@@ -119,8 +122,8 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
     const long long c_lo = (long long)blockIdx.x * per, c_hi = min(n_chunks, c_lo + per);
     if (c_lo >= c_hi || nq == 0 || qflag[b]) return;
     const int n = (int)(c_hi - c_lo);
-    for (int i = threadIdx.x; i < 256 * VB; i += blockDim.x) {
-        const int byte = i / VB, j = i - byte * VB;
+    for (int i = threadIdx.x; i < 256 * VB * TR; i += blockDim.x) {
+        const int byte = i / (VB * TR), j = i % VB;
         Th[i] = __float2half_rn(w_rev[(byte >> (8 - NBITS * (j + 1))) & ((1 << NBITS) - 1)]);
     }
     for (int idx = threadIdx.x; idx < NQT * KC; idx += blockDim.x) {
@@ -198,9 +201,9 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
                 uint32_t wv[4];
                 if (NBITS == 4) {
                     const uint32_t x = pw[kc];
-                    const uint32_t *T32 = reinterpret_cast<const uint32_t *>(Th);
+                    const uint32_t *T32 = reinterpret_cast<const uint32_t *>(Th) + (t & (TR - 1));
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) wv[j] = T32[(x >> (8 * j)) & 255u];
+                    for (int j = 0; j < 4; ++j) wv[j] = T32[((x >> (8 * j)) & 255u) * TR];
                 } else if (NBITS == 2) {
                     const uint32_t x = pw[kc >> 1] >> (16 * (kc & 1));
                     const uint2 *T64 = reinterpret_cast<const uint2 *>(Th);
@@ -271,6 +274,18 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
         const char *STb = reinterpret_cast<const char *>(ST16 + (size_t)b * K * QS);
         const unsigned rowb = (unsigned)QS * 2u;
         const float band = EMIT ? 2.0f * band_unit * qnmax[b] + 1e-6f : 0.0f;
+        // pass 2: the threshold keys of the token's doc for query tokens lane, lane + 32 (what a warp whose 32 tokens share
+        // their doc needs), fetched with the side loads so that src_rank -> maxkey is off the epilogue's critical path
+        auto load_thr = [&](const MsMeta &m, uint32_t (&tk)[NQT / 32]) __attribute__((always_inline)) {
+#pragma unroll
+            for (int h = 0; h < NQT / 32; ++h) tk[h] = 0u;
+            if (EMIT && m.r >= 0) {
+                const uint32_t *trow = maxkey + ((size_t)b * Mcap + src_rank[(size_t)b * Mcap + m.r]) * QS;
+#pragma unroll
+                for (int h = 0; h < NQT / 32; ++h)
+                    if (32 * h + lane < nq) tk[h] = trow[32 * h + lane];
+            }
+        };
         auto load_side = [&](const MsMeta &m, uint32_t (&sw)[SW], float &inv) __attribute__((always_inline)) {
             inv = 1.0f;  // (a token slot past the stream: its bias is -inf, the product must stay -inf)
             if (m.r >= 0) {
@@ -290,8 +305,8 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
                 for (int i = 0; i < SW; ++i) sw[i] = 0u;
             }
         };
-        auto step = [&](int i, const MsMeta &cur, const uint32_t (&sw)[SW], float inv, MsMeta &nxt, uint32_t (&swn)[SW],
-                        float &invn) __attribute__((always_inline)) {
+        auto step = [&](int i, const MsMeta &cur, const uint32_t (&sw)[SW], float inv, const uint32_t (&tk)[NQT / 32], MsMeta &nxt,
+                        uint32_t (&swn)[SW], float &invn, uint32_t (&tkn)[NQT / 32]) __attribute__((always_inline)) {
             nxt.r = -1;
             nxt.g = 0;
             nxt.code = 0;
@@ -301,6 +316,7 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
                 nxt = meta[ms * 128 + t];
             }
             load_side(nxt, swn, invn);
+            load_thr(nxt, tkn);
             const int s = i & 1;
             mbar_wait(&t_full[s], (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
@@ -362,10 +378,7 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
                     // thresholds of the warp's doc: lane = query token (a warp that straddles docs reads per token)
                     const bool uni = grp == PB_FULL;
                     float thr_l = -INFINITY;
-                    if (uni && rank >= 0 && 32 * h + lane < nq) {
-                        const uint32_t k = maxkey[((size_t)b * Mcap + src_rank[(size_t)b * Mcap + rank]) * QS + 32 * h + lane];
-                        if (k) thr_l = key_to_score(k) - band;
-                    }
+                    if (uni && rank >= 0 && 32 * h + lane < nq && tk[h]) thr_l = key_to_score(tk[h]) - band;
                     const uint32_t *trow = nullptr;
                     if (!uni && rank >= 0) trow = maxkey + ((size_t)b * Mcap + src_rank[(size_t)b * Mcap + rank]) * QS + 32 * h;
 #pragma unroll
@@ -387,14 +400,15 @@ k_maxsim_tc(const float *__restrict__ Q, const int *__restrict__ q_off, int QS, 
             }
         };
         MsMeta mA, mB;
-        uint32_t sA[SW], sB[SW];
+        uint32_t sA[SW], sB[SW], kA[NQT / 32], kB[NQT / 32];
         float iA, iB;
         mbar_wait(&m_full[0], 0u);
         mA = meta[t];
         load_side(mA, sA, iA);
+        load_thr(mA, kA);
         for (int i = 0; i < n; i += 2) {
-            step(i, mA, sA, iA, mB, sB, iB);
-            if (i + 1 < n) step(i + 1, mB, sB, iB, mA, sA, iA);
+            step(i, mA, sA, iA, kA, mB, sB, iB, kB);
+            if (i + 1 < n) step(i + 1, mB, sB, iB, kB, mA, sA, iA, kA);
         }
     }
     tc_fence_before();
@@ -475,10 +489,22 @@ k_pair_exact(const u64 *__restrict__ pairs, const int *__restrict__ n_pairs, int
                 if (!(norm >= 1e-12f)) norm = 1e-12f;  // f32::max(1e-12)
                 if (lane < G) {
                     float *dst = rows + (size_t)(r0 + e) * LD + 4 * lane;
-                    dst[0] = __fdiv_rn(v.x, norm);
-                    dst[1] = __fdiv_rn(v.y, norm);
-                    dst[2] = __fdiv_rn(v.z, norm);
-                    dst[3] = __fdiv_rn(v.w, norm);
+                    // the hoisted form of the IEEE division (k_exact.cuh: div_setup / div_fast) where it is exact
+                    const uint32_t a0 = __float_as_uint(v.x) & 0x7fffffffu, a1 = __float_as_uint(v.y) & 0x7fffffffu;
+                    const uint32_t a2 = __float_as_uint(v.z) & 0x7fffffffu, a3 = __float_as_uint(v.w) & 0x7fffffffu;
+                    const uint32_t nb = __float_as_uint(norm);
+                    if (div_range_ok(min(min(min(a0, a1), min(a2, a3)), nb), max(max(max(a0, a1), max(a2, a3)), nb))) {
+                        const float yr = div_setup(norm);
+                        dst[0] = div_fast(v.x, norm, yr);
+                        dst[1] = div_fast(v.y, norm, yr);
+                        dst[2] = div_fast(v.z, norm, yr);
+                        dst[3] = div_fast(v.w, norm, yr);
+                    } else {
+                        dst[0] = __fdiv_rn(v.x, norm);
+                        dst[1] = __fdiv_rn(v.y, norm);
+                        dst[2] = __fdiv_rn(v.z, norm);
+                        dst[3] = __fdiv_rn(v.w, norm);
+                    }
                 }
             }
         }
