@@ -2261,7 +2261,7 @@ extern "C" pb_status pb_codec_open(int32_t device, const float *centroids, int64
         CKS(upload(c->cutoffs, bucket_cutoffs, (size_t)((1 << nbits) - 1) * 4, PB_MEM_HOST));
         c->has_cutoffs = true;
     }
-    // tensor-core filter: bf16 copy of the centroids, their largest norm, finiteness
+    // tensor-core filter: fp16 copy of the centroids (tile order), their largest norm, finiteness
     c->use_tc = (dim == 64 || dim == 96 || dim == 128) && K >= 256 && !getenv("PB_ASSIGN_EXACT") &&
                 smem_assign_tc(dim) <= 227 * 1024;
     if (c->use_tc) {
@@ -2517,7 +2517,7 @@ extern "C" int64_t pb_codec_heldout_tokens(int64_t num_embeddings) {  // min(0.0
     return (int64_t)std::min(0.05 * (double)num_embeddings, 50000.0);
 }
 
-// k-means assignment step.  dims 64 / 96 / 128 with K >= 256: the bf16 tcgen05 GEMM of the encode path with the
+// k-means assignment step.  dims 64 / 96 / 128 with K >= 256: the fp16 tcgen05 GEMM of the encode path with the
 // -|c|^2/2 bias added in its epilogue, best shortlist entry taken as is; otherwise the exact fp32 kernel.
 struct KmeansAssign {
     DevBuf xb, cb, bias, ts, ti, scratch;

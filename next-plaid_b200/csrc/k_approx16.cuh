@@ -216,18 +216,27 @@ k_select_u32(const uint32_t *__restrict__ sel_keys, const int *__restrict__ sel_
             for (int i = threadIdx.x; i < 32 * 256; i += blockDim.x) (&hist[0][0])[i] = 0;
             __syncthreads();
             const uint32_t prefix = prefix_s, mask = mask_s;
-            for (int i0 = 0; i0 < ns; i0 += blockDim.x) {
-                const int i = i0 + threadIdx.x;
-                const uint32_t k = i < ns ? ~L[i] : 0u;
-                const bool in = i < ns && (k & mask) == prefix;
-                const uint32_t dg = (k >> shift) & 255u;
-                const unsigned act = __ballot_sync(PB_FULL, in);
-                if (!act) continue;
-                const uint32_t d0 = __shfl_sync(PB_FULL, dg, __ffs(act) - 1);
-                if (__all_sync(PB_FULL, !in || dg == d0)) {
-                    if (ln == 0) hist[wv][d0] += __popc(act);  // (this warp's own histogram: no atomic needed)
-                } else if (in) atomicAdd(&hist[wv][dg], 1);
-                __syncwarp();
+            for (int i0 = 0; i0 < ns; i0 += blockDim.x * 8) {  // 8 independent loads per thread, then the histogram updates
+                uint32_t kk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int i = i0 + j * (int)blockDim.x + (int)threadIdx.x;
+                    kk[j] = i < ns ? ~L[i] : 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int i = i0 + j * (int)blockDim.x + (int)threadIdx.x;
+                    const uint32_t k = kk[j];
+                    const bool in = i < ns && (k & mask) == prefix;
+                    const uint32_t dg = (k >> shift) & 255u;
+                    const unsigned act = __ballot_sync(PB_FULL, in);
+                    if (!act) continue;
+                    const uint32_t d0 = __shfl_sync(PB_FULL, dg, __ffs(act) - 1);
+                    if (__all_sync(PB_FULL, !in || dg == d0)) {
+                        if (ln == 0) hist[wv][d0] += __popc(act);  // (this warp's own histogram: no atomic needed)
+                    } else if (in) atomicAdd(&hist[wv][dg], 1);
+                    __syncwarp();
+                }
             }
             __syncthreads();
             if (threadIdx.x < 256) {
@@ -273,14 +282,25 @@ k_select_u32(const uint32_t *__restrict__ sel_keys, const int *__restrict__ sel_
     if (threadIdx.x == 0) fill_s = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    for (int base = 0; base < nf; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        const bool keep = i < nf && F[i] >= thr;
-        const unsigned bal = __ballot_sync(PB_FULL, keep);
-        int off = 0;
-        if (lane == 0 && bal) off = atomicAdd(&fill_s, __popc(bal));
-        off = __shfl_sync(PB_FULL, off, 0);
-        if (keep) cout[off + __popc(bal & ((1u << lane) - 1u))] = cin[i];
+    for (int base = 0; base < nf; base += blockDim.x * 8) {
+        uint32_t fv[8], cv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = base + j * (int)blockDim.x + (int)threadIdx.x;
+            fv[j] = i < nf ? F[i] : 0u;
+            cv[j] = i < nf ? cin[i] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = base + j * (int)blockDim.x + (int)threadIdx.x;
+            const bool keep = i < nf && fv[j] >= thr;
+            const unsigned bal = __ballot_sync(PB_FULL, keep);
+            if (!bal) continue;
+            int off = 0;
+            if (lane == 0) off = atomicAdd(&fill_s, __popc(bal));
+            off = __shfl_sync(PB_FULL, off, 0);
+            if (keep) cout[off + __popc(bal & ((1u << lane) - 1u))] = cv[j];
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) out_n[b] = fill_s;

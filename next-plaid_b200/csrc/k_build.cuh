@@ -191,12 +191,15 @@ __global__ void k_gather_rows(const float *__restrict__ X, const long long *__re
 // ==========================================================================================
 // tcgen05 certified filter for nearest-centroid assignment (index-build path).
 //
-// The exact kernel above spends 128 fp32 FMAs per (token, centroid) pair.  Here a bf16 UMMA
-// (tcgen05.mma, fp32 accumulators in TMEM) scores every pair and the epilogue keeps the 4 best
-// centroids per token.  |s_tc - s_exact| <= eps = (2^-7 + 2^-16) * |x| * max|c| + 1e-5 (two bf16
-// roundings per product, Cauchy-Schwarz, fp32 accumulation slack), so if the 4th best tensor-core score
-// is more than 2*eps below the best, the true argmax is among the first three; those are re-scored in
-// the pinned fp32 order and ranked with the reference's tie rule.  Tokens that cannot be certified
+// The exact kernel above spends 128 fp32 FMAs per (token, centroid) pair.  Here an fp16 UMMA
+// (tcgen05.mma.kind::f16, fp32 accumulators in TMEM) scores every pair and the epilogue keeps the 4 best
+// centroids per token.  |s_tc - s_exact| <= eps = (2^-10 + 2^-22) |x| max|c| + 2^-24 sqrt(dim) (|x| + max|c|) + 1e-5
+// (two fp16 roundings per product, Cauchy-Schwarz; the absolute spacing of fp16 subnormals; fp32 accumulation
+// slack), so if the 4th best tensor-core score is more than 2*eps below the best, the true argmax is among the
+// first three; those are re-scored in the pinned fp32 order and ranked with the reference's tie rule.  (bf16
+// operands, round 1: eps = 2^-7 |x| max|c| -- on k-means centroids of real data, where a token has several
+// centroids within 0.01 of its best, nearly every token failed the certificate: 99.98 % exact fallback on the
+// clustered benchmark corpus.  fp16 narrows the band 8x; values past the fp16 range become inf and are flagged.)  Tokens that cannot be certified
 // (near ties, non-finite values) go through k_assign.  The result is therefore bit-identical to
 // compress_into_codes_cpu while ~98 % of the arithmetic runs on the tensor cores.
 //
@@ -268,7 +271,8 @@ PB_DEV void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// f32 rows -> bf16 (round to nearest even) in UMMA tile order + the L2 norm of every row.
+// f32 rows -> fp16 (round to nearest even; the array type says bf16 for history, the bits are fp16) in UMMA tile order
+// + the L2 norm of every row.
 // Tile order: blocks of 128 rows, each block stored exactly as the kernel wants it in shared memory --
 // K-major canonical no-swizzle layout, byte (kc*16 + r/8)*128 + (r%8)*16 + 2*e for row r, 16-byte K chunk
 // kc, element e -- so one cp.async.bulk (TMA 1-D copy) moves a whole operand tile.  The array is padded
@@ -285,7 +289,7 @@ __global__ void k_rows_to_bf16(const float *__restrict__ X, long long n, int dim
         for (int j = lane; j < dim; j += 32) {
             const float v = X[(size_t)r * dim + j];
             const int kc = j >> 3, e = j & 7;
-            Xb[tbase + (size_t)(kc * 16 + (rr >> 3)) * 64 + (rr & 7) * 8 + e] = __float2bfloat16_rn(v);
+            reinterpret_cast<__half *>(Xb)[tbase + (size_t)(kc * 16 + (rr >> 3)) * 64 + (rr & 7) * 8 + e] = __float2half_rn(v);
             p = fmaf(v, v, p);
         }
         for (int m = 16; m >= 1; m >>= 1) p += __shfl_xor_sync(PB_FULL, p, m);
@@ -358,10 +362,9 @@ k_assign_tc(const __nv_bfloat16 *__restrict__ Xb, long long n, const __nv_bfloat
         }
     } else if (w == 9) {
         // ---------------- MMA issuer ----------------
-        // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1,
-        // b=bf16 [10,13)=1, both K-major, N>>3 [17,23), M>>4 [24,29)
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PB_TC_N >> 3) << 17) |
-                               ((uint32_t)(PB_TC_M >> 4) << 24);
+        // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=f16 [7,10)=0,
+        // b=f16 [10,13)=0, both K-major, N>>3 [17,23), M>>4 [24,29)
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(PB_TC_N >> 3) << 17) | ((uint32_t)(PB_TC_M >> 4) << 24);
         mbar_wait(abar, 0);  // token tiles landed
         for (long long t = 0; t < n_tiles; ++t) {
             const int st = (int)(t % PB_TC_STAGES), acc = (int)(t & 1);
@@ -447,7 +450,8 @@ __global__ void k_assign_certify(const float *__restrict__ X, long long n, int d
         const float4 s = reinterpret_cast<const float4 *>(top_s)[t];
         const uint4 id = reinterpret_cast<const uint4 *>(top_i)[t];
         const float xn = xnorm[t];
-        const float eps = 0.00782776f * xn * cmax + 1e-5f;  // (2^-7 + 2^-16) |x| max|c| + accumulation slack (bf16 unit roundoff 2^-8, twice)
+        // (2^-10 + 2^-22) |x| max|c| (fp16 unit roundoff 2^-11, twice) + subnormal spacing + accumulation slack
+        const float eps = 0.00097680f * xn * cmax + 5.9604645e-8f * sqrtf((float)dim) * (xn + cmax) + 1e-5f;
         // certified iff everything is finite, four candidates exist and the 4th is out of the band
         bool ok = c_finite && xn < 1e18f && (s.x > -1e30f) && (s.x < 1e30f) && id.w != 0xffffffffu && (s.w < s.x - 2.0f * eps);
         if (ok) {

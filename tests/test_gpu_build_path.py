@@ -113,7 +113,7 @@ def test_gpu_built_index_serves_searches(oracle, npb):
 
 
 def test_tensor_core_filter_is_exact_on_hard_inputs(oracle, npb):
-    # near ties inside the bf16 error band, duplicated centroids, non-unit norms and a NaN token:
+    # near ties inside the fp16 error band, duplicated centroids, non-unit norms and a NaN token:
     # whatever the tcgen05 shortlist cannot certify must fall back to the exact kernel
     rng = np.random.default_rng(7)
     K, dim = 2048, 128
@@ -237,7 +237,7 @@ def test_data_parallel_kmeans_over_an_in_process_group(oracle, npb):
 
 
 def test_kmeans_on_the_tensor_cores_matches_the_fp32_assignment_statistically(oracle, npb, monkeypatch):
-    # dims 64/96/128 with K >= 256: the Lloyd assignment step runs as the bf16 tcgen05 GEMM with the -|c|^2/2 bias in
+    # dims 64/96/128 with K >= 256: the Lloyd assignment step runs as the fp16 tcgen05 GEMM with the -|c|^2/2 bias in
     # its epilogue (k_assign_tc<., true>); PB_KMEANS_EXACT=1 keeps the fp32 kernel.  Same seed -> same start; bf16
     # rounding may move points that sit between two centroids, the clustering quality must not change.
     docs = oracle.synthetic_corpus(1500, 32, dim=128, seed=8)
