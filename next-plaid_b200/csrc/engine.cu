@@ -353,6 +353,7 @@ struct pb_index {
     bool filter_v1 = false;    // PB_FILTER_V1=1: always the decompressing filter k_exact_tc (A/B measurement)
     bool pair_exact = true;    // exact stage on the (token, query token) pairs that can hold a maximum (PB_PAIR_EXACT=0: k_exact)
     int ws_grid = 8;           // k_maxsim_tc CTAs per SM across the batch (PB_WS_GRID)
+    int ws_grid2 = 2;          // the same for its pass 2 over the filter's survivors (PB_WS_GRID2)
     int lanes = 1;             // slices of a batch searched concurrently, each on its own stream (pb_set_lanes / PB_LANES; 1 = off)
     std::mutex lane_mu;        // one laned call at a time per handle (a second concurrent caller runs un-laned)
     std::vector<std::unique_ptr<LaneWorker>> lane_workers;
@@ -636,6 +637,7 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_FILTER_V1")) ix->filter_v1 = atoi(e) != 0;
         if (const char *e = getenv("PB_PAIR_EXACT")) ix->pair_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_WS_GRID")) ix->ws_grid = std::max(1, atoi(e));
+        if (const char *e = getenv("PB_WS_GRID2")) ix->ws_grid2 = std::max(1, atoi(e));
         if (const char *e = getenv("PB_LANES")) ix->lanes = std::min(8, std::max(1, atoi(e)));
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
         if (const char *e = getenv("PB_K1_TC_DIAG")) ix->k1_diag = atoi(e) != 0;
@@ -1059,12 +1061,14 @@ static size_t smem_maxsim_tc(int dim, int packed, int nqt) {
 static pb_status launch_maxsim_tc(pb_index *ix, Workspace &ws, const KeptView &in, int B, int QS, int Mcap, long long max_tokens,
                                   int nq_max, uint32_t *keys, const uint32_t *src_rank, float band_unit, u64 *pairs,
                                   int *n_pairs, int pair_cap, int kev) {
+    const bool emit = pairs != nullptr;
+    // pass 1 (all kept docs): ws_grid CTAs per SM over the batch; pass 2 (the survivors, ~1/10 of the tokens): one wave of
+    // 2 CTAs per SM, so that a CTA's chunk range stays long against the fill and drain of its pipeline
     long long chunks = (max_tokens + 127) / 128;
-    long long want = std::max<long long>(1, ((long long)ix->sm_count * ix->ws_grid + B - 1) / B);
+    long long want = std::max<long long>(1, ((long long)ix->sm_count * (emit ? ix->ws_grid2 : ix->ws_grid) + B - 1) / B);
     int gx = (int)std::max<long long>(1, std::min<long long>(chunks, want));
     const int nqt = nq_max <= 32 ? 32 : 64;
     const size_t sm = smem_maxsim_tc(ix->dim, ix->packed, nqt);
-    const bool emit = pairs != nullptr;
     CKS(ws.gbase.ensure((size_t)B * Mcap * 8));
     k_doc_gbase<<<dim3((Mcap + 255) / 256, B), 256, 0, ws.stream>>>(in.kept, in.nkept, in.tokp, ix->doc_off.as<long long>(), Mcap,
                                                                     ws.gbase.as<long long>());

@@ -18,6 +18,9 @@ VARIANTS = [
     ("list-scan probe (exact a2)", {"PB_PROBE16": "0", "PB_K1_TC": "0"}),
     ("decompressing filter (PB_FILTER_V1)", {"PB_FILTER_V1": "1"}),
     ("token-form exact stage (PB_PAIR_EXACT=0)", {"PB_PAIR_EXACT": "0"}),
+    ("pass-2 grid 1", {"PB_WS_GRID2": "1"}),
+    ("pass-2 grid 4", {"PB_WS_GRID2": "4"}),
+    ("pass-2 grid 8", {"PB_WS_GRID2": "8"}),
     ("ws grid 4", {"PB_WS_GRID": "4"}),
     ("ws grid 16", {"PB_WS_GRID": "16"}),
     ("ws grid 32", {"PB_WS_GRID": "32"}),
