@@ -353,7 +353,7 @@ struct pb_index {
     bool filter_v1 = false;    // PB_FILTER_V1=1: always the decompressing filter k_exact_tc (A/B measurement)
     bool pair_exact = true;    // exact stage on the (token, query token) pairs that can hold a maximum (PB_PAIR_EXACT=0: k_exact)
     int ws_grid = 8;           // k_maxsim_tc CTAs per SM across the batch (PB_WS_GRID)
-    int ws_grid2 = 2;          // the same for its pass 2 over the filter's survivors (PB_WS_GRID2)
+    int ws_grid2 = 8;          // the same for its pass 2 over the filter's survivors (PB_WS_GRID2; 1: 0.54, 2: 0.43, 4 and 8: 0.40 ms)
     int lanes = 1;             // slices of a batch searched concurrently, each on its own stream (pb_set_lanes / PB_LANES; 1 = off)
     std::mutex lane_mu;        // one laned call at a time per handle (a second concurrent caller runs un-laned)
     std::vector<std::unique_ptr<LaneWorker>> lane_workers;
@@ -1062,8 +1062,8 @@ static pb_status launch_maxsim_tc(pb_index *ix, Workspace &ws, const KeptView &i
                                   int nq_max, uint32_t *keys, const uint32_t *src_rank, float band_unit, u64 *pairs,
                                   int *n_pairs, int pair_cap, int kev) {
     const bool emit = pairs != nullptr;
-    // pass 1 (all kept docs): ws_grid CTAs per SM over the batch; pass 2 (the survivors, ~1/10 of the tokens): one wave of
-    // 2 CTAs per SM, so that a CTA's chunk range stays long against the fill and drain of its pipeline
+    // CTAs per SM over the batch: ws_grid for pass 1 (all kept docs), ws_grid2 for pass 2 (the survivors, ~1/10 of the
+    // tokens; fewer, longer CTAs measured slower: the pass is latency-bound and wants the parallelism)
     long long chunks = (max_tokens + 127) / 128;
     long long want = std::max<long long>(1, ((long long)ix->sm_count * (emit ? ix->ws_grid2 : ix->ws_grid) + B - 1) / B);
     int gx = (int)std::max<long long>(1, std::min<long long>(chunks, want));
