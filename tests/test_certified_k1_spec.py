@@ -4,6 +4,8 @@ score), so a code moves by at most E = 1 and
   * probe:    an entry of a token's exact top n has code~ >= tau~ - (2E + 1)   (tau~ = n-th largest chunk maximum)
   * a5:       a doc of the exact top M has L~ >= (M-th largest L~) - W,  W = nq (1.004 + 2 err) + nq^2/256 + 4
   * re-check: the code attaining a doc's exact per-token maximum has code~ >= (largest code~ of the doc) - (2E + 1)
+and of the two certificates of the MaxSim stage (k_maxsim_tc.cuh): the docs that can reach the top_k, and inside them the
+(token, query token) pairs that can hold a per-token maximum.
 Pure numpy, adversarial perturbations of the full err; the GPU tests run the kernels themselves."""
 import numpy as np
 import pytest
@@ -95,3 +97,48 @@ def test_recheck_margin_contains_the_exact_argmax(seed):
             delta[star] = -eps1
             ct = _codes(e + delta, R, scale)
             assert ct[star] >= ct.max() - 3, (seed, q)
+
+
+# ------------------------------------------------------------------------------------------
+# The MaxSim stage (k_maxsim_tc.cuh): every similarity estimate is within eps of the exact one.
+#   * pass 1: a doc of the exact top_k has estimate sum >= (top_k-th largest estimate sum) - 2 nq eps
+#   * pass 2: the token holding a (doc, query token) exact maximum has estimate >= (largest estimate of the pair) - 2 eps,
+#             so the exact MaxSim of a doc is the sum over q of the maxima of the exact sims over the listed tokens only
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("mode", ["random", "adversarial"])
+def test_maxsim_filter_and_pair_band_are_supersets(seed, mode):
+    rng = np.random.default_rng(100 + seed)
+    n_docs, nq, top_k, eps = 200, 12, 10, 2e-3
+    lens = rng.integers(1, 40, n_docs)
+    sims = [rng.uniform(-1, 1, (l, nq)).astype(np.float64) for l in lens]
+    for d in range(0, n_docs, 7):                     # near ties inside a doc and between docs
+        sims[d][-1] = sims[d][0] + rng.uniform(-eps, eps, nq) * 0.5
+        if d + 1 < n_docs:
+            sims[d + 1] = sims[d][: max(1, min(len(sims[d]), lens[d + 1]))].copy()
+    exact = np.array([s.max(0).sum() for s in sims])
+    if mode == "random":
+        est = [s + rng.uniform(-eps, eps, s.shape) for s in sims]
+    else:   # push every per-token winner down and everything else up by the full bound
+        est = []
+        for s in sims:
+            e = s + eps
+            e[s.argmax(0), np.arange(nq)] = s.max(0) - eps
+            est.append(e)
+    est_sum = np.array([e.max(0).sum() for e in est])
+    # pass 1
+    order = np.argsort(-exact, kind="stable")
+    true_top = set(order[:top_k].tolist())
+    tau = np.sort(est_sum)[::-1][top_k - 1]
+    survivors = set(np.nonzero(est_sum >= tau - 2 * nq * eps - 1e-12)[0].tolist())
+    assert true_top <= survivors
+    # pass 2 on the survivors: only listed (token, q) pairs are evaluated exactly
+    n_pairs = 0
+    for d in survivors:
+        listed = est[d] >= est[d].max(0)[None, :] - 2 * eps - 1e-12
+        n_pairs += int(listed.sum())
+        assert listed.any(0).all()
+        got = np.where(listed, sims[d], -np.inf).max(0).sum()
+        assert got == exact[d]
+    if mode == "random":    # the band is narrow: about one pair per (doc, q), not every token
+        assert n_pairs < 2.5 * nq * len(survivors)

@@ -21,6 +21,8 @@ VARIANTS = [
     ("pass-2 grid 1", {"PB_WS_GRID2": "1"}),
     ("pass-2 grid 4", {"PB_WS_GRID2": "4"}),
     ("pass-2 grid 8", {"PB_WS_GRID2": "8"}),
+    ("pass-2 grid 16", {"PB_WS_GRID2": "16"}),
+    ("pass-2 grid 32", {"PB_WS_GRID2": "32"}),
     ("ws grid 4", {"PB_WS_GRID": "4"}),
     ("ws grid 16", {"PB_WS_GRID": "16"}),
     ("ws grid 32", {"PB_WS_GRID": "32"}),
