@@ -353,7 +353,6 @@ struct pb_index {
     bool filter_v1 = false;    // PB_FILTER_V1=1: always the decompressing filter k_exact_tc (A/B measurement)
     bool pair_exact = true;    // exact stage on the (token, query token) pairs that can hold a maximum (PB_PAIR_EXACT=0: k_exact)
     int ws_grid = 8;           // k_maxsim_tc CTAs per SM across the batch (PB_WS_GRID)
-    bool k1_early = false;     // k_scores16_tc: both TMEM loads in flight, accumulator released before the stores (PB_K1_EARLY)
     int ws_grid2 = 8;          // the same for its pass 2 over the filter's survivors (PB_WS_GRID2; 1: 0.54, 2: 0.43, 4 and 8: 0.40 ms)
     int lanes = 1;             // slices of a batch searched concurrently, each on its own stream (pb_set_lanes / PB_LANES; 1 = off)
     std::mutex lane_mu;        // one laned call at a time per handle (a second concurrent caller runs un-laned)
@@ -638,7 +637,6 @@ pb_status pb_index_finalize(pb_index *ix) {
         if (const char *e = getenv("PB_FILTER_V1")) ix->filter_v1 = atoi(e) != 0;
         if (const char *e = getenv("PB_PAIR_EXACT")) ix->pair_exact = atoi(e) != 0;
         if (const char *e = getenv("PB_WS_GRID")) ix->ws_grid = std::max(1, atoi(e));
-        if (const char *e = getenv("PB_K1_EARLY")) ix->k1_early = atoi(e) != 0;
         if (const char *e = getenv("PB_WS_GRID2")) ix->ws_grid2 = std::max(1, atoi(e));
         if (const char *e = getenv("PB_LANES")) ix->lanes = std::min(8, std::max(1, atoi(e)));
         if (const char *e = getenv("PB_PROBE16")) ix->probe16 = atoi(e) != 0;
@@ -834,8 +832,7 @@ static pb_status launch_k1_table(pb_index *ix, Workspace &ws, int B, int QS, uns
         KEV_BEGIN(PB_KERNEL_SCORES);                                                                                   \
         kern<<<tiles, 320, sm, ws.stream>>>(ix->cent_h16t.as<__half>(), ix->cent_l16t.as<__half>(), ix->K,             \
                                             ws.Qh16t.as<__half>(), ws.Ql16t.as<__half>(), n_groups, B, QS,             \
-                                            ws.qoff.as<int>(), ws.qrange_tc.as<float2>(), table, flags,               \
-                                            ix->k1_early ? 1 : 0);                                                     \
+                                            ws.qoff.as<int>(), ws.qrange_tc.as<float2>(), table, flags);               \
         KEV_END(PB_KERNEL_SCORES);                                                                                     \
     }
     switch (ix->dim) {

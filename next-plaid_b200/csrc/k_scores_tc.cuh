@@ -82,57 +82,11 @@ __global__ void k_query_range_tc(const float2 *__restrict__ qrange, const int *_
     qrange_tc[b] = make_float2(rg.x, ldexpf(rg.y, -(qexp[b] + kc)));
 }
 
-// tcgen05.ld without the wait (several loads in flight; tc_ld_wait, then tc_pin32 ties the registers to the wait)
-PB_DEV void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-PB_DEV void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-PB_DEV void tc_pin32(uint32_t (&r)[32]) {
-    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
-}
-
-// epilogue of k_scores16_tc for 32 accumulator columns of one centroid row: 16-bit codes, 16-byte runs of ST16[b][c][.]
-PB_DEV void scores16_emit(const uint32_t (&rr)[32], int row_base, long long c, long long K, int B, int QS,
-                          const float2 *__restrict__ qrange_tc, unsigned short *__restrict__ ST16, int *__restrict__ qflag) {
-#pragma unroll
-    for (int sub = 0; sub < 4; ++sub) {
-        const int row0 = row_base + sub * 8;  // 8 query rows of one query (QS % 8 == 0)
-        const int b = row0 / QS, q = row0 - b * QS;
-        if (b >= B || c >= K) continue;
-        const float2 rg = qrange_tc[b];  // (R*scale, scale / 2^(kq+kc))
-        uint32_t cd[8];
-        bool ok = true;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            // code = floor(x) clamped to [0, 65535]; x outside [+0, 65536) (NaN, -0 included) raises the
-            // query's flag and the sub-batch is redone on the exact path, so only in-range codes matter.
-            // Padding rows hold a zero accumulator: x = R*scale, in range.
-            const float x = __fmaf_rn(__uint_as_float(rr[sub * 8 + i]), rg.y, rg.x);
-            ok &= __float_as_uint(x) < 0x47800000u;
-            cd[i] = min(__float2uint_rd(x), 65535u);
-        }
-        if (!ok) atomicOr(&qflag[b], 1);
-        *reinterpret_cast<uint4 *>(ST16 + ((size_t)b * K + c) * QS + q) =
-            make_uint4(cd[0] | (cd[1] << 16), cd[2] | (cd[3] << 16), cd[4] | (cd[5] << 16), cd[6] | (cd[7] << 16));
-    }
-}
-
 template <int DIM>
 __global__ void __launch_bounds__(320, 1)
 k_scores16_tc(const __half *__restrict__ Ch, const __half *__restrict__ Cl, long long K, const __half *__restrict__ Qh,
               const __half *__restrict__ Ql, int n_groups, int B, int QS, const int *__restrict__ q_off,
-              const float2 *__restrict__ qrange_tc, unsigned short *__restrict__ ST16, int *__restrict__ qflag, int early) {
+              const float2 *__restrict__ qrange_tc, unsigned short *__restrict__ ST16, int *__restrict__ qflag) {
     extern __shared__ __align__(128) unsigned char smem_k1[];
     constexpr int KSTEPS = DIM / 16;
     constexpr uint32_t T_BYTES = 128 * DIM * 2;  // one 128-row fp16 tile
@@ -210,29 +164,33 @@ k_scores16_tc(const __half *__restrict__ Ch, const __half *__restrict__ Cl, long
             const int acc = g & 1;
             mbar_wait(&tfull[acc], (uint32_t)((g >> 1) & 1));
             tc_fence_after();
-            const uint32_t t0 = tmem_base + ((uint32_t)(32 * lg) << 16) + acc * 128 + 2 * ch * 32;
-            if (early) {
-                // both 32-column loads in flight, one wait, and the accumulator goes back to the MMA warp before the
-                // conversion and the stores (the MMAs of group g + 2 then run under this group's epilogue)
-                uint32_t ra[32], rb[32];
-                tc_ld32_issue(t0, ra);
-                tc_ld32_issue(t0 + 32, rb);
-                tc_ld_wait();
-                tc_pin32(ra);
-                tc_pin32(rb);
-                tc_fence_before();
-                mbar_arrive(&tempty[acc]);
-                scores16_emit(ra, g * 128 + 2 * ch * 32, c, K, B, QS, qrange_tc, ST16, qflag);
-                scores16_emit(rb, g * 128 + 2 * ch * 32 + 32, c, K, B, QS, qrange_tc, ST16, qflag);
-                continue;
-            }
-#pragma unroll 1
             // (Both 32-column loads in flight and the accumulator handed back before the conversion and the stores was
             // measured: 0.349 against 0.351 ms -- the TMEM read latency is not what bounds the epilogue.)
+#pragma unroll 1
             for (int cb = 2 * ch; cb < 2 * ch + 2; ++cb) {
                 uint32_t rr[32];
                 tc_ld32(tmem_base + ((uint32_t)(32 * lg) << 16) + acc * 128 + cb * 32, rr);
-                scores16_emit(rr, g * 128 + cb * 32, c, K, B, QS, qrange_tc, ST16, qflag);
+#pragma unroll
+                for (int sub = 0; sub < 4; ++sub) {
+                    const int row0 = g * 128 + cb * 32 + sub * 8;  // 8 query rows of one query (QS % 8 == 0)
+                    const int b = row0 / QS, q = row0 - b * QS;
+                    if (b >= B || c >= K) continue;
+                    const float2 rg = qrange_tc[b];  // (R*scale, scale / 2^(kq+kc))
+                    uint32_t cd[8];
+                    bool ok = true;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        // code = floor(x) clamped to [0, 65535]; x outside [+0, 65536) (NaN, -0 included) raises the
+                        // query's flag and the sub-batch is redone on the exact path, so only in-range codes matter.
+                        // Padding rows hold a zero accumulator: x = R*scale, in range.
+                        const float x = __fmaf_rn(__uint_as_float(rr[sub * 8 + i]), rg.y, rg.x);
+                        ok &= __float_as_uint(x) < 0x47800000u;
+                        cd[i] = min(__float2uint_rd(x), 65535u);
+                    }
+                    if (!ok) atomicOr(&qflag[b], 1);
+                    *reinterpret_cast<uint4 *>(ST16 + ((size_t)b * K + c) * QS + q) =
+                        make_uint4(cd[0] | (cd[1] << 16), cd[2] | (cd[3] << 16), cd[4] | (cd[5] << 16), cd[6] | (cd[7] << 16));
+                }
             }
             tc_fence_before();
             mbar_arrive(&tempty[acc]);

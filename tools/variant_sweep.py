@@ -26,8 +26,6 @@ VARIANTS = [
     ("ws grid 4", {"PB_WS_GRID": "4"}),
     ("ws grid 16", {"PB_WS_GRID": "16"}),
     ("ws grid 32", {"PB_WS_GRID": "32"}),
-    ("a2 early accumulator release (PB_K1_EARLY=1)", {"PB_K1_EARLY": "1"}),
-    ("a2 late accumulator release (PB_K1_EARLY=0)", {"PB_K1_EARLY": "0"}),
     ("lanes 2 (PB_LANES=2)", {"PB_LANES": "2"}),
     ("lanes 3", {"PB_LANES": "3"}),
     ("lanes 4", {"PB_LANES": "4"}),
